@@ -1,0 +1,147 @@
+/* soilmachine_b200 -- C ABI of the B200-native particle/terrain hot path.
+ *
+ * The reference (weigert/SoilMachine) has no plugin or FFI layer: its frame loop
+ * (SoilMachine.cpp:283-329) calls WaterParticle/WindParticle::move/interact
+ * (source/particle/water.h:43-121, wind.h:54-136), Particle::cascade (particle.h:24-101) and the
+ * Layermap column operations (source/layermap.h:230-439) directly.  This header is the boundary a
+ * binding of that loop would call instead; include/soilmachine/ holds the C++ facade that exposes
+ * the reference's own class names on top of it.  Every entry point cites what it replaces.
+ *
+ * Conventions: plain pointers and sizes, caller-owned host buffers, context-owned device memory,
+ * int status (0 = ok), sm_last_error() for the message, never throws, one caller thread per
+ * context.  Cell order of every per-cell array is x*dimy + y (layermap.h:151) unless stated;
+ * frequency/track arrays use y*dimx + x (water.h:53,349).
+ */
+#ifndef SOILMACHINE_B200_H
+#define SOILMACHINE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SM_OK 0
+#define SM_ERR_INVALID 1      /* bad argument */
+#define SM_ERR_CUDA 2         /* CUDA runtime error (message in sm_last_error) */
+#define SM_ERR_POOL 3         /* section pool exhausted: the reference prints and drops mass
+                                 (layermap.h:92-95,232-234); here the drop is counted and reported */
+#define SM_ERR_REACH 4        /* a particle step left its conflict box (internal invariant) */
+#define SM_ERR_NOGPU 5        /* no CUDA device: there is no CPU fallback */
+
+#define SM_MAX_SOILS 64
+
+typedef struct sm_context sm_context;
+
+/* Numeric mirror of SurfParam (surface.h:11-39).  Index in the table = SurfType; 0 is "Air"
+ * (surface.h:41-57). */
+typedef struct sm_soil {
+  int32_t transports, erodes, cascades, abrades;
+  float density, porosity, solubility, equrate, friction, erosionrate, maxdiff, settling,
+      suspension, abrasion;
+} sm_soil;
+
+/* Numeric mirror of SurfLayer (surface.h:65-101): value = max(min, bias + scale*fbm). */
+typedef struct sm_layer {
+  int32_t type;
+  float min, bias, scale, octaves, lacunarity, gain, frequency;
+} sm_layer;
+
+typedef struct sm_config {
+  int32_t dimx, dimy;       /* SIZEX, SIZEY (SoilMachine.cpp:9-10) */
+  int32_t scale;            /* SCALE (SoilMachine.cpp:11) */
+  int32_t device;           /* CUDA device ordinal */
+  int64_t pool_capacity;    /* buried-section pool slots (POOLSIZE, SoilMachine.cpp:16); 0 = auto */
+  int32_t max_particles;    /* largest batch a *_run call will be given; 0 = 262144 */
+  int32_t flags;            /* reserved, 0 */
+} sm_config;
+
+/* Per-call counters (all accumulated over the call). */
+typedef struct sm_stats {
+  int64_t steps;       /* particle-steps: move() true and interact() ran */
+  int64_t sweeps;      /* lockstep sweeps executed */
+  int64_t exit_oob;    /* water: left the map (water.h:65-69) | wind: move() false (wind.h:56,83-88) */
+  int64_t exit_evap;   /* water: volume <= minvol (water.h:119) */
+  int64_t exit_stall;  /* water: no motion (water.h:56-57), the reference's flood candidates */
+  int64_t pool_drops;  /* sections dropped because the pool was exhausted */
+  int64_t alive;       /* particles still alive when the call returned (max_sweeps reached) */
+  double device_ms;    /* CUDA-event time of the sweep kernel(s) of this call */
+} sm_stats;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int sm_create(const sm_config* cfg, sm_context** out);
+void sm_destroy(sm_context* ctx);
+const char* sm_last_error(const sm_context* ctx);   /* ctx may be NULL: last create error */
+int sm_sync(sm_context* ctx);
+
+/* ---- tables: soils[] / layers (surface.h:41-57,104; io.h:7-230 fills them) -------------------- */
+int sm_set_soils(sm_context* ctx, const sm_soil* soils, int32_t n);
+
+/* ---- terrain -------------------------------------------------------------------------------- */
+/* Layermap::initialize (layermap.h:163-216): for each layer, for each cell, add(noise section).
+ * Bit-identical to the reference's FastNoiseLite OpenSimplex2/FBm path (FastNoiseLite.h:321-340,
+ * 686-727,865-885,1053-1150; noise seed fixed at 1337, SEED only shifts z). */
+int sm_initialize(sm_context* ctx, int32_t seed, const sm_layer* layers, int32_t nlayers);
+
+/* Columns as bottom->top CSR; floor is recomputed as the running sum exactly as add() does
+ * (layermap.h:304).  saturation may be NULL (zeros). */
+int sm_upload_columns(sm_context* ctx, const int64_t* offsets, const int32_t* type,
+                      const double* size, const double* saturation);
+int sm_section_count(sm_context* ctx, int64_t* n);
+int sm_download_columns(sm_context* ctx, int64_t capacity, int64_t* offsets, int32_t* type,
+                        double* size, double* floor, double* saturation);
+int sm_download_height(sm_context* ctx, double* height);     /* Layermap::height(ivec2), layermap.h:422 */
+int sm_download_surface(sm_context* ctx, int32_t* surface);  /* Layermap::surface, layermap.h:417 */
+int sm_height_sum(sm_context* ctx, double* sum);             /* deterministic tree sum on device */
+
+/* WaterParticle::frequency/track, WindParticle::frequency (water.h:345-346, wind.h:48).
+ * Any pointer may be NULL. */
+int sm_get_frequency(sm_context* ctx, float* water_frequency, float* water_track, float* wind_frequency);
+int sm_set_frequency(sm_context* ctx, const float* water_frequency, const float* water_track,
+                     const float* wind_frequency);
+/* mapfrequency + resetfrequency (water.h:353-365; SoilMachine.cpp:313-320) */
+int sm_frequency_update(sm_context* ctx);
+
+/* ---- single-cell operations (what the facade's legacy Layermap calls forward to) -------------- */
+int sm_cell_add(sm_context* ctx, int32_t x, int32_t y, double size, int32_t type); /* layermap.h:230 */
+int sm_cell_remove(sm_context* ctx, int32_t x, int32_t y, double h, double* leftover); /* :310 */
+int sm_cell_cascade(sm_context* ctx, float x, float y, int32_t transferloop);  /* particle.h:24 */
+int sm_cell_query(sm_context* ctx, int32_t x, int32_t y, double* height, int32_t* surface,
+                  float* normal3);  /* layermap.h:422,417,341 */
+int sm_height_bilinear(sm_context* ctx, float x, float y, double* height); /* layermap.h:427 */
+
+/* ---- the hot path --------------------------------------------------------------------------- */
+/* One batch of n particles run to completion in lockstep sweeps: in every sweep each live particle,
+ * in ascending index order, executes move() && interact().  Replaces the loop
+ * SoilMachine.cpp:288-298 (water, flood excluded) / 304-307 (wind).  spawn_xy = n (x,y) pairs,
+ * the positions the ctor draws (water.h:13, wind.h:15).  max_sweeps <= 0: until all are dead. */
+int sm_water_run(sm_context* ctx, int32_t n, const float* spawn_xy, int32_t max_sweeps, sm_stats* stats);
+int sm_wind_run(sm_context* ctx, int32_t n, const float* spawn_xy, int32_t max_sweeps, sm_stats* stats);
+
+/* Same, spawn list already in device memory (no host<->device copy, no sync; stats fetched by
+ * sm_last_stats after sm_sync). */
+int sm_water_run_device(sm_context* ctx, int32_t n, const float* d_spawn_xy, int32_t max_sweeps);
+int sm_wind_run_device(sm_context* ctx, int32_t n, const float* d_spawn_xy, int32_t max_sweeps);
+int sm_last_stats(sm_context* ctx, sm_stats* stats);
+
+/* Stepping interface for parity tests: begin a batch, advance k sweeps, read particle state. */
+int sm_water_begin(sm_context* ctx, int32_t n, const float* spawn_xy);
+int sm_water_sweeps(sm_context* ctx, int32_t k, sm_stats* stats);
+int sm_water_state(sm_context* ctx, float* pos2, float* speed2, double* volume, double* sediment,
+                   int32_t* contains, int32_t* alive);
+int sm_wind_begin(sm_context* ctx, int32_t n, const float* spawn_xy);
+int sm_wind_sweeps(sm_context* ctx, int32_t k, sm_stats* stats);
+int sm_wind_state(sm_context* ctx, float* pos2, float* speed3, double* height, double* sediment,
+                  int32_t* contains, int32_t* alive);
+
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+int sm_launch_count(sm_context* ctx, int64_t* n);
+/* Device pointer helpers so a caller can keep spawn lists resident. */
+int sm_device_alloc(sm_context* ctx, int64_t bytes, void** dptr);
+int sm_device_free(sm_context* ctx, void* dptr);
+int sm_device_upload(sm_context* ctx, void* dptr, const void* host, int64_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

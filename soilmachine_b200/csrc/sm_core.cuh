@@ -1,0 +1,420 @@
+// sm_core.cuh -- column operations and particle-step arithmetic of the hot path.
+//
+// Everything here is written against an "accessor" A that hands out mutable top-of-column
+// records, so the same arithmetic runs (a) inside the sm_100a sweep kernels on records staged in
+// shared memory / read through L2, and (b) on the host inside the facade's single-cell calls.
+// The arithmetic is a type-exact transcription of the reference expressions: every float/double
+// promotion, association order and narrowing is kept, FMA contraction must be OFF
+// (nvcc -fmad=false, gcc -ffp-contract=off) and division / sqrt must be IEEE (nvcc defaults).
+//
+// Reference map:  Layermap::add/remove/height/normal/surface  source/layermap.h:230-439
+//                 Particle::cascade                             source/particle/particle.h:24-101
+//                 WaterParticle::move/interact                  source/particle/water.h:43-121
+//                 WindParticle::move/interact                   source/particle/wind.h:54-136
+//                 GLM semantics (normalize, mix, cross, round)  SURVEY.md section 8c
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define SM_HD __host__ __device__ __forceinline__
+#define SM_HD_NOINLINE __host__ __device__
+#else
+#define SM_HD inline
+#define SM_HD_NOINLINE inline
+#endif
+
+#define SM_NIL 0xFFFFFFFFu
+#define SM_EMPTY 0xFFFFFFFFu   // Sec32::type of an empty column (dat[] == NULL, layermap.h:176)
+#define SM_AIR 0u              // soilmap["Air"] (surface.h:53-57)
+
+// One run of a column ("sec", layermap.h:37-62) as a 32-byte record = one DRAM sector.
+// The TOP section of every cell lives in DevMap::top[x*dimy+y]; buried sections live in the pool
+// and are chained through `below` (the reference's `prev`).
+struct
+#if defined(__CUDACC__)
+    __align__(32)
+#else
+    alignas(32)
+#endif
+        Sec32 {
+  double size;        // run length              (sec::size)
+  double floor;       // cumulative height below (sec::floor)
+  double saturation;  // (sec::saturation) carried, only hydrology changes it
+  uint32_t type;      // SurfType, SM_EMPTY = no section
+  uint32_t below;     // pool slot of the section underneath, SM_NIL = none
+};
+
+// the SurfParam fields the path reads (surface.h:11-39)
+struct SoilDev {
+  float friction, solubility, equrate, erosionrate, maxdiff, settling, suspension, porosity;
+  uint32_t transports, erodes, cascades, abrades;
+};
+
+struct WaterP {  // WaterParticle state that survives a step (water.h:27-41, particle.h:16-18)
+  float px, py, sx, sy;
+  double volume, sediment;
+  uint32_t contains;
+};
+struct WindP {  // WindParticle state (wind.h:29-40)
+  float px, py;
+  float sx, sy, sz;
+  double sediment, height;
+  uint32_t contains;
+};
+
+enum { SM_ALIVE = 0, SM_EXIT_OOB = 1, SM_EXIT_STALL = 2, SM_EXIT_EVAP = 3 };
+
+// ------------------------------------------------------------------------------------------------
+// record-level column operations
+// ------------------------------------------------------------------------------------------------
+SM_HD double rec_height(const Sec32& r) {  // Layermap::height(ivec2), layermap.h:422-425
+  return r.type == SM_EMPTY ? 0.0 : (r.floor + r.size);
+}
+SM_HD uint32_t rec_surface(const Sec32& r) {  // Layermap::surface, layermap.h:417-420
+  return r.type == SM_EMPTY ? 0u : r.type;
+}
+SM_HD void rec_set_empty(Sec32& r) {
+  r.size = 0.0; r.floor = 0.0; r.saturation = 0.0; r.type = SM_EMPTY; r.below = SM_NIL;
+}
+
+// dat[] = E->prev; pool.unget(E)   (layermap.h:318-320, 332-334)
+template <class A> SM_HD void col_pop(A& a, Sec32& r) {
+  uint32_t b = r.below;
+  if (b == SM_NIL) {
+    rec_set_empty(r);
+  } else {
+    r = a.pool_load(b);
+    a.pool_free(b);
+  }
+}
+// E->prev = dat[]; E->floor = height(pos); dat[] = E   (layermap.h:302-305)
+template <class A> SM_HD void col_push(A& a, Sec32& r, double size, uint32_t type, double sat) {
+  uint32_t slot = a.pool_alloc();
+  if (slot == SM_NIL) return;  // pool exhausted: the reference drops the section (layermap.h:92-95,232-234)
+  a.pool_store(slot, r);
+  double fl = r.floor + r.size;
+  r.size = size; r.floor = fl; r.saturation = sat; r.type = type; r.below = slot;
+}
+
+// Layermap::add(pos, E) with E = sec(size,type) carrying `sat`  (layermap.h:230-307)
+template <class A> SM_HD void col_add(A& a, Sec32& r, double size, uint32_t type, double sat = 0.0) {
+  if (size <= 0) return;                       // :237-240
+  if (r.type == SM_EMPTY) {                    // :243-246
+    r.size = size; r.floor = 0.0; r.saturation = sat; r.type = type; r.below = SM_NIL;
+    return;
+  }
+  if (r.type == type) {                        // :249-253
+    r.size += size;
+    return;
+  }
+  if (r.type == SM_AIR) {                      // :258-275  insert under the water section
+    double wsize = r.size, wsat = r.saturation;
+    uint32_t b = r.below;
+    if (b == SM_NIL) rec_set_empty(r);
+    else { r = a.pool_load(b); a.pool_free(b); }
+    // add(pos, E): the section under water is never Air (adjacent equal types merge)
+    if (r.type == SM_EMPTY) {
+      r.size = size; r.floor = 0.0; r.saturation = sat; r.type = type; r.below = SM_NIL;
+    } else if (r.type == type) {
+      r.size += size;
+    } else {
+      col_push(a, r, size, type, sat);
+    }
+    // add(pos, top): the water section goes back on with a recomputed floor (:302-305)
+    if (wsize <= 0) return;
+    if (r.type == SM_AIR) r.size += wsize;    // only reachable when `type` could not be pushed
+    else col_push(a, r, wsize, SM_AIR, wsat);
+    return;
+  }
+  col_push(a, r, size, type, sat);             // :302-305
+}
+
+// Layermap::remove(pos, h) -> leftover   (layermap.h:310-339)
+template <class A> SM_HD double col_remove(A& a, Sec32& r, double h) {
+  if (r.type == SM_EMPTY) return 0.0;          // :313-314
+  if (r.size <= 0.0) {                         // :317-322
+    col_pop(a, r);
+    return 0.0;
+  }
+  if (h <= 0.0) return 0.0;                    // :325-326
+  double diff = h - r.size;                    // :328-329
+  r.size -= h;
+  if (diff >= 0.0) {                           // :331-336
+    col_pop(a, r);
+    return diff;
+  }
+  return 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// queries through the accessor
+// ------------------------------------------------------------------------------------------------
+template <class A> SM_HD double map_height(A& a, int x, int y) { return rec_height(*a.rec(x, y)); }
+
+// Layermap::height(vec2), layermap.h:427-439 (weights cross-wired exactly as upstream)
+template <class A> SM_HD double map_height_bilinear(A& a, float px, float py) {
+  float fx = floorf(px), fy = floorf(py);
+  int ix = (int)fx, iy = (int)fy;
+  float wx = px - fx, wy = py - fy;            // fract = x - floor(x)
+  double h = 0.0;
+  h += (1.0 - wx) * (1.0 - wy) * map_height(a, ix, iy);
+  h += (1.0 - wx) * wy * map_height(a, ix + 1, iy);
+  h += wx * (1.0 - wy) * map_height(a, ix, iy + 1);
+  h += wx * wy * map_height(a, ix + 1, iy + 1);   // wx*wy is a float product
+  return h;
+}
+
+struct sm_f3 { float x, y, z; };
+SM_HD sm_f3 f3_sub(sm_f3 a, sm_f3 b) { return sm_f3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+SM_HD sm_f3 f3_cross(sm_f3 x, sm_f3 y) {
+  return sm_f3{x.y * y.z - y.y * x.z, x.z * y.x - y.z * x.x, x.x * y.y - y.x * x.y};
+}
+
+// Layermap::normal(ivec2), layermap.h:341-377
+template <class A> SM_HD sm_f3 map_normal(A& a, int x, int y) {
+  const int SCALE = a.scale();
+  const int dimx = a.dimx(), dimy = a.dimy();
+  sm_f3 n{0.0f, 0.0f, 0.0f};
+  sm_f3 p{(float)x, (float)(SCALE * map_height(a, x, y)), (float)y};
+  int k = 0;
+  // the four neighbour heights are shared by the quadrants; each is read once
+  float hxm = 0.0f, hxp = 0.0f, hym = 0.0f, hyp = 0.0f;
+  if (x > 0) hxm = (float)(SCALE * map_height(a, x - 1, y));
+  if (x < dimx - 1) hxp = (float)(SCALE * map_height(a, x + 1, y));
+  if (y > 0) hym = (float)(SCALE * map_height(a, x, y - 1));
+  if (y < dimy - 1) hyp = (float)(SCALE * map_height(a, x, y + 1));
+  if (x > 0 && y > 0) {
+    sm_f3 b{(float)(x - 1), hxm, (float)y};
+    sm_f3 c{(float)x, hym, (float)(y - 1)};
+    sm_f3 r = f3_cross(f3_sub(c, p), f3_sub(b, p));
+    n.x += r.x; n.y += r.y; n.z += r.z;
+    k++;
+  }
+  if (x > 0 && y < dimy - 1) {
+    sm_f3 b{(float)(x - 1), hxm, (float)y};
+    sm_f3 c{(float)x, hyp, (float)(y + 1)};
+    sm_f3 r = f3_cross(f3_sub(c, p), f3_sub(b, p));
+    n.x -= r.x; n.y -= r.y; n.z -= r.z;
+    k++;
+  }
+  if (x < dimx - 1 && y > 0) {
+    sm_f3 b{(float)(x + 1), hxp, (float)y};
+    sm_f3 c{(float)x, hym, (float)(y - 1)};
+    sm_f3 r = f3_cross(f3_sub(c, p), f3_sub(b, p));
+    n.x -= r.x; n.y -= r.y; n.z -= r.z;
+    k++;
+  }
+  if (x < dimx - 1 && y < dimy - 1) {
+    sm_f3 b{(float)(x + 1), hxp, (float)y};
+    sm_f3 c{(float)x, hyp, (float)(y + 1)};
+    sm_f3 r = f3_cross(f3_sub(c, p), f3_sub(b, p));
+    n.x += r.x; n.y += r.y; n.z += r.z;
+    k++;
+  }
+  float fk = (float)k;
+  n.x = n.x / fk; n.y = n.y / fk; n.z = n.z / fk;               // n/(float)k
+  float d = n.x * n.x + n.y * n.y + n.z * n.z;                  // normalize = v * (1/sqrt(dot))
+  float inv = 1.0f / sqrtf(d);
+  return sm_f3{n.x * inv, n.y * inv, n.z * inv};
+}
+
+// ------------------------------------------------------------------------------------------------
+// Particle::cascade, particle.h:24-101.  DEPTH = how many nested re-cascades are compiled in.
+// ------------------------------------------------------------------------------------------------
+template <int DEPTH, class A> struct Cascade {
+  static SM_HD_NOINLINE void run(A& a, int cx, int cy, int transferloop) {
+    const int dimx = a.dimx(), dimy = a.dimy();
+    const int SCALE = a.scale();
+    // neighbour order of particle.h:30-39
+    const int ox[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
+    const int oy[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
+    int sx[8], sy[8];
+    double sh[8];
+    int num = 0;
+    for (int i = 0; i < 8; i++) {
+      int nx = cx + ox[i], ny = cy + oy[i];
+      if (nx >= dimx || ny >= dimy || nx < 0 || ny < 0) continue;   // :51-52
+      // stable insertion by height, highest first (std::sort on <= 8 elements == stable
+      // insertion sort in libstdc++; comparator a.h > b.h, particle.h:58-60)
+      double h = map_height(a, nx, ny);
+      int j = num;
+      while (j > 0 && h > sh[j - 1]) {
+        sh[j] = sh[j - 1]; sx[j] = sx[j - 1]; sy[j] = sy[j - 1];
+        j--;
+      }
+      sh[j] = h; sx[j] = nx; sy[j] = ny;
+      num++;
+    }
+    for (int i = 0; i < num; i++) {
+      int nx = sx[i], ny = sy[i];
+      // :66  full height difference, narrowed to float
+      float diff = (float)((map_height(a, cx, cy) - map_height(a, nx, ny)) * (float)SCALE / 80.0f);
+      if (diff == 0) continue;
+      int tx = (diff > 0) ? cx : nx, ty = (diff > 0) ? cy : ny;     // :71-72
+      int bx = (diff > 0) ? nx : cx, by = (diff > 0) ? ny : cy;
+      Sec32* tr = a.rec(tx, ty);
+      uint32_t type = rec_surface(*tr);                             // :74-75
+      const SoilDev sp = a.soil(type);
+      float excess = fabsf(diff) - sp.maxdiff;                      // :78
+      if (excess <= 0) continue;
+      float transfer = sp.settling * excess / 2.0f;                 // :83
+      double tsize = (tr->type == SM_EMPTY) ? 0.0 : tr->size;
+      if (transfer > tsize) transfer = (float)tsize;                // :87-88 (f64 -> f32 narrowing)
+      bool recascade = false;
+      if (col_remove(a, *tr, (double)transfer) != 0) recascade = true;   // :90-91
+      a.dirty(tx, ty);
+      col_add(a, *a.rec(bx, by), (double)transfer, sp.cascades);    // :92
+      a.dirty(bx, by);
+      if constexpr (DEPTH > 0) {
+        if (recascade && transferloop > 0) {                        // :96-97
+          --transferloop;
+          Cascade<DEPTH - 1, A>::run(a, nx, ny, transferloop);
+        }
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// WaterParticle  (water.h)
+// ------------------------------------------------------------------------------------------------
+#define SM_SQRT2F 1.41421354f   // sqrt(2.0f) rounded to float (water.h:61)
+
+// ctor body water.h:14-17 / wind.h:17-20: what the particle transports
+template <class A> SM_HD uint32_t spawn_contains(A& a, float px, float py) {
+  int ix = (int)roundf(px), iy = (int)roundf(py);
+  return a.soil(rec_surface(*a.rec(ix, iy))).transports;
+}
+
+// one move() && interact().  `a` must cover plus(ipos) and the 3x3 around the new position.
+template <class A> SM_HD int water_step(A& a, WaterP& p) {
+  const int dimx = a.dimx(), dimy = a.dimy();
+  const int SCALE = a.scale();
+  // ---- move, water.h:43-73 ----
+  const int ix = (int)roundf(p.px), iy = (int)roundf(p.py);        // :45
+  a.begin(ix, iy);
+  sm_f3 n = map_normal(a, ix, iy);                                  // :46
+  Sec32* ir = a.rec(ix, iy);
+  uint32_t surface = rec_surface(*ir);                              // :47
+  SoilDev param = a.soil(surface);                                  // :48
+  double evaprate = 0.01;                                           // :49
+  const int ind = iy * dimx + ix;
+  a.track_add(ind, p.volume);                                       // :50, 348-351
+  const float freq = a.water_frequency(ind);
+  param.friction = param.friction * (1.0f - freq);                  // :53
+  evaprate = evaprate * (1.0f - 0.2f * freq);                       // :54
+  {
+    float vx = n.x * param.friction, vz = n.z * param.friction;     // :56
+    float len = sqrtf(vx * vx + vz * vz);
+    if (len < 1E-5) return SM_EXIT_STALL;
+  }
+  {
+    float f = param.friction;                                       // :60 mix(n.xz, speed, friction)
+    float mx = n.x * (1.0f - f) + p.sx * f;
+    float my = n.z * (1.0f - f) + p.sy * f;
+    float inv = 1.0f / sqrtf(mx * mx + my * my);                    // :61 sqrt(2)*normalize
+    p.sx = SM_SQRT2F * (mx * inv);
+    p.sy = SM_SQRT2F * (my * inv);
+  }
+  p.px += p.sx;                                                     // :62
+  p.py += p.sy;
+  if (!(p.px >= 0.0f && p.py >= 0.0f) ||                            // :65-69
+      !(p.px < (float)dimx - 1.0f && p.py < (float)dimy - 1.0f)) {
+    p.volume = 0.0;
+    return SM_EXIT_OOB;
+  }
+  // ---- interact, water.h:75-121 ----
+  const int nx = (int)roundf(p.px), ny = (int)roundf(p.py);
+  a.target(nx, ny);
+  double c_eq = param.solubility * (rec_height(*ir) - map_height_bilinear(a, p.px, p.py)) *
+                (double)SCALE / 80.0;                               // :78
+  if (c_eq < 0.0) c_eq = 0.0;
+  if (c_eq > 1.0) c_eq = 1.0;
+  if ((double)(a.soil(p.contains).erosionrate) < freq)              // :83-84
+    p.contains = a.soil(p.contains).erodes;
+  double cdiff = c_eq - p.sediment;                                 // :87
+  if (cdiff > 0) {                                                  // :91-101
+    p.sediment += param.equrate * cdiff;
+    p.contains = a.soil(rec_surface(*ir)).transports;
+    double diff = col_remove(a, *ir, param.equrate * cdiff * p.volume);
+    while (fabs(diff) > 1E-8) diff = col_remove(a, *ir, diff);
+    a.dirty(ix, iy);
+  } else if (cdiff < 0) {                                           // :105-110
+    const float eq = a.soil(p.contains).equrate;
+    p.sediment += eq * cdiff;
+    col_add(a, *ir, -eq * cdiff * p.volume, p.contains);
+    a.dirty(ix, iy);
+  }
+  Cascade<0, A>::run(a, nx, ny, 0);                                 // :113
+  p.sediment /= (1.0 - evaprate);                                   // :116-119
+  if (p.sediment > 1.0) p.sediment = 1.0;
+  p.volume *= (1.0 - evaprate);
+  return (p.volume > 0.01) ? SM_ALIVE : SM_EXIT_EVAP;
+}
+
+// ------------------------------------------------------------------------------------------------
+// WindParticle  (wind.h)
+// ------------------------------------------------------------------------------------------------
+template <class A> SM_HD int wind_step(A& a, WindP& p) {
+  const int dimx = a.dimx(), dimy = a.dimy();
+  const int SCALE = a.scale();
+  // ---- move, wind.h:54-92 ----
+  if (a.soil(p.contains).suspension == 0.0) return SM_EXIT_OOB;     // :56-57
+  const int ix = (int)roundf(p.px), iy = (int)roundf(p.py);         // :60
+  a.begin(ix, iy);
+  sm_f3 n = map_normal(a, ix, iy);                                  // :61
+  Sec32* ir = a.rec(ix, iy);
+  const SoilDev param = a.soil(rec_surface(*ir));                   // :62-63
+  a.wind_frequency_touch(iy * dimx + ix);                           // :64, 49-52
+  double sheight = rec_height(*ir) * (float)SCALE / 80.0f;          // :67
+  if (p.height < sheight) p.height = sheight;                       // :68-70
+  if (p.height > sheight) {                                         // :73-74
+    p.sy = (float)(p.sy - 0.25);
+  } else {                                                          // :76 mix(speed, cross(cross(speed,n),n), 0.8)
+    sm_f3 s{p.sx, p.sy, p.sz};
+    sm_f3 v = f3_cross(f3_cross(s, n), n);
+    const double w = 0.8;
+    p.sx = (float)((double)s.x * (1.0 - w) + (double)v.x * w);
+    p.sy = (float)((double)s.y * (1.0 - w) + (double)v.y * w);
+    p.sz = (float)((double)s.z * (1.0 - w) + (double)v.z * w);
+  }
+  {                                                                 // :78 mix(speed, pspeed, 0.2)
+    const double w = 0.2;
+    p.sx = (float)((double)p.sx * (1.0 - w) + (double)(-2.0f) * w);
+    p.sy = (float)((double)p.sy * (1.0 - w) + (double)(0.0f) * w);
+    p.sz = (float)((double)p.sz * (1.0 - w) + (double)(1.0f) * w);
+  }
+  p.px += p.sx;                                                     // :79
+  p.py += p.sz;
+  p.height += p.sy;                                                 // :80
+  if (!(p.px >= 0.0f && p.py >= 0.0f) ||                            // :83-85
+      !((int)p.px < dimx - 1 && (int)p.py < dimy - 1))
+    return SM_EXIT_OOB;
+  if (sqrtf(p.sx * p.sx + p.sy * p.sy + p.sz * p.sz) < 0.01)        // :87-88
+    return SM_EXIT_OOB;
+  // ---- interact, wind.h:94-136 ----
+  const int nx = (int)roundf(p.px), ny = (int)roundf(p.py);         // :99
+  a.target(nx, ny);
+  if (p.height <= map_height_bilinear(a, p.px, p.py) * (float)SCALE / 80.0f) {   // :102
+    if (param.transports == p.contains) {                           // :105
+      float len = sqrtf(p.sx * p.sx + p.sy * p.sy + p.sz * p.sz);
+      double force = len * (map_height(a, nx, ny) - p.height) * (float)SCALE / 80.0f *
+                     (1.0f - p.sediment);                           // :107
+      double diff = col_remove(a, *ir, param.suspension * force);   // :109
+      a.dirty(ix, iy);
+      p.sediment += (param.suspension * force - diff);              // :110
+      Cascade<1, A>::run(a, ix, iy, 1);                             // :112
+    }
+  } else if (param.suspension > 0.0) {                              // :119
+    const float sc = a.soil(p.contains).suspension;
+    p.sediment -= sc * p.sediment;                                  // :121
+    col_add(a, *a.rec(nx, ny), 0.5f * sc * p.sediment, p.contains); // :123
+    a.dirty(nx, ny);
+    col_add(a, *ir, 0.5f * sc * p.sediment, p.contains);            // :124
+    a.dirty(ix, iy);
+    Cascade<1, A>::run(a, ix, iy, 1);                               // :126
+    Cascade<1, A>::run(a, nx, ny, 1);                               // :129
+  }
+  return SM_ALIVE;
+}

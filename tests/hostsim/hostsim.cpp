@@ -1,0 +1,151 @@
+// tests/hostsim -- the product's step arithmetic (soilmachine_b200/csrc/sm_core.cuh) compiled
+// for the HOST behind the same lockstep driver shape as the oracle.  TEST TOOL ONLY: it lets the
+// CPU test-suite check the type-exact transcription against oracle/_ref bit for bit without a
+// GPU.  It is not shipped, not linked into the product library and is not a CPU fallback.
+#include <vector>
+#include <cstring>
+#include <cstdint>
+#include <cstdio>
+#include "../../soilmachine_b200/csrc/sm_core.cuh"
+
+namespace {
+struct HostMap {
+  int dimx = 0, dimy = 0, scale = 80;
+  std::vector<Sec32> top, pool;
+  std::vector<uint32_t> freelist;
+  std::vector<SoilDev> soils;
+  std::vector<float> wfreq, wtrack, windfreq;
+  int64_t drops = 0;
+} M;
+
+struct HostAccess {
+  int dimx() const { return M.dimx; }
+  int dimy() const { return M.dimy; }
+  int scale() const { return M.scale; }
+  const SoilDev& soil(uint32_t t) const { return M.soils[t]; }
+  Sec32* rec(int x, int y) { return &M.top[(size_t)x * M.dimy + y]; }
+  void begin(int, int) {}
+  void target(int, int) {}
+  void dirty(int, int) {}
+  Sec32 pool_load(uint32_t i) { return M.pool[i]; }
+  void pool_store(uint32_t i, const Sec32& r) { M.pool[i] = r; }
+  uint32_t pool_alloc() {
+    if (!M.freelist.empty()) { uint32_t i = M.freelist.back(); M.freelist.pop_back(); return i; }
+    M.pool.push_back(Sec32{});
+    return (uint32_t)(M.pool.size() - 1);
+  }
+  void pool_free(uint32_t i) { M.freelist.push_back(i); }
+  void track_add(int ind, double v) { M.wtrack[ind] = (float)(M.wtrack[ind] + v); }
+  float water_frequency(int ind) { return M.wfreq[ind]; }
+  void wind_frequency_touch(int ind) { M.windfreq[ind] = (float)(0.5 * M.windfreq[ind] + 0.5f); }
+};
+
+struct Stats { int64_t steps, sweeps, exit_oob, exit_evap, exit_stall; double seconds; };
+std::vector<WaterP> W; std::vector<int> Wlive;
+std::vector<WindP> D; std::vector<int> Dlive;
+}  // namespace
+
+extern "C" {
+void hs_init(int dimx, int dimy, int scale, int nsoils, const SoilDev* soils) {
+  M = HostMap();
+  M.dimx = dimx; M.dimy = dimy; M.scale = scale;
+  M.soils.assign(soils, soils + nsoils);
+  M.top.resize((size_t)dimx * dimy);
+  for (auto& r : M.top) rec_set_empty(r);
+  M.wfreq.assign((size_t)dimx * dimy, 0.f); M.wtrack = M.wfreq; M.windfreq = M.wfreq;
+}
+void hs_set_columns(const int64_t* off, const int32_t* type, const double* size, const double* sat) {
+  HostAccess a;
+  for (int x = 0; x < M.dimx; x++) for (int y = 0; y < M.dimy; y++) {
+    size_t c = (size_t)x * M.dimy + y;
+    rec_set_empty(M.top[c]);
+    for (int64_t k = off[c]; k < off[c + 1]; k++) col_add(a, M.top[c], size[k], (uint32_t)type[k], sat ? sat[k] : 0.0);
+  }
+}
+int64_t hs_nsections() {
+  int64_t n = 0;
+  for (auto& r : M.top) { if (r.type == SM_EMPTY) continue; n++; for (uint32_t b = r.below; b != SM_NIL; b = M.pool[b].below) n++; }
+  return n;
+}
+void hs_get_columns(int64_t* off, int32_t* type, double* size, double* floor_, double* sat) {
+  int64_t n = 0;
+  for (size_t c = 0; c < M.top.size(); c++) {
+    off[c] = n;
+    std::vector<Sec32> st;
+    const Sec32& r = M.top[c];
+    if (r.type != SM_EMPTY) { st.push_back(r); for (uint32_t b = r.below; b != SM_NIL; b = M.pool[b].below) st.push_back(M.pool[b]); }
+    for (size_t i = st.size(); i-- > 0;) { type[n] = (int32_t)st[i].type; size[n] = st[i].size; floor_[n] = st[i].floor; sat[n] = st[i].saturation; n++; }
+  }
+  off[M.top.size()] = n;
+}
+void hs_heights(double* out) { for (size_t c = 0; c < M.top.size(); c++) out[c] = rec_height(M.top[c]); }
+void hs_get_frequency(float* a, float* b, float* c) {
+  size_t n = M.wfreq.size() * 4;
+  if (a) memcpy(a, M.wfreq.data(), n); if (b) memcpy(b, M.wtrack.data(), n); if (c) memcpy(c, M.windfreq.data(), n);
+}
+void hs_set_frequency(const float* a, const float* b, const float* c) {
+  size_t n = M.wfreq.size() * 4;
+  if (a) memcpy(M.wfreq.data(), a, n); if (b) memcpy(M.wtrack.data(), b, n); if (c) memcpy(M.windfreq.data(), c, n);
+}
+void hs_normal(int x, int y, float* o) { HostAccess a; sm_f3 n = map_normal(a, x, y); o[0] = n.x; o[1] = n.y; o[2] = n.z; }
+double hs_height_f(float x, float y) { HostAccess a; return map_height_bilinear(a, x, y); }
+void hs_add(int x, int y, double s, int t) { HostAccess a; col_add(a, *a.rec(x, y), s, (uint32_t)t); }
+double hs_remove(int x, int y, double h) { HostAccess a; return col_remove(a, *a.rec(x, y), h); }
+void hs_cascade(float x, float y, int loop) { HostAccess a; Cascade<3, HostAccess>::run(a, (int)roundf(x), (int)roundf(y), loop); }
+
+void hs_water_begin(int n, const float* xy) {
+  HostAccess a; W.clear(); Wlive.clear();
+  for (int i = 0; i < n; i++) {
+    WaterP p{xy[2 * i], xy[2 * i + 1], 0.f, 0.f, 1.0, 0.0, 0};
+    p.contains = spawn_contains(a, p.px, p.py);
+    W.push_back(p); Wlive.push_back(i);
+  }
+}
+int hs_water_sweep(Stats* st) {
+  HostAccess a; std::vector<int> next;
+  for (int i : Wlive) {
+    int r = water_step(a, W[i]);
+    if (r == SM_EXIT_OOB) { st->exit_oob++; continue; }
+    if (r == SM_EXIT_STALL) { st->exit_stall++; continue; }
+    st->steps++;
+    if (r == SM_EXIT_EVAP) { st->exit_evap++; continue; }
+    next.push_back(i);
+  }
+  Wlive.swap(next); st->sweeps++;
+  return (int)Wlive.size();
+}
+void hs_water_state(float* pos, float* speed, double* vol, double* sed, int32_t* cont, int32_t* alive) {
+  for (size_t i = 0; i < W.size(); i++) {
+    pos[2 * i] = W[i].px; pos[2 * i + 1] = W[i].py; speed[2 * i] = W[i].sx; speed[2 * i + 1] = W[i].sy;
+    vol[i] = W[i].volume; sed[i] = W[i].sediment; cont[i] = (int32_t)W[i].contains; alive[i] = 0;
+  }
+  for (int i : Wlive) alive[i] = 1;
+}
+void hs_wind_begin(int n, const float* xy) {
+  HostAccess a; D.clear(); Dlive.clear();
+  for (int i = 0; i < n; i++) {
+    WindP p{xy[2 * i], xy[2 * i + 1], -2.f, 0.f, 1.f, 0.0, 0.0, 0};
+    p.contains = spawn_contains(a, p.px, p.py);
+    D.push_back(p); Dlive.push_back(i);
+  }
+}
+int hs_wind_sweep(Stats* st) {
+  HostAccess a; std::vector<int> next;
+  for (int i : Dlive) {
+    int r = wind_step(a, D[i]);
+    if (r != SM_ALIVE) { st->exit_oob++; continue; }
+    st->steps++;
+    next.push_back(i);
+  }
+  Dlive.swap(next); st->sweeps++;
+  return (int)Dlive.size();
+}
+void hs_wind_state(float* pos, float* speed3, double* h, double* sed, int32_t* cont, int32_t* alive) {
+  for (size_t i = 0; i < D.size(); i++) {
+    pos[2 * i] = D[i].px; pos[2 * i + 1] = D[i].py;
+    speed3[3 * i] = D[i].sx; speed3[3 * i + 1] = D[i].sy; speed3[3 * i + 2] = D[i].sz;
+    h[i] = D[i].height; sed[i] = D[i].sediment; cont[i] = (int32_t)D[i].contains; alive[i] = 0;
+  }
+  for (int i : Dlive) alive[i] = 1;
+}
+}
