@@ -18,10 +18,12 @@
 
 #if defined(__CUDACC__)
 #define SM_HD __host__ __device__ __forceinline__
-#define SM_HD_NOINLINE __host__ __device__
+#define SM_HD_NOINLINE __host__ __device__ __noinline__
+#define SM_UNROLL1 _Pragma("unroll 1")
 #else
 #define SM_HD inline
 #define SM_HD_NOINLINE inline
+#define SM_UNROLL1
 #endif
 
 #define SM_NIL 0xFFFFFFFFu
@@ -232,6 +234,7 @@ template <int DEPTH, class A> struct Cascade {
     int sx[8], sy[8];
     double sh[8];
     int num = 0;
+    SM_UNROLL1
     for (int i = 0; i < 8; i++) {
       int nx = cx + ox[i], ny = cy + oy[i];
       if (nx >= dimx || ny >= dimy || nx < 0 || ny < 0) continue;   // :51-52
@@ -239,6 +242,7 @@ template <int DEPTH, class A> struct Cascade {
       // insertion sort in libstdc++; comparator a.h > b.h, particle.h:58-60)
       double h = map_height(a, nx, ny);
       int j = num;
+      SM_UNROLL1
       while (j > 0 && h > sh[j - 1]) {
         sh[j] = sh[j - 1]; sx[j] = sx[j - 1]; sy[j] = sy[j - 1];
         j--;
@@ -246,6 +250,7 @@ template <int DEPTH, class A> struct Cascade {
       sh[j] = h; sx[j] = nx; sy[j] = ny;
       num++;
     }
+    SM_UNROLL1
     for (int i = 0; i < num; i++) {
       int nx = sx[i], ny = sy[i];
       // :66  full height difference, narrowed to float
@@ -338,6 +343,7 @@ template <class A> SM_HD int water_step(A& a, WaterP& p) {
     p.sediment += param.equrate * cdiff;
     p.contains = a.soil(rec_surface(*ir)).transports;
     double diff = col_remove(a, *ir, param.equrate * cdiff * p.volume);
+    SM_UNROLL1
     while (fabs(diff) > 1E-8) diff = col_remove(a, *ir, diff);
     a.dirty(ix, iy);
   } else if (cdiff < 0) {                                           // :105-110

@@ -1,0 +1,895 @@
+// sm_engine.cu -- sm_100a kernels and the C ABI of include/soilmachine_b200.h.
+//
+// Hot path = k_run<KIND>: ONE persistent, co-resident kernel per particle batch.  Every sweep each
+// live particle executes move()+interact() (sm_core.cuh) exactly once; particles whose conflict
+// boxes overlap are serialised in ascending particle index by a dataflow wait (a particle spins
+// until every lower-index particle within reach has published the current sweep tag), so the
+// result is bit-identical to the reference functions driven sweep by sweep in index order
+// (oracle lockstep mode).  One grid barrier per sweep; no kernel launch per sweep.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "../../include/soilmachine_b200.h"
+#include "sm_device.cuh"
+
+#define KIND_WATER 0
+#define KIND_WIND 1
+
+// conflict reach: a water step stays within ipos+-3, a wind step within
+// ipos+-5, so two steps commute unless |dipos|_inf <= 6 (water) / 10 (wind).  Bin edge >= reach*2
+// keeps every possible blocker inside the 3x3 bins around a particle.
+template <int KIND> struct Reach {
+  static constexpr int D = (KIND == KIND_WATER) ? 6 : 10;
+  static constexpr int G = (KIND == KIND_WATER) ? 8 : 16;
+  static constexpr int STEP = (KIND == KIND_WATER) ? 2 : 3;   // max |npos - ipos|_inf
+};
+#define SM_MIN_BIN 8
+#define SM_SWEEPS_NONE 0x40000000   // internal: run the prologue only
+
+// ---------------------------------------------------------------------------------------------
+// bins
+// ---------------------------------------------------------------------------------------------
+template <int KIND>
+__device__ __forceinline__ void bin_insert(const DevCtx& c, unsigned int tag, int pid, int ix, int iy) {
+  const unsigned int par = tag & 1u;
+  const int G = Reach<KIND>::G;
+  const int nby = (c.dimy + G - 1) / G;
+  const int b = (ix / G) * nby + (iy / G);
+  c.key[par][pid] = ((uint32_t)ix << 16) | (uint32_t)iy;
+  unsigned long long old =
+      atomicExch(&c.head[par][b], ((unsigned long long)tag << 32) | (unsigned long long)(uint32_t)pid);
+  c.next[par][pid] = ((unsigned int)(old >> 32) == tag) ? (uint32_t)old : SM_NIL;
+}
+
+// Wait until every lower-index live particle whose conflict box overlaps mine has finished sweep
+// `tag`.  Lists were completed before the grid barrier that opened this sweep.
+template <int KIND>
+__device__ __forceinline__ void wait_blockers(const DevCtx& c, unsigned int tag, int pid, int ix, int iy) {
+  const unsigned int par = tag & 1u;
+  const int G = Reach<KIND>::G, D = Reach<KIND>::D;
+  const int nbx = (c.dimx + G - 1) / G, nby = (c.dimy + G - 1) / G;
+  const int bx = ix / G, by = iy / G;
+  const int K = 8;
+  uint32_t list[K];
+  for (;;) {
+    int found = 0;
+    bool more = false;
+    for (int dbx = -1; dbx <= 1; dbx++) {
+      const int cx = bx + dbx;
+      if (cx < 0 || cx >= nbx) continue;
+      for (int dby = -1; dby <= 1; dby++) {
+        const int cy = by + dby;
+        if (cy < 0 || cy >= nby) continue;
+        unsigned long long h = *((volatile unsigned long long*)&c.head[par][cx * nby + cy]);
+        if ((unsigned int)(h >> 32) != tag) continue;
+        uint32_t j = (uint32_t)h;
+        while (j != SM_NIL) {
+          const uint32_t nxt = c.next[par][j];
+          if (j < (uint32_t)pid) {
+            const uint32_t k = c.key[par][j];
+            int dx = (int)(k >> 16) - ix, dy = (int)(k & 0xFFFFu) - iy;
+            dx = dx < 0 ? -dx : dx;
+            dy = dy < 0 ? -dy : dy;
+            if (dx <= D && dy <= D && ld_volatile_u32(&c.done[j]) < tag) {
+              if (found < K) list[found++] = j;
+              else more = true;
+            }
+          }
+          j = nxt;
+        }
+      }
+    }
+    if (found == 0) break;
+    for (int i = 0; i < found; i++) {
+      while (ld_volatile_u32(&c.done[list[i]]) < tag) { __nanosleep(40); }
+    }
+    if (!more) break;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// particle state I/O
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_particle(const DevCtx& c, int pid, WaterP& p) {
+  float4 a = c.pa[pid]; double2 b = c.pb[pid]; uint2 d = c.pc[pid];
+  p.px = a.x; p.py = a.y; p.sx = a.z; p.sy = a.w; p.volume = b.x; p.sediment = b.y; p.contains = d.x;
+}
+__device__ __forceinline__ void store_particle(const DevCtx& c, int pid, const WaterP& p) {
+  c.pa[pid] = make_float4(p.px, p.py, p.sx, p.sy);
+  c.pb[pid] = make_double2(p.volume, p.sediment);
+  c.pc[pid] = make_uint2(p.contains, 0u);
+}
+__device__ __forceinline__ void load_particle(const DevCtx& c, int pid, WindP& p) {
+  float4 a = c.pa[pid]; double2 b = c.pb[pid]; uint2 d = c.pc[pid];
+  p.px = a.x; p.py = a.y; p.sx = a.z; p.sy = a.w; p.sediment = b.x; p.height = b.y;
+  p.contains = d.x; p.sz = __uint_as_float(d.y);
+}
+__device__ __forceinline__ void store_particle(const DevCtx& c, int pid, const WindP& p) {
+  c.pa[pid] = make_float4(p.px, p.py, p.sx, p.sy);
+  c.pb[pid] = make_double2(p.sediment, p.height);
+  c.pc[pid] = make_uint2(p.contains, __float_as_uint(p.sz));
+}
+template <int KIND> struct PType { typedef WaterP T; };
+template <> struct PType<KIND_WIND> { typedef WindP T; };
+
+__device__ __forceinline__ int do_step(DevAccess& a, WaterP& p) { return water_step(a, p); }
+__device__ __forceinline__ int do_step(DevAccess& a, WindP& p) { return wind_step(a, p); }
+
+// ---------------------------------------------------------------------------------------------
+// the persistent sweep kernel
+// ---------------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(256) k_run(DevCtx c, int n, const float* __restrict__ spawn,
+                                            int max_sweeps, int lshift) {
+  typedef typename PType<KIND>::T P;
+  __shared__ SoilDev s_soils[SM_MAX_SOILS];
+  __shared__ unsigned int s_alive;
+  for (int i = threadIdx.x; i < c.nsoils; i += blockDim.x) s_soils[i] = c.soils[i];
+  if (threadIdx.x == 0) s_alive = 0;
+  __syncthreads();
+
+  RunCtl* ctl = c.ctl;
+  unsigned int epoch = 0;
+  const unsigned int tag0 = ctl->tag_base;   // constant during the launch (rewritten at the very end)
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool leader = (gtid & ((1 << lshift) - 1)) == 0;
+  const int slot = gtid >> lshift;
+  const int nslots = (gridDim.x * blockDim.x) >> lshift;
+
+  unsigned long long n_steps = 0, n_oob = 0, n_evap = 0, n_stall = 0;
+
+  // ---- prologue: spawn (ctor bodies water.h:13-17 / wind.h:15-20) or resume, fill the bins ----
+  {
+    unsigned int my_alive = 0;
+    if (leader) {
+      for (int pid = slot; pid < n; pid += nslots) {
+        P p;
+        bool alive;
+        if (spawn != nullptr) {
+          DevAccess a(c, s_soils, tag0);
+          const float x = spawn[2 * pid], y = spawn[2 * pid + 1];
+          if (KIND == KIND_WATER) {
+            WaterP w{x, y, 0.0f, 0.0f, 1.0, 0.0, 0u};
+            w.contains = spawn_contains(a, x, y);
+            store_particle(c, pid, w);
+            alive = true;
+          } else {
+            WindP w{x, y, -2.0f, 0.0f, 1.0f, 0.0, 0.0, 0u};
+            w.contains = spawn_contains(a, x, y);
+            store_particle(c, pid, w);
+            // wind.h:56-57: a particle whose load cannot be suspended dies in its first move()
+            // without touching anything
+            alive = !(s_soils[w.contains].suspension == 0.0);
+            if (!alive) n_oob++;
+          }
+          c.alive[pid] = alive ? 1 : 0;
+          c.done[pid] = alive ? (tag0 - 1u) : 0xFFFFFFFFu;
+        } else {
+          alive = c.alive[pid] != 0;
+        }
+        if (alive) {
+          float4 pa = c.pa[pid];
+          bin_insert<KIND>(c, tag0, pid, (int)roundf(pa.x), (int)roundf(pa.y));
+          my_alive++;
+        }
+      }
+    }
+    if (my_alive) atomicAdd(&s_alive, my_alive);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (s_alive) atomicAdd(&ctl->alive_slot[0], s_alive);
+      s_alive = 0;
+    }
+    grid_barrier(&ctl->barrier, epoch);
+  }
+
+  int s = 0;
+  unsigned int total_alive = 0;
+  for (;; s++) {
+    const unsigned int tag = tag0 + (unsigned int)s;
+    total_alive = ld_volatile_u32(&ctl->alive_slot[s % 3]);
+    if (total_alive == 0 || (max_sweeps >= 0 && s >= max_sweeps)) break;
+    if (gtid == 0) st_volatile_u32(&ctl->alive_slot[(s + 2) % 3], 0u);
+
+    unsigned int my_alive = 0;
+    if (leader) {
+      for (int pid = slot; pid < n; pid += nslots) {
+        if (c.alive[pid] == 0) continue;
+        P p;
+        load_particle(c, pid, p);
+        const int ix = (int)roundf(p.px), iy = (int)roundf(p.py);
+        wait_blockers<KIND>(c, tag, pid, ix, iy);
+        __threadfence();
+        DevAccess a(c, s_soils, tag);
+        const int r = do_step(a, p);
+        store_particle(c, pid, p);
+        if (r == SM_ALIVE) {
+          n_steps++;
+          const int jx = (int)roundf(p.px), jy = (int)roundf(p.py);
+          int ddx = jx - ix, ddy = jy - iy;
+          ddx = ddx < 0 ? -ddx : ddx; ddy = ddy < 0 ? -ddy : ddy;
+          if (ddx > Reach<KIND>::STEP || ddy > Reach<KIND>::STEP) atomicOr(&ctl->err, 1u << 4);  // SM_ERR_REACH
+          bin_insert<KIND>(c, tag + 1u, pid, jx, jy);
+          my_alive++;
+        } else {
+          c.alive[pid] = 0;
+          if (r == SM_EXIT_OOB) n_oob++;
+          else if (r == SM_EXIT_STALL) n_stall++;
+          else { n_steps++; n_evap++; }
+        }
+        __threadfence();
+        st_volatile_u32(&c.done[pid], r == SM_ALIVE ? tag : 0xFFFFFFFFu);
+      }
+    }
+    if (my_alive) atomicAdd(&s_alive, my_alive);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (s_alive) atomicAdd(&ctl->alive_slot[(s + 1) % 3], s_alive);
+      s_alive = 0;
+    }
+    grid_barrier(&ctl->barrier, epoch);
+  }
+
+  // ---- epilogue ----
+  if (n_steps) atomicAdd(&ctl->steps, n_steps);
+  if (n_oob) atomicAdd(&ctl->exit_oob, n_oob);
+  if (n_evap) atomicAdd(&ctl->exit_evap, n_evap);
+  if (n_stall) atomicAdd(&ctl->exit_stall, n_stall);
+  // tag_base was read by every block before its first barrier; barrier/alive_slot are reset by the
+  // host before the next launch
+  if (gtid == 0) {
+    ctl->sweeps += (unsigned long long)s;
+    ctl->alive = total_alive;
+    ctl->tag_base = tag0 + (unsigned int)s + 2u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// full-grid and utility kernels
+// ---------------------------------------------------------------------------------------------
+// mapfrequency + resetfrequency, water.h:353-365 (one fused pass: 16 B per cell)
+__global__ void k_frequency_update(float* __restrict__ freq, float* __restrict__ track, size_t n) {
+  const float lrate = 0.01f, K = 50.0f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float t = track[i];
+    freq[i] = (1.0f - lrate) * freq[i] + lrate * K * t / (1.0f + K * t);
+    track[i] = 0.0f;
+  }
+}
+
+__global__ void k_heights(const Sec32* __restrict__ top, double* __restrict__ out, int32_t* __restrict__ surf,
+                          size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const Sec32 r = top[i];
+    if (out) out[i] = rec_height(r);
+    if (surf) surf[i] = (int32_t)rec_surface(r);
+  }
+}
+
+// deterministic sum: fixed chunking, fixed in-block tree; second pass sums the partials in order
+#define SUM_BLOCKS 1024
+__global__ void k_height_sum1(const Sec32* __restrict__ top, size_t n, double* __restrict__ partial) {
+  __shared__ double sh[256];
+  const size_t chunk = (n + SUM_BLOCKS - 1) / SUM_BLOCKS;
+  const size_t lo = (size_t)blockIdx.x * chunk, hi = (lo + chunk < n) ? lo + chunk : n;
+  double acc = 0.0;
+  for (size_t i = lo + threadIdx.x; i < hi; i += 256) acc += rec_height(top[i]);
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s2 = 128; s2 > 0; s2 >>= 1) {
+    if (threadIdx.x < s2) sh[threadIdx.x] += sh[threadIdx.x + s2];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+__global__ void k_height_sum2(const double* __restrict__ partial, double* __restrict__ out) {
+  __shared__ double sh[SUM_BLOCKS];
+  for (int i = threadIdx.x; i < SUM_BLOCKS; i += blockDim.x) sh[i] = partial[i];
+  __syncthreads();
+  for (int s2 = SUM_BLOCKS / 2; s2 > 0; s2 >>= 1) {
+    for (int i = threadIdx.x; i < s2; i += blockDim.x) sh[i] += sh[i + s2];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sh[0];
+}
+
+// single-cell operations for the facade's legacy Layermap calls: op 0 add, 1 remove, 2 cascade,
+// 3 query (height, surface, normal), 4 bilinear height
+struct CellOp { int op; int x, y; float fx, fy; double v; int t; };
+struct CellRes { double d; int32_t surface; float n[3]; };
+__global__ void k_cell_op(DevCtx c, CellOp o, CellRes* res) {
+  __shared__ SoilDev s_soils[SM_MAX_SOILS];
+  for (int i = 0; i < c.nsoils; i++) s_soils[i] = c.soils[i];
+  DevAccess a(c, s_soils, 0u);
+  CellRes r{0.0, 0, {0.f, 0.f, 0.f}};
+  if (o.op == 0) col_add(a, *a.rec(o.x, o.y), o.v, (uint32_t)o.t);
+  else if (o.op == 1) r.d = col_remove(a, *a.rec(o.x, o.y), o.v);
+  else if (o.op == 2) Cascade<3, DevAccess>::run(a, (int)roundf(o.fx), (int)roundf(o.fy), o.t);
+  else if (o.op == 3) {
+    r.d = map_height(a, o.x, o.y);
+    r.surface = (int32_t)rec_surface(*a.rec(o.x, o.y));
+    sm_f3 n = map_normal(a, o.x, o.y);
+    r.n[0] = n.x; r.n[1] = n.y; r.n[2] = n.z;
+  } else if (o.op == 4) r.d = map_height_bilinear(a, o.fx, o.fy);
+  *res = r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct sm_context {
+  sm_config cfg;
+  DevCtx d;
+  std::string err;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  size_t cells = 0;
+  int max_particles = 0;
+  int nsoils = 0;
+  SoilDev* d_soils = nullptr;
+  float* d_spawn = nullptr;
+  double* d_scratch = nullptr;    // height download / partial sums
+  int32_t* d_iscratch = nullptr;
+  CellRes* d_cellres = nullptr;
+  RunCtl* h_ctl = nullptr;        // pinned
+  int64_t launches = 0;
+  int cur_kind = -1, cur_n = 0;
+  bool timing_pending = false;
+  int num_sms = 0;
+  int occ[2] = {0, 0};
+};
+
+static std::string g_create_err;
+
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                      \
+      return SM_ERR_CUDA;                                                                 \
+    }                                                                                     \
+  } while (0)
+
+static int fail(sm_context* ctx, int code, const char* msg) {
+  ctx->err = msg;
+  return code;
+}
+
+static void host_soil_to_dev(const sm_soil& s, SoilDev& d) {
+  d.friction = s.friction; d.solubility = s.solubility; d.equrate = s.equrate;
+  d.erosionrate = s.erosionrate; d.maxdiff = s.maxdiff; d.settling = s.settling;
+  d.suspension = s.suspension; d.porosity = s.porosity;
+  d.transports = (uint32_t)s.transports; d.erodes = (uint32_t)s.erodes;
+  d.cascades = (uint32_t)s.cascades; d.abrades = (uint32_t)s.abrades;
+}
+
+extern "C" {
+
+const char* sm_last_error(const sm_context* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+void sm_destroy(sm_context* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->cfg.device);
+  cudaDeviceSynchronize();
+  DevCtx& d = ctx->d;
+  cudaFree(d.top); cudaFree(d.pool); cudaFree(d.ringbuf[0]); cudaFree(d.ringbuf[1]);
+  cudaFree(d.wfreq); cudaFree(d.wtrack); cudaFree(d.windfreq); cudaFree(ctx->d_soils);
+  cudaFree(d.ctl); cudaFree(d.pa); cudaFree(d.pb); cudaFree(d.pc); cudaFree(d.alive); cudaFree(d.done);
+  for (int i = 0; i < 2; i++) { cudaFree(d.head[i]); cudaFree(d.next[i]); cudaFree(d.key[i]); }
+  cudaFree(ctx->d_spawn); cudaFree(ctx->d_scratch); cudaFree(ctx->d_iscratch); cudaFree(ctx->d_cellres);
+  if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+static int alloc_pool(sm_context* ctx, unsigned long long cap) {
+  DevCtx& d = ctx->d;
+  if (d.pool && d.pool_cap >= cap) return SM_OK;
+  cudaFree(d.pool); cudaFree(d.ringbuf[0]); cudaFree(d.ringbuf[1]);
+  d.pool = nullptr; d.ringbuf[0] = d.ringbuf[1] = nullptr;
+  CK(cudaMalloc(&d.pool, cap * sizeof(Sec32)));
+  CK(cudaMalloc(&d.ringbuf[0], cap * sizeof(uint32_t)));
+  CK(cudaMalloc(&d.ringbuf[1], cap * sizeof(uint32_t)));
+  d.pool_cap = cap;
+  return SM_OK;
+}
+
+int sm_create(const sm_config* cfg, sm_context** out) {
+  if (!cfg || !out || cfg->dimx < 2 || cfg->dimy < 2 || cfg->dimx > 65535 || cfg->dimy > 65535) {
+    g_create_err = "sm_create: invalid configuration";
+    return SM_ERR_INVALID;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    g_create_err = "sm_create: no CUDA device (this library has no CPU fallback)";
+    return SM_ERR_NOGPU;
+  }
+  sm_context* ctx = new sm_context();
+  ctx->cfg = *cfg;
+  memset(&ctx->d, 0, sizeof(DevCtx));
+  int rc = [&]() -> int {
+    CK(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, cfg->device));
+    ctx->num_sms = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&ctx->ev0));
+    CK(cudaEventCreate(&ctx->ev1));
+    DevCtx& d = ctx->d;
+    d.dimx = cfg->dimx; d.dimy = cfg->dimy; d.scale = cfg->scale;
+    ctx->cells = (size_t)cfg->dimx * cfg->dimy;
+    ctx->max_particles = cfg->max_particles > 0 ? cfg->max_particles : 262144;
+    const size_t C = ctx->cells, N = (size_t)ctx->max_particles;
+    CK(cudaMalloc(&d.top, C * sizeof(Sec32)));
+    CK(cudaMalloc(&d.wfreq, C * 4)); CK(cudaMalloc(&d.wtrack, C * 4)); CK(cudaMalloc(&d.windfreq, C * 4));
+    CK(cudaMemsetAsync(d.wfreq, 0, C * 4, ctx->stream));
+    CK(cudaMemsetAsync(d.wtrack, 0, C * 4, ctx->stream));
+    CK(cudaMemsetAsync(d.windfreq, 0, C * 4, ctx->stream));
+    CK(cudaMalloc(&ctx->d_soils, SM_MAX_SOILS * sizeof(SoilDev)));
+    d.soils = ctx->d_soils;
+    CK(cudaMalloc(&d.ctl, sizeof(RunCtl)));
+    CK(cudaMemsetAsync(d.ctl, 0, sizeof(RunCtl), ctx->stream));
+    CK(cudaMalloc(&d.pa, N * sizeof(float4))); CK(cudaMalloc(&d.pb, N * sizeof(double2)));
+    CK(cudaMalloc(&d.pc, N * sizeof(uint2))); CK(cudaMalloc(&d.alive, N)); CK(cudaMalloc(&d.done, N * 4));
+    d.nbx = (cfg->dimx + SM_MIN_BIN - 1) / SM_MIN_BIN; d.nby = (cfg->dimy + SM_MIN_BIN - 1) / SM_MIN_BIN;
+    for (int i = 0; i < 2; i++) {
+      CK(cudaMalloc(&d.head[i], (size_t)d.nbx * d.nby * 8));
+      CK(cudaMemsetAsync(d.head[i], 0, (size_t)d.nbx * d.nby * 8, ctx->stream));
+      CK(cudaMalloc(&d.next[i], N * 4)); CK(cudaMalloc(&d.key[i], N * 4));
+    }
+    CK(cudaMalloc(&ctx->d_spawn, N * 8));
+    CK(cudaMalloc(&ctx->d_scratch, std::max(C, (size_t)SUM_BLOCKS + 8) * 8));
+    CK(cudaMalloc(&ctx->d_iscratch, C * 4));
+    CK(cudaMalloc(&ctx->d_cellres, sizeof(CellRes)));
+    CK(cudaMallocHost(&ctx->h_ctl, sizeof(RunCtl)));
+    // tags start at 1 so that zero-initialised bin heads never match
+    RunCtl init; memset(&init, 0, sizeof(init)); init.tag_base = 2;
+    CK(cudaMemcpyAsync(d.ctl, &init, sizeof(RunCtl), cudaMemcpyHostToDevice, ctx->stream));
+    // empty terrain
+    {
+      std::vector<Sec32> empty(C);
+      for (auto& r : empty) rec_set_empty(r);
+      CK(cudaMemcpyAsync(d.top, empty.data(), C * sizeof(Sec32), cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+    }
+    int rcp = alloc_pool(ctx, cfg->pool_capacity > 0 ? (unsigned long long)cfg->pool_capacity
+                                                     : (unsigned long long)C + (4ull << 20));
+    if (rcp != SM_OK) return rcp;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ[0], k_run<KIND_WATER>, 256, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ[1], k_run<KIND_WIND>, 256, 0));
+    if (ctx->occ[0] < 1 || ctx->occ[1] < 1) return fail(ctx, SM_ERR_CUDA, "sweep kernel does not fit an SM");
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SM_OK;
+  }();
+  if (rc != SM_OK) {
+    g_create_err = ctx->err;
+    sm_destroy(ctx);
+    return rc;
+  }
+  *out = ctx;
+  return SM_OK;
+}
+
+int sm_sync(sm_context* ctx) {
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SM_OK;
+}
+
+int sm_set_soils(sm_context* ctx, const sm_soil* soils, int32_t n) {
+  if (!soils || n < 1 || n > SM_MAX_SOILS) return fail(ctx, SM_ERR_INVALID, "sm_set_soils: 1..64 soils");
+  for (int i = 0; i < n; i++) {
+    const sm_soil& s = soils[i];
+    if (s.transports < 0 || s.transports >= n || s.erodes < 0 || s.erodes >= n || s.cascades < 0 ||
+        s.cascades >= n || s.abrades < 0 || s.abrades >= n)
+      return fail(ctx, SM_ERR_INVALID, "sm_set_soils: soil reference out of range");
+  }
+  std::vector<SoilDev> dev(n);
+  for (int i = 0; i < n; i++) host_soil_to_dev(soils[i], dev[i]);
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaMemcpyAsync(ctx->d_soils, dev.data(), n * sizeof(SoilDev), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->nsoils = n;
+  ctx->d.nsoils = n;
+  return SM_OK;
+}
+
+// ---- columns --------------------------------------------------------------------------------
+namespace {
+struct HostBuild {  // accessor used to replay add() on the host while building the upload image
+  std::vector<Sec32>* pool;
+  Sec32 pool_load(uint32_t i) { return (*pool)[i]; }
+  void pool_store(uint32_t i, const Sec32& r) { (*pool)[i] = r; }
+  uint32_t pool_alloc() { pool->push_back(Sec32{}); return (uint32_t)(pool->size() - 1); }
+  void pool_free(uint32_t) {}
+};
+}  // namespace
+
+static int reset_pool_ctl(sm_context* ctx, unsigned long long used) {
+  // bump = used, rings empty
+  CK(cudaStreamSynchronize(ctx->stream));
+  RunCtl h;
+  CK(cudaMemcpy(&h, ctx->d.ctl, sizeof(RunCtl), cudaMemcpyDeviceToHost));
+  h.bump = used;
+  h.ring[0].head = h.ring[0].tail = 0;
+  h.ring[1].head = h.ring[1].tail = 0;
+  h.err = 0; h.drops = 0;
+  CK(cudaMemcpy(ctx->d.ctl, &h, sizeof(RunCtl), cudaMemcpyHostToDevice));
+  return SM_OK;
+}
+
+int sm_upload_columns(sm_context* ctx, const int64_t* offsets, const int32_t* type, const double* size,
+                      const double* saturation) {
+  if (!offsets || !type || !size) return fail(ctx, SM_ERR_INVALID, "sm_upload_columns: null argument");
+  CK(cudaSetDevice(ctx->cfg.device));
+  const size_t C = ctx->cells;
+  std::vector<Sec32> top(C), pool;
+  pool.reserve((size_t)std::max<int64_t>(0, offsets[C] - (int64_t)C) + 16);
+  HostBuild hb{&pool};
+  for (size_t c = 0; c < C; c++) {
+    rec_set_empty(top[c]);
+    for (int64_t k = offsets[c]; k < offsets[c + 1]; k++) {
+      if (type[k] < 0 || (ctx->nsoils > 0 && type[k] >= ctx->nsoils))
+        return fail(ctx, SM_ERR_INVALID, "sm_upload_columns: section type out of range");
+      col_add(hb, top[c], size[k], (uint32_t)type[k], saturation ? saturation[k] : 0.0);
+    }
+  }
+  const unsigned long long need = pool.size();
+  if (ctx->cfg.pool_capacity > 0) {
+    if (need > ctx->d.pool_cap) return fail(ctx, SM_ERR_POOL, "sm_upload_columns: pool_capacity too small");
+  } else {
+    int rc = alloc_pool(ctx, need + (unsigned long long)C + (4ull << 20));
+    if (rc != SM_OK) return rc;
+  }
+  CK(cudaMemcpy(ctx->d.top, top.data(), C * sizeof(Sec32), cudaMemcpyHostToDevice));
+  if (need) CK(cudaMemcpy(ctx->d.pool, pool.data(), need * sizeof(Sec32), cudaMemcpyHostToDevice));
+  return reset_pool_ctl(ctx, need);
+}
+
+static int fetch_image(sm_context* ctx, std::vector<Sec32>& top, std::vector<Sec32>& pool) {
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  RunCtl h;
+  CK(cudaMemcpy(&h, ctx->d.ctl, sizeof(RunCtl), cudaMemcpyDeviceToHost));
+  const size_t used = (size_t)std::min<unsigned long long>(h.bump, ctx->d.pool_cap);
+  top.resize(ctx->cells);
+  pool.resize(used);
+  CK(cudaMemcpy(top.data(), ctx->d.top, ctx->cells * sizeof(Sec32), cudaMemcpyDeviceToHost));
+  if (used) CK(cudaMemcpy(pool.data(), ctx->d.pool, used * sizeof(Sec32), cudaMemcpyDeviceToHost));
+  return SM_OK;
+}
+
+int sm_section_count(sm_context* ctx, int64_t* n) {
+  std::vector<Sec32> top, pool;
+  int rc = fetch_image(ctx, top, pool);
+  if (rc != SM_OK) return rc;
+  int64_t cnt = 0;
+  for (const Sec32& r : top) {
+    if (r.type == SM_EMPTY) continue;
+    cnt++;
+    for (uint32_t b = r.below; b != SM_NIL; b = pool[b].below) cnt++;
+  }
+  *n = cnt;
+  return SM_OK;
+}
+
+int sm_download_columns(sm_context* ctx, int64_t capacity, int64_t* offsets, int32_t* type, double* size,
+                        double* floor_, double* saturation) {
+  std::vector<Sec32> top, pool;
+  int rc = fetch_image(ctx, top, pool);
+  if (rc != SM_OK) return rc;
+  int64_t n = 0;
+  std::vector<const Sec32*> st;
+  for (size_t c = 0; c < top.size(); c++) {
+    offsets[c] = n;
+    st.clear();
+    const Sec32& r = top[c];
+    if (r.type != SM_EMPTY) {
+      st.push_back(&r);
+      for (uint32_t b = r.below; b != SM_NIL; b = pool[b].below) {
+        if (b >= pool.size()) return fail(ctx, SM_ERR_INVALID, "sm_download_columns: corrupt chain");
+        st.push_back(&pool[b]);
+      }
+    }
+    if (n + (int64_t)st.size() > capacity) return fail(ctx, SM_ERR_INVALID, "sm_download_columns: capacity");
+    for (size_t i = st.size(); i-- > 0;) {
+      if (type) type[n] = (int32_t)st[i]->type;
+      if (size) size[n] = st[i]->size;
+      if (floor_) floor_[n] = st[i]->floor;
+      if (saturation) saturation[n] = st[i]->saturation;
+      n++;
+    }
+  }
+  offsets[top.size()] = n;
+  return SM_OK;
+}
+
+int sm_download_height(sm_context* ctx, double* height) {
+  CK(cudaSetDevice(ctx->cfg.device));
+  k_heights<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(ctx->d.top, ctx->d_scratch, nullptr, ctx->cells);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(height, ctx->d_scratch, ctx->cells * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SM_OK;
+}
+
+int sm_download_surface(sm_context* ctx, int32_t* surface) {
+  CK(cudaSetDevice(ctx->cfg.device));
+  k_heights<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(ctx->d.top, nullptr, ctx->d_iscratch, ctx->cells);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(surface, ctx->d_iscratch, ctx->cells * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SM_OK;
+}
+
+int sm_height_sum(sm_context* ctx, double* sum) {
+  CK(cudaSetDevice(ctx->cfg.device));
+  k_height_sum1<<<SUM_BLOCKS, 256, 0, ctx->stream>>>(ctx->d.top, ctx->cells, ctx->d_scratch);
+  k_height_sum2<<<1, 256, 0, ctx->stream>>>(ctx->d_scratch, ctx->d_scratch + SUM_BLOCKS);
+  ctx->launches += 2;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(sum, ctx->d_scratch + SUM_BLOCKS, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SM_OK;
+}
+
+int sm_get_frequency(sm_context* ctx, float* wf, float* wt, float* windf) {
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (wf) CK(cudaMemcpy(wf, ctx->d.wfreq, ctx->cells * 4, cudaMemcpyDeviceToHost));
+  if (wt) CK(cudaMemcpy(wt, ctx->d.wtrack, ctx->cells * 4, cudaMemcpyDeviceToHost));
+  if (windf) CK(cudaMemcpy(windf, ctx->d.windfreq, ctx->cells * 4, cudaMemcpyDeviceToHost));
+  return SM_OK;
+}
+int sm_set_frequency(sm_context* ctx, const float* wf, const float* wt, const float* windf) {
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (wf) CK(cudaMemcpy(ctx->d.wfreq, wf, ctx->cells * 4, cudaMemcpyHostToDevice));
+  if (wt) CK(cudaMemcpy(ctx->d.wtrack, wt, ctx->cells * 4, cudaMemcpyHostToDevice));
+  if (windf) CK(cudaMemcpy(ctx->d.windfreq, windf, ctx->cells * 4, cudaMemcpyHostToDevice));
+  return SM_OK;
+}
+int sm_frequency_update(sm_context* ctx) {
+  CK(cudaSetDevice(ctx->cfg.device));
+  k_frequency_update<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(ctx->d.wfreq, ctx->d.wtrack, ctx->cells);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return SM_OK;
+}
+
+// ---- single-cell operations -----------------------------------------------------------------------
+static int cell_op(sm_context* ctx, const CellOp& o, CellRes* out) {
+  if (ctx->nsoils < 1) return fail(ctx, SM_ERR_INVALID, "soil table not set");
+  CK(cudaSetDevice(ctx->cfg.device));
+  k_cell_op<<<1, 1, 0, ctx->stream>>>(ctx->d, o, ctx->d_cellres);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CellRes r;
+  CK(cudaMemcpyAsync(&r, ctx->d_cellres, sizeof(CellRes), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (out) *out = r;
+  return SM_OK;
+}
+static bool inb(sm_context* ctx, int x, int y) { return x >= 0 && y >= 0 && x < ctx->d.dimx && y < ctx->d.dimy; }
+
+int sm_cell_add(sm_context* ctx, int32_t x, int32_t y, double size, int32_t type) {
+  if (!inb(ctx, x, y) || type < 0 || type >= ctx->nsoils) return fail(ctx, SM_ERR_INVALID, "sm_cell_add: range");
+  return cell_op(ctx, CellOp{0, x, y, 0.f, 0.f, size, type}, nullptr);
+}
+int sm_cell_remove(sm_context* ctx, int32_t x, int32_t y, double h, double* leftover) {
+  if (!inb(ctx, x, y)) return fail(ctx, SM_ERR_INVALID, "sm_cell_remove: range");
+  CellRes r;
+  int rc = cell_op(ctx, CellOp{1, x, y, 0.f, 0.f, h, 0}, &r);
+  if (rc == SM_OK && leftover) *leftover = r.d;
+  return rc;
+}
+int sm_cell_cascade(sm_context* ctx, float x, float y, int32_t transferloop) {
+  if (!inb(ctx, (int)roundf(x), (int)roundf(y)) || transferloop < 0 || transferloop > 3)
+    return fail(ctx, SM_ERR_INVALID, "sm_cell_cascade: range (transferloop 0..3)");
+  return cell_op(ctx, CellOp{2, 0, 0, x, y, 0.0, transferloop}, nullptr);
+}
+int sm_cell_query(sm_context* ctx, int32_t x, int32_t y, double* height, int32_t* surface, float* normal3) {
+  if (!inb(ctx, x, y)) return fail(ctx, SM_ERR_INVALID, "sm_cell_query: range");
+  CellRes r;
+  int rc = cell_op(ctx, CellOp{3, x, y, 0.f, 0.f, 0.0, 0}, &r);
+  if (rc != SM_OK) return rc;
+  if (height) *height = r.d;
+  if (surface) *surface = r.surface;
+  if (normal3) { normal3[0] = r.n[0]; normal3[1] = r.n[1]; normal3[2] = r.n[2]; }
+  return SM_OK;
+}
+int sm_height_bilinear(sm_context* ctx, float x, float y, double* height) {
+  if (!(x >= 0.f && y >= 0.f && x < (float)(ctx->d.dimx - 1) && y < (float)(ctx->d.dimy - 1)))
+    return fail(ctx, SM_ERR_INVALID, "sm_height_bilinear: range");
+  CellRes r;
+  int rc = cell_op(ctx, CellOp{4, 0, 0, x, y, 0.0, 0}, &r);
+  if (rc == SM_OK && height) *height = r.d;
+  return rc;
+}
+
+// ---- the hot path -----------------------------------------------------------------------------------
+static int launch_run(sm_context* ctx, int kind, int n, const float* d_spawn, int max_sweeps) {
+  if (ctx->nsoils < 1) return fail(ctx, SM_ERR_INVALID, "soil table not set");
+  if (n < 0 || n > ctx->max_particles) return fail(ctx, SM_ERR_INVALID, "batch larger than max_particles");
+  CK(cudaSetDevice(ctx->cfg.device));
+  const int threads = 256;
+  const int maxblocks = ctx->num_sms * ctx->occ[kind];
+  const long long capacity = (long long)maxblocks * threads;
+  int lshift = 0;
+  {
+    const char* e = getenv("SM_LANES");
+    int want = e ? atoi(e) : 8;
+    while ((1 << (lshift + 1)) <= want && (long long)std::max(n, 1) * (1 << (lshift + 1)) <= capacity) lshift++;
+  }
+  long long need_threads = (long long)std::max(n, 1) << lshift;
+  int blocks = (int)std::min<long long>(maxblocks, (need_threads + threads - 1) / threads);
+  if (blocks < 1) blocks = 1;
+  DevCtx d = ctx->d;
+  if (max_sweeps <= 0) max_sweeps = -1;            // run until every particle is dead
+  if (max_sweeps == SM_SWEEPS_NONE) max_sweeps = 0;  // prologue only (the *_begin calls)
+  void* args[] = {&d, &n, (void*)&d_spawn, &max_sweeps, &lshift};
+  CK(cudaMemsetAsync(ctx->d.ctl, 0, 4 * sizeof(unsigned int), ctx->stream));  // barrier + alive_slot[3]
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  if (kind == KIND_WATER)
+    CK(cudaLaunchCooperativeKernel((void*)k_run<KIND_WATER>, dim3(blocks), dim3(threads), args, 0, ctx->stream));
+  else
+    CK(cudaLaunchCooperativeKernel((void*)k_run<KIND_WIND>, dim3(blocks), dim3(threads), args, 0, ctx->stream));
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->launches++;
+  ctx->timing_pending = true;
+  return SM_OK;
+}
+
+static int zero_counters(sm_context* ctx) {
+  // steps..alive are contiguous in RunCtl
+  CK(cudaMemsetAsync(&ctx->d.ctl->steps, 0, 7 * sizeof(unsigned long long), ctx->stream));
+  return SM_OK;
+}
+
+int sm_last_stats(sm_context* ctx, sm_stats* st) {
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaMemcpyAsync(ctx->h_ctl, ctx->d.ctl, sizeof(RunCtl), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const RunCtl& h = *ctx->h_ctl;
+  float ms = 0.f;
+  if (ctx->timing_pending) CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  if (st) {
+    st->steps = (int64_t)h.steps; st->sweeps = (int64_t)h.sweeps; st->exit_oob = (int64_t)h.exit_oob;
+    st->exit_evap = (int64_t)h.exit_evap; st->exit_stall = (int64_t)h.exit_stall;
+    st->pool_drops = (int64_t)h.drops; st->alive = (int64_t)h.alive; st->device_ms = ms;
+  }
+  if (h.err & (1u << 4)) return fail(ctx, SM_ERR_REACH, "a particle step left its conflict box");
+  if (h.err & (1u << 3)) return fail(ctx, SM_ERR_POOL, "section pool exhausted (sections were dropped)");
+  return SM_OK;
+}
+
+static int run_host(sm_context* ctx, int kind, int n, const float* spawn_xy, int max_sweeps, sm_stats* st) {
+  if (n > 0 && !spawn_xy) return fail(ctx, SM_ERR_INVALID, "null spawn list");
+  if (n < 0 || n > ctx->max_particles) return fail(ctx, SM_ERR_INVALID, "batch larger than max_particles");
+  CK(cudaSetDevice(ctx->cfg.device));
+  if (n) CK(cudaMemcpyAsync(ctx->d_spawn, spawn_xy, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = zero_counters(ctx);
+  if (rc != SM_OK) return rc;
+  ctx->cur_kind = kind; ctx->cur_n = n;
+  rc = launch_run(ctx, kind, n, ctx->d_spawn, max_sweeps);
+  if (rc != SM_OK) return rc;
+  return sm_last_stats(ctx, st);
+}
+
+int sm_water_run(sm_context* ctx, int32_t n, const float* xy, int32_t max_sweeps, sm_stats* st) {
+  return run_host(ctx, KIND_WATER, n, xy, max_sweeps, st);
+}
+int sm_wind_run(sm_context* ctx, int32_t n, const float* xy, int32_t max_sweeps, sm_stats* st) {
+  return run_host(ctx, KIND_WIND, n, xy, max_sweeps, st);
+}
+int sm_water_run_device(sm_context* ctx, int32_t n, const float* d_xy, int32_t max_sweeps) {
+  int rc = zero_counters(ctx);
+  if (rc != SM_OK) return rc;
+  ctx->cur_kind = KIND_WATER; ctx->cur_n = n;
+  return launch_run(ctx, KIND_WATER, n, d_xy, max_sweeps);
+}
+int sm_wind_run_device(sm_context* ctx, int32_t n, const float* d_xy, int32_t max_sweeps) {
+  int rc = zero_counters(ctx);
+  if (rc != SM_OK) return rc;
+  ctx->cur_kind = KIND_WIND; ctx->cur_n = n;
+  return launch_run(ctx, KIND_WIND, n, d_xy, max_sweeps);
+}
+
+// stepping interface: *_begin runs the prologue only (spawn + bins), *_sweeps(k) resumes the batch
+int sm_water_begin(sm_context* ctx, int32_t n, const float* xy) {
+  return run_host(ctx, KIND_WATER, n, xy, SM_SWEEPS_NONE, nullptr);
+}
+int sm_wind_begin(sm_context* ctx, int32_t n, const float* xy) {
+  return run_host(ctx, KIND_WIND, n, xy, SM_SWEEPS_NONE, nullptr);
+}
+static int sweeps_k(sm_context* ctx, int kind, int k, sm_stats* st) {
+  if (ctx->cur_kind != kind) return fail(ctx, SM_ERR_INVALID, "no batch of this kind in flight");
+  if (k <= 0) return fail(ctx, SM_ERR_INVALID, "k must be positive");
+  int rc = zero_counters(ctx);
+  if (rc != SM_OK) return rc;
+  rc = launch_run(ctx, kind, ctx->cur_n, nullptr, k);
+  if (rc != SM_OK) return rc;
+  return sm_last_stats(ctx, st);
+}
+int sm_water_sweeps(sm_context* ctx, int32_t k, sm_stats* st) { return sweeps_k(ctx, KIND_WATER, k, st); }
+int sm_wind_sweeps(sm_context* ctx, int32_t k, sm_stats* st) { return sweeps_k(ctx, KIND_WIND, k, st); }
+
+static int fetch_state(sm_context* ctx, int kind, std::vector<float4>& a, std::vector<double2>& b,
+                       std::vector<uint2>& c, std::vector<unsigned char>& al) {
+  if (ctx->cur_kind != kind) return fail(ctx, SM_ERR_INVALID, "no batch of this kind in flight");
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const size_t n = (size_t)ctx->cur_n;
+  a.resize(n); b.resize(n); c.resize(n); al.resize(n);
+  if (!n) return SM_OK;
+  CK(cudaMemcpy(a.data(), ctx->d.pa, n * sizeof(float4), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(b.data(), ctx->d.pb, n * sizeof(double2), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(c.data(), ctx->d.pc, n * sizeof(uint2), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(al.data(), ctx->d.alive, n, cudaMemcpyDeviceToHost));
+  return SM_OK;
+}
+int sm_water_state(sm_context* ctx, float* pos2, float* speed2, double* volume, double* sediment,
+                   int32_t* contains, int32_t* alive) {
+  std::vector<float4> a; std::vector<double2> b; std::vector<uint2> c; std::vector<unsigned char> al;
+  int rc = fetch_state(ctx, KIND_WATER, a, b, c, al);
+  if (rc != SM_OK) return rc;
+  for (size_t i = 0; i < a.size(); i++) {
+    if (pos2) { pos2[2 * i] = a[i].x; pos2[2 * i + 1] = a[i].y; }
+    if (speed2) { speed2[2 * i] = a[i].z; speed2[2 * i + 1] = a[i].w; }
+    if (volume) volume[i] = b[i].x;
+    if (sediment) sediment[i] = b[i].y;
+    if (contains) contains[i] = (int32_t)c[i].x;
+    if (alive) alive[i] = al[i];
+  }
+  return SM_OK;
+}
+int sm_wind_state(sm_context* ctx, float* pos2, float* speed3, double* height, double* sediment,
+                  int32_t* contains, int32_t* alive) {
+  std::vector<float4> a; std::vector<double2> b; std::vector<uint2> c; std::vector<unsigned char> al;
+  int rc = fetch_state(ctx, KIND_WIND, a, b, c, al);
+  if (rc != SM_OK) return rc;
+  for (size_t i = 0; i < a.size(); i++) {
+    if (pos2) { pos2[2 * i] = a[i].x; pos2[2 * i + 1] = a[i].y; }
+    if (speed3) {
+      speed3[3 * i] = a[i].z; speed3[3 * i + 1] = a[i].w;
+      float sz; memcpy(&sz, &c[i].y, 4); speed3[3 * i + 2] = sz;
+    }
+    if (sediment) sediment[i] = b[i].x;
+    if (height) height[i] = b[i].y;
+    if (contains) contains[i] = (int32_t)c[i].x;
+    if (alive) alive[i] = al[i];
+  }
+  return SM_OK;
+}
+
+int sm_launch_count(sm_context* ctx, int64_t* n) { *n = ctx->launches; return SM_OK; }
+int sm_device_alloc(sm_context* ctx, int64_t bytes, void** dptr) {
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaMalloc(dptr, (size_t)bytes));
+  return SM_OK;
+}
+int sm_device_free(sm_context* ctx, void* dptr) {
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaFree(dptr));
+  return SM_OK;
+}
+int sm_device_upload(sm_context* ctx, void* dptr, const void* host, int64_t bytes) {
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaMemcpyAsync(dptr, host, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SM_OK;
+}
+
+int sm_initialize(sm_context* ctx, int32_t, const sm_layer*, int32_t) {
+  return fail(ctx, SM_ERR_INVALID, "sm_initialize: not built yet");
+}
+
+}  // extern "C"
