@@ -1,0 +1,118 @@
+"""GPU parity: the CUDA hot path through the C ABI vs the reference's own functions driven in
+lockstep (oracle/_ref).  Bit-exact on every per-cell quantity (heights, every section of every
+column, frequency/track maps), on every particle's state and on the exit counters."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(ref, soil, dim, seed=42):
+    import soilmachine_b200 as smb
+    ref.init(soil, seed=seed, dimx=dim, dimy=dim, poolsize=dim * dim * 4 + 2000000)
+    ctx = smb.Context(ref.dimx, ref.dimy, ref.scale, max_particles=65536)
+    ctx.set_soils(ref.soils())
+    cols = ref.columns()
+    ctx.upload_columns(cols["offsets"], cols["type"], cols["size"], cols["saturation"])
+    return ctx, cols
+
+
+def _same(a, b, what):
+    a = np.ascontiguousarray(a); b = np.ascontiguousarray(b)
+    assert a.shape == b.shape, what
+    if not np.array_equal(a.view(np.uint8), b.view(np.uint8)):
+        bad = np.nonzero(a.reshape(-1) != b.reshape(-1))[0]
+        raise AssertionError("%s differs at %d entries, first %s: %r vs %r" %
+                             (what, len(bad), bad[:4], a.reshape(-1)[bad[:4]], b.reshape(-1)[bad[:4]]))
+
+
+def _compare_maps(ref, ctx):
+    _same(ref.heights(), ctx.heights(), "height")
+    c1, c2 = ref.columns(), ctx.download_columns()
+    for k in ("offsets", "type", "size", "floor", "saturation"):
+        _same(c1[k], c2[k], "columns." + k)
+    f1, f2 = ref.frequency(), ctx.frequency()
+    for k in f1:
+        _same(f1[k], f2[k], k)
+
+
+def test_upload_download_roundtrip(ref):
+    ctx, cols = _setup(ref, "rockgravelpebblessand", 64)
+    got = ctx.download_columns()
+    for k in ("offsets", "type", "size", "floor", "saturation"):
+        _same(cols[k], got[k], k)
+    _same(ref.heights(), ctx.heights(), "height")
+    _same(ref.surfaces(), ctx.surfaces(), "surface")
+    assert abs(ctx.height_sum() - ref.heights().sum()) < 1e-6
+
+
+@pytest.mark.parametrize("soil,dim,n", [("default", 64, 64), ("rocksand", 96, 256)])
+def test_water_stepwise(ref, soil, dim, n):
+    ctx, _ = _setup(ref, soil, dim)
+    xy = ref.spawn_list(n, seed=7)
+    ref.water_begin(xy); ctx.water_begin(xy)
+    for k in ("pos", "speed", "volume", "sediment", "contains", "alive"):
+        _same(ref.water_state()[k], ctx.water_state()[k], "spawn." + k)
+    for sweep in range(40):
+        alive, _ = ref.water_sweep()
+        st = ctx.water_sweeps(1)
+        s1, s2 = ref.water_state(), ctx.water_state()
+        for k in s1:
+            _same(s1[k], s2[k], "sweep %d %s" % (sweep, k))
+        assert st.alive == alive
+    _compare_maps(ref, ctx)
+
+
+@pytest.mark.parametrize("soil,dim,n", [
+    ("default", 256, 1000), ("rocksand", 256, 2000), ("rockgravelpebblessand", 256, 2000),
+    ("bigbutte", 256, 2000), ("rockgravelpebbles_big", 192, 1500)])
+def test_water_run(ref, soil, dim, n):
+    ctx, _ = _setup(ref, soil, dim)
+    xy = ref.spawn_list(n, seed=42)
+    r = ref.water_run(xy)
+    g = ctx.water_run(xy)
+    assert (g.steps, g.sweeps, g.exit_oob, g.exit_evap, g.exit_stall) == \
+        (r.steps, r.sweeps, r.exit_oob, r.exit_evap, r.exit_stall)
+    assert g.alive == 0 and g.pool_drops == 0
+    _compare_maps(ref, ctx)
+    s1, s2 = ref.water_state(), ctx.water_state()
+    for k in s1:
+        _same(s1[k], s2[k], "final " + k)
+
+
+@pytest.mark.parametrize("soil,dim,n", [("rocksand", 256, 1000), ("rockgravelpebblessand", 256, 1500)])
+def test_wind_run(ref, soil, dim, n):
+    ctx, _ = _setup(ref, soil, dim)
+    xy = ref.spawn_list(n, seed=43)
+    r = ref.wind_run(xy)
+    g = ctx.wind_run(xy)
+    assert (g.steps, g.exit_oob) == (r.steps, r.exit_oob)
+    _compare_maps(ref, ctx)
+    s1, s2 = ref.wind_state(), ctx.wind_state()
+    for k in s1:
+        _same(s1[k], s2[k], "final " + k)
+
+
+def test_frame_sequence(ref):
+    """water batch, wind batch, frequency update - three frames (SoilMachine.cpp:287-320 without
+    flood/seep)."""
+    ctx, _ = _setup(ref, "rocksand", 192)
+    ref.lib.smref_srand(99)
+    for frame in range(3):
+        xw = ref.spawn_list(600); xd = ref.spawn_list(300)
+        ref.water_run(xw); ctx.water_run(xw)
+        ref.wind_run(xd); ctx.wind_run(xd)
+        ref.frequency_update(); ctx.frequency_update()
+        _compare_maps(ref, ctx)
+
+
+def test_determinism(ref):
+    ctx, cols = _setup(ref, "rockgravelpebblessand", 128)
+    xy = ref.spawn_list(1500, seed=5)
+    ctx.water_run(xy)
+    h1 = ctx.heights().copy()
+    ctx.upload_columns(cols["offsets"], cols["type"], cols["size"], cols["saturation"])
+    ctx.set_frequency(np.zeros(ctx.cells, np.float32), np.zeros(ctx.cells, np.float32),
+                      np.zeros(ctx.cells, np.float32))
+    ctx.water_run(xy)
+    _same(h1, ctx.heights(), "height (run twice)")
