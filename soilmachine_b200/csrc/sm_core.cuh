@@ -234,6 +234,7 @@ template <int DEPTH, class A> struct Cascade {
     int sx[8], sy[8];
     double sh[8];
     int num = 0;
+    a.cascade_prefetch(cx, cy);
     SM_UNROLL1
     for (int i = 0; i < 8; i++) {
       int nx = cx + ox[i], ny = cy + oy[i];

@@ -50,8 +50,7 @@ struct DevCtx {
   unsigned char* alive;
   unsigned int* done;            // tag of the last sweep this particle completed (0xFFFFFFFF = dead)
   unsigned long long* head[2];   // bin heads per sweep parity
-  uint32_t* next[2];
-  uint32_t* key[2];              // ipos packed x<<16|y
+  uint2* node[2];                // per particle: .x = next particle in the bin list, .y = ipos x<<16|y
   int nbx, nby;                  // allocated bin grid (for the smallest bin edge)
 };
 
@@ -93,6 +92,7 @@ struct DevAccess {
   __device__ __forceinline__ void begin(int, int) {}
   __device__ __forceinline__ void target(int, int) {}
   __device__ __forceinline__ void dirty(int, int) {}
+  __device__ __forceinline__ void cascade_prefetch(int, int) {}
   __device__ __forceinline__ Sec32 pool_load(uint32_t i) { return c.pool[i]; }
   __device__ __forceinline__ void pool_store(uint32_t i, const Sec32& r) { c.pool[i] = r; }
   __device__ uint32_t pool_alloc() {
@@ -121,5 +121,126 @@ struct DevAccess {
   __device__ __forceinline__ float water_frequency(int ind) { return c.wfreq[ind]; }
   __device__ __forceinline__ void wind_frequency_touch(int ind) {    // wind.h:49-52
     c.windfreq[ind] = (float)(0.5 * c.windfreq[ind] + 0.5f);
+  }
+};
+
+
+// ---- accessor: shared-memory window ---------------------------------------------------------------
+// The records a particle-step touches are staged in shared memory: patch A = the 3x3 block around
+// ipos (slots 0-8; move() reads its plus-shaped subset), patch B = the 3x3 block around the new
+// position (slots 9-17; bilinear height + cascade).  A cell inside both patches always resolves to
+// patch A.  Records are pulled from L2 with cp.async (16-byte .cg copies straight into shared
+// memory, all in flight at once), modified in place and written back once at the end of the step.
+// Cells outside both patches (only the re-cascade of a wind step reaches them) are accessed in
+// global memory directly.
+#define SM_WIN_SLOTS 18
+#define SM_WIN_BYTES (SM_WIN_SLOTS * 32)
+#define SM_PLUS_MASK 186u   // (1<<1)|(1<<3)|(1<<4)|(1<<5)|(1<<7): the 5-point stencil inside a 3x3 patch
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+template <int KIND_>
+struct WinAccess {
+  const DevCtx& c;
+  const SoilDev* s_soils;
+  Sec32* win;               // SM_WIN_SLOTS records in shared memory, private to this particle
+  unsigned int phase;
+  int ax, ay, bx, by;
+  uint32_t valid, dirtym;
+  bool has_b;
+  float f_freq, f_track;    // water: frequency/track at ipos | wind: wind frequency at ipos
+  __device__ __forceinline__ WinAccess(const DevCtx& ctx, const SoilDev* ss, unsigned int ph, Sec32* w)
+      : c(ctx), s_soils(ss), win(w), phase(ph & 1u), ax(0), ay(0), bx(0), by(0), valid(0), dirtym(0),
+        has_b(false), f_freq(0.f), f_track(0.f) {}
+  __device__ __forceinline__ int dimx() const { return c.dimx; }
+  __device__ __forceinline__ int dimy() const { return c.dimy; }
+  __device__ __forceinline__ int scale() const { return c.scale; }
+  __device__ __forceinline__ SoilDev soil(uint32_t t) const { return s_soils[t]; }
+
+  // issue the copies for the wanted cells of one patch (no wait)
+  __device__ __forceinline__ void issue_patch(int ox, int oy, int base, uint32_t want) {
+    uint32_t got = 0;
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+      const int x = ox + k / 3 - 1, y = oy + k % 3 - 1;
+      bool need = ((want >> k) & 1u) && !((valid >> (base + k)) & 1u) && x >= 0 && y >= 0 &&
+                  x < c.dimx && y < c.dimy;
+      if (base == 9 && need) {
+        const int dx = x - ax + 1, dy = y - ay + 1;
+        if ((unsigned)dx < 3u && (unsigned)dy < 3u) need = false;   // resolves to patch A
+      }
+      if (need) {
+        const Sec32* src = &c.top[(size_t)x * c.dimy + y];
+        cp_async16(&win[base + k], src);
+        cp_async16(((char*)&win[base + k]) + 16, ((const char*)src) + 16);
+        got |= 1u << k;
+      }
+    }
+    valid |= got << base;
+  }
+  __device__ __forceinline__ void begin(int ix, int iy) {
+    ax = ix; ay = iy; has_b = false; valid = 0; dirtym = 0;
+    issue_patch(ix, iy, 0, SM_PLUS_MASK);
+    const int ind = iy * c.dimx + ix;
+    if (KIND_ == 0) { f_freq = c.wfreq[ind]; f_track = c.wtrack[ind]; }
+    else { f_freq = c.windfreq[ind]; }
+    cp_async_wait_all();
+  }
+  __device__ __forceinline__ void target(int nx, int ny) {
+    bx = nx; by = ny; has_b = true;
+    issue_patch(nx, ny, 9, 0x1FFu);
+    cp_async_wait_all();
+  }
+  __device__ __forceinline__ void cascade_prefetch(int cx, int cy) {
+    if (cx == ax && cy == ay) { issue_patch(ax, ay, 0, 0x1FFu); cp_async_wait_all(); }
+    else if (has_b && cx == bx && cy == by) { issue_patch(bx, by, 9, 0x1FFu); cp_async_wait_all(); }
+  }
+  __device__ __forceinline__ int slot_of(int x, int y) const {
+    int dx = x - ax + 1, dy = y - ay + 1;
+    if ((unsigned)dx < 3u && (unsigned)dy < 3u) return dx * 3 + dy;
+    if (has_b) {
+      dx = x - bx + 1; dy = y - by + 1;
+      if ((unsigned)dx < 3u && (unsigned)dy < 3u) return 9 + dx * 3 + dy;
+    }
+    return -1;
+  }
+  __device__ __forceinline__ Sec32* rec(int x, int y) {
+    const int s = slot_of(x, y);
+    Sec32* g = &c.top[(size_t)x * c.dimy + y];
+    if (s < 0) return g;
+    if (!((valid >> s) & 1u)) { win[s] = *g; valid |= 1u << s; }
+    return &win[s];
+  }
+  __device__ __forceinline__ void dirty(int x, int y) {
+    const int s = slot_of(x, y);
+    if (s >= 0) dirtym |= 1u << s;
+  }
+  // write the modified records back (end of step)
+  __device__ __forceinline__ void flush() {
+    uint32_t m = dirtym;
+    while (m) {
+      const int s = __ffs(m) - 1;
+      m &= m - 1;
+      int x, y;
+      if (s < 9) { x = ax + s / 3 - 1; y = ay + s % 3 - 1; }
+      else { x = bx + (s - 9) / 3 - 1; y = by + (s - 9) % 3 - 1; }
+      c.top[(size_t)x * c.dimy + y] = win[s];
+    }
+    dirtym = 0;
+  }
+  __device__ __forceinline__ Sec32 pool_load(uint32_t i) { return c.pool[i]; }
+  __device__ __forceinline__ void pool_store(uint32_t i, const Sec32& r) { c.pool[i] = r; }
+  __device__ uint32_t pool_alloc() { DevAccess d(c, s_soils, phase); return d.pool_alloc(); }
+  __device__ void pool_free(uint32_t i) { DevAccess d(c, s_soils, phase); d.pool_free(i); }
+  __device__ __forceinline__ void track_add(int ind, double v) {     // water.h:348-351
+    c.wtrack[ind] = (float)(f_track + v);
+  }
+  __device__ __forceinline__ float water_frequency(int) { return f_freq; }
+  __device__ __forceinline__ void wind_frequency_touch(int ind) {    // wind.h:49-52
+    c.windfreq[ind] = (float)(0.5 * f_freq + 0.5f);
   }
 };

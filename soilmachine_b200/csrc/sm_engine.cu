@@ -39,55 +39,47 @@ __device__ __forceinline__ void bin_insert(const DevCtx& c, unsigned int tag, in
   const int G = Reach<KIND>::G;
   const int nby = (c.dimy + G - 1) / G;
   const int b = (ix / G) * nby + (iy / G);
-  c.key[par][pid] = ((uint32_t)ix << 16) | (uint32_t)iy;
   unsigned long long old =
       atomicExch(&c.head[par][b], ((unsigned long long)tag << 32) | (unsigned long long)(uint32_t)pid);
-  c.next[par][pid] = ((unsigned int)(old >> 32) == tag) ? (uint32_t)old : SM_NIL;
+  c.node[par][pid] = make_uint2(((unsigned int)(old >> 32) == tag) ? (uint32_t)old : SM_NIL,
+                                ((uint32_t)ix << 16) | (uint32_t)iy);
 }
 
 // Wait until every lower-index live particle whose conflict box overlaps mine has finished sweep
-// `tag`.  Lists were completed before the grid barrier that opened this sweep.
+// `tag`.  Lists were completed before the grid barrier that opened this sweep.  Single pass: each
+// in-range lower-index particle is polled where it is met in the list (all of them must finish
+// anyway, so the order of polling does not matter).
 template <int KIND>
 __device__ __forceinline__ void wait_blockers(const DevCtx& c, unsigned int tag, int pid, int ix, int iy) {
   const unsigned int par = tag & 1u;
   const int G = Reach<KIND>::G, D = Reach<KIND>::D;
   const int nbx = (c.dimx + G - 1) / G, nby = (c.dimy + G - 1) / G;
   const int bx = ix / G, by = iy / G;
-  const int K = 8;
-  uint32_t list[K];
-  for (;;) {
-    int found = 0;
-    bool more = false;
-    for (int dbx = -1; dbx <= 1; dbx++) {
-      const int cx = bx + dbx;
-      if (cx < 0 || cx >= nbx) continue;
-      for (int dby = -1; dby <= 1; dby++) {
-        const int cy = by + dby;
-        if (cy < 0 || cy >= nby) continue;
-        unsigned long long h = *((volatile unsigned long long*)&c.head[par][cx * nby + cy]);
-        if ((unsigned int)(h >> 32) != tag) continue;
-        uint32_t j = (uint32_t)h;
-        while (j != SM_NIL) {
-          const uint32_t nxt = c.next[par][j];
-          if (j < (uint32_t)pid) {
-            const uint32_t k = c.key[par][j];
-            int dx = (int)(k >> 16) - ix, dy = (int)(k & 0xFFFFu) - iy;
-            dx = dx < 0 ? -dx : dx;
-            dy = dy < 0 ? -dy : dy;
-            if (dx <= D && dy <= D && ld_volatile_u32(&c.done[j]) < tag) {
-              if (found < K) list[found++] = j;
-              else more = true;
-            }
-          }
-          j = nxt;
+  // the (at most 9) bin heads are independent loads: fetch them all first
+  unsigned long long heads[9];
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    const int cx = bx + k / 3 - 1, cy = by + k % 3 - 1;
+    heads[k] = (cx >= 0 && cx < nbx && cy >= 0 && cy < nby)
+                   ? *((volatile unsigned long long*)&c.head[par][cx * nby + cy]) : 0ull;
+  }
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    const unsigned long long h = heads[k];
+    if ((unsigned int)(h >> 32) != tag) continue;
+    uint32_t j = (uint32_t)h;
+    while (j != SM_NIL) {
+      const uint2 nd = c.node[par][j];
+      if (j < (uint32_t)pid) {
+        int dx = (int)(nd.y >> 16) - ix, dy = (int)(nd.y & 0xFFFFu) - iy;
+        dx = dx < 0 ? -dx : dx;
+        dy = dy < 0 ? -dy : dy;
+        if (dx <= D && dy <= D) {
+          while (ld_volatile_u32(&c.done[j]) < tag) { __nanosleep(20); }
         }
       }
+      j = nd.x;
     }
-    if (found == 0) break;
-    for (int i = 0; i < found; i++) {
-      while (ld_volatile_u32(&c.done[list[i]]) < tag) { __nanosleep(40); }
-    }
-    if (!more) break;
   }
 }
 
@@ -116,8 +108,8 @@ __device__ __forceinline__ void store_particle(const DevCtx& c, int pid, const W
 template <int KIND> struct PType { typedef WaterP T; };
 template <> struct PType<KIND_WIND> { typedef WindP T; };
 
-__device__ __forceinline__ int do_step(DevAccess& a, WaterP& p) { return water_step(a, p); }
-__device__ __forceinline__ int do_step(DevAccess& a, WindP& p) { return wind_step(a, p); }
+template <class A> __device__ __forceinline__ int do_step(A& a, WaterP& p) { return water_step(a, p); }
+template <class A> __device__ __forceinline__ int do_step(A& a, WindP& p) { return wind_step(a, p); }
 
 // ---------------------------------------------------------------------------------------------
 // the persistent sweep kernel
@@ -128,9 +120,11 @@ __global__ void __launch_bounds__(256) k_run(DevCtx c, int n, const float* __res
   typedef typename PType<KIND>::T P;
   __shared__ SoilDev s_soils[SM_MAX_SOILS];
   __shared__ unsigned int s_alive;
+  extern __shared__ __align__(32) unsigned char s_win[];   // (blockDim.x >> lshift) windows
   for (int i = threadIdx.x; i < c.nsoils; i += blockDim.x) s_soils[i] = c.soils[i];
   if (threadIdx.x == 0) s_alive = 0;
   __syncthreads();
+  Sec32* my_win = (Sec32*)(s_win + (size_t)(threadIdx.x >> lshift) * SM_WIN_BYTES);
 
   RunCtl* ctl = c.ctl;
   unsigned int epoch = 0;
@@ -204,8 +198,9 @@ __global__ void __launch_bounds__(256) k_run(DevCtx c, int n, const float* __res
         const int ix = (int)roundf(p.px), iy = (int)roundf(p.py);
         wait_blockers<KIND>(c, tag, pid, ix, iy);
         __threadfence();
-        DevAccess a(c, s_soils, tag);
+        WinAccess<KIND> a(c, s_soils, tag, my_win);
         const int r = do_step(a, p);
+        a.flush();
         store_particle(c, pid, p);
         if (r == SM_ALIVE) {
           n_steps++;
@@ -340,7 +335,6 @@ struct sm_context {
   int cur_kind = -1, cur_n = 0;
   bool timing_pending = false;
   int num_sms = 0;
-  int occ[2] = {0, 0};
 };
 
 static std::string g_create_err;
@@ -379,7 +373,7 @@ void sm_destroy(sm_context* ctx) {
   cudaFree(d.top); cudaFree(d.pool); cudaFree(d.ringbuf[0]); cudaFree(d.ringbuf[1]);
   cudaFree(d.wfreq); cudaFree(d.wtrack); cudaFree(d.windfreq); cudaFree(ctx->d_soils);
   cudaFree(d.ctl); cudaFree(d.pa); cudaFree(d.pb); cudaFree(d.pc); cudaFree(d.alive); cudaFree(d.done);
-  for (int i = 0; i < 2; i++) { cudaFree(d.head[i]); cudaFree(d.next[i]); cudaFree(d.key[i]); }
+  for (int i = 0; i < 2; i++) { cudaFree(d.head[i]); cudaFree(d.node[i]); }
   cudaFree(ctx->d_spawn); cudaFree(ctx->d_scratch); cudaFree(ctx->d_iscratch); cudaFree(ctx->d_cellres);
   if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -441,7 +435,7 @@ int sm_create(const sm_config* cfg, sm_context** out) {
     for (int i = 0; i < 2; i++) {
       CK(cudaMalloc(&d.head[i], (size_t)d.nbx * d.nby * 8));
       CK(cudaMemsetAsync(d.head[i], 0, (size_t)d.nbx * d.nby * 8, ctx->stream));
-      CK(cudaMalloc(&d.next[i], N * 4)); CK(cudaMalloc(&d.key[i], N * 4));
+      CK(cudaMalloc(&d.node[i], N * sizeof(uint2)));
     }
     CK(cudaMalloc(&ctx->d_spawn, N * 8));
     CK(cudaMalloc(&ctx->d_scratch, std::max(C, (size_t)SUM_BLOCKS + 8) * 8));
@@ -461,9 +455,8 @@ int sm_create(const sm_config* cfg, sm_context** out) {
     int rcp = alloc_pool(ctx, cfg->pool_capacity > 0 ? (unsigned long long)cfg->pool_capacity
                                                      : (unsigned long long)C + (4ull << 20));
     if (rcp != SM_OK) return rcp;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ[0], k_run<KIND_WATER>, 256, 0));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ[1], k_run<KIND_WIND>, 256, 0));
-    if (ctx->occ[0] < 1 || ctx->occ[1] < 1) return fail(ctx, SM_ERR_CUDA, "sweep kernel does not fit an SM");
+    CK(cudaFuncSetAttribute(k_run<KIND_WATER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * SM_WIN_BYTES));
+    CK(cudaFuncSetAttribute(k_run<KIND_WIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * SM_WIN_BYTES));
     CK(cudaStreamSynchronize(ctx->stream));
     return SM_OK;
   }();
@@ -721,17 +714,29 @@ static int launch_run(sm_context* ctx, int kind, int n, const float* d_spawn, in
   if (n < 0 || n > ctx->max_particles) return fail(ctx, SM_ERR_INVALID, "batch larger than max_particles");
   CK(cudaSetDevice(ctx->cfg.device));
   const int threads = 256;
-  const int maxblocks = ctx->num_sms * ctx->occ[kind];
-  const long long capacity = (long long)maxblocks * threads;
-  int lshift = 0;
+  // lanes per particle (a power of two): only the first lane of each group carries a particle, which
+  // keeps divergent particle-steps out of each other's warps and shrinks the window footprint
+  int lshift = 0, blocks = 1;
+  size_t smem = 0;
   {
     const char* e = getenv("SM_LANES");
     int want = e ? atoi(e) : 8;
-    while ((1 << (lshift + 1)) <= want && (long long)std::max(n, 1) * (1 << (lshift + 1)) <= capacity) lshift++;
+    int ls = 0;
+    while ((1 << (ls + 1)) <= want && ls < 5) ls++;
+    for (;; ls--) {
+      smem = (size_t)(threads >> ls) * SM_WIN_BYTES;
+      int occ = 0;
+      if (kind == KIND_WATER) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run<KIND_WATER>, threads, smem));
+      else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run<KIND_WIND>, threads, smem));
+      if (occ < 1) return fail(ctx, SM_ERR_CUDA, "sweep kernel does not fit an SM");
+      const long long maxblocks = (long long)ctx->num_sms * occ;
+      const long long need_threads = (long long)std::max(n, 1) << ls;
+      lshift = ls;
+      blocks = (int)std::min<long long>(maxblocks, (need_threads + threads - 1) / threads);
+      if (need_threads <= maxblocks * threads || ls == 0) break;   // every particle has its own thread
+    }
+    if (blocks < 1) blocks = 1;
   }
-  long long need_threads = (long long)std::max(n, 1) << lshift;
-  int blocks = (int)std::min<long long>(maxblocks, (need_threads + threads - 1) / threads);
-  if (blocks < 1) blocks = 1;
   DevCtx d = ctx->d;
   if (max_sweeps <= 0) max_sweeps = -1;            // run until every particle is dead
   if (max_sweeps == SM_SWEEPS_NONE) max_sweeps = 0;  // prologue only (the *_begin calls)
@@ -739,9 +744,9 @@ static int launch_run(sm_context* ctx, int kind, int n, const float* d_spawn, in
   CK(cudaMemsetAsync(ctx->d.ctl, 0, 4 * sizeof(unsigned int), ctx->stream));  // barrier + alive_slot[3]
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   if (kind == KIND_WATER)
-    CK(cudaLaunchCooperativeKernel((void*)k_run<KIND_WATER>, dim3(blocks), dim3(threads), args, 0, ctx->stream));
+    CK(cudaLaunchCooperativeKernel((void*)k_run<KIND_WATER>, dim3(blocks), dim3(threads), args, smem, ctx->stream));
   else
-    CK(cudaLaunchCooperativeKernel((void*)k_run<KIND_WIND>, dim3(blocks), dim3(threads), args, 0, ctx->stream));
+    CK(cudaLaunchCooperativeKernel((void*)k_run<KIND_WIND>, dim3(blocks), dim3(threads), args, smem, ctx->stream));
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->launches++;
   ctx->timing_pending = true;
