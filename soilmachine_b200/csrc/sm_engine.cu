@@ -46,16 +46,21 @@ __device__ __forceinline__ void bin_insert(const DevCtx& c, unsigned int tag, in
 }
 
 // Wait until every lower-index live particle whose conflict box overlaps mine has finished sweep
-// `tag`.  Lists were completed before the grid barrier that opened this sweep.  Single pass: each
-// in-range lower-index particle is polled where it is met in the list (all of them must finish
-// anyway, so the order of polling does not matter).
+// `tag`.  Lists were completed before the grid barrier that opened this sweep.
+//
+// Two phases so that the hand-off from the last blocker to this particle is O(1):
+//   scan (non-blocking): walk the 3x3 bins once; remember (a) pred[k] = the largest lower index in
+//        bin k at ANY distance and (b) up to K lower-index particles that are really in range.
+//   wait: if the in-range set fitted (sparse case) wait for exactly those plus the own-bin
+//        predecessor; otherwise (crowded pit) wait for the 9 per-bin predecessors only.
+// Every particle always waits for its own-bin predecessor, hence "X done" implies "every lower index
+// in X's bin is done", which makes the per-bin predecessors a complete (conservative) blocker set.
 template <int KIND>
 __device__ __forceinline__ void wait_blockers(const DevCtx& c, unsigned int tag, int pid, int ix, int iy) {
   const unsigned int par = tag & 1u;
   const int G = Reach<KIND>::G, D = Reach<KIND>::D;
   const int nbx = (c.dimx + G - 1) / G, nby = (c.dimy + G - 1) / G;
   const int bx = ix / G, by = iy / G;
-  // the (at most 9) bin heads are independent loads: fetch them all first
   unsigned long long heads[9];
 #pragma unroll
   for (int k = 0; k < 9; k++) {
@@ -63,22 +68,47 @@ __device__ __forceinline__ void wait_blockers(const DevCtx& c, unsigned int tag,
     heads[k] = (cx >= 0 && cx < nbx && cy >= 0 && cy < nby)
                    ? *((volatile unsigned long long*)&c.head[par][cx * nby + cy]) : 0ull;
   }
+  const int K = 6;
+  uint32_t near_[K];
+  uint32_t pred[9];
+  int nnear = 0;
+  bool crowded = false;
 #pragma unroll
   for (int k = 0; k < 9; k++) {
+    pred[k] = SM_NIL;
     const unsigned long long h = heads[k];
     if ((unsigned int)(h >> 32) != tag) continue;
     uint32_t j = (uint32_t)h;
+    uint32_t best = SM_NIL;
     while (j != SM_NIL) {
       const uint2 nd = c.node[par][j];
       if (j < (uint32_t)pid) {
+        if (best == SM_NIL || j > best) best = j;
         int dx = (int)(nd.y >> 16) - ix, dy = (int)(nd.y & 0xFFFFu) - iy;
         dx = dx < 0 ? -dx : dx;
         dy = dy < 0 ? -dy : dy;
         if (dx <= D && dy <= D) {
-          while (ld_volatile_u32(&c.done[j]) < tag) { __nanosleep(20); }
+          if (nnear < K) {
+#pragma unroll
+            for (int q = 0; q < K; q++) if (q == nnear) near_[q] = j;
+            nnear++;
+          } else crowded = true;
         }
       }
       j = nd.x;
+    }
+    pred[k] = best;
+  }
+  if (!crowded) {
+#pragma unroll
+    for (int q = 0; q < K; q++) {
+      if (q < nnear) { while (ld_volatile_u32(&c.done[near_[q]]) < tag) { __nanosleep(20); } }
+    }
+    if (pred[4] != SM_NIL) { while (ld_volatile_u32(&c.done[pred[4]]) < tag) { __nanosleep(20); } }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+      if (pred[k] != SM_NIL) { while (ld_volatile_u32(&c.done[pred[k]]) < tag) { __nanosleep(20); } }
     }
   }
 }
