@@ -64,10 +64,11 @@ def load():
     """Load the shared library; raises if it was not built (no fallback)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("SM_LIB_PATH", LIB_PATH)   # debugging builds (e.g. -DSM_PROFILE) only
+        if not os.path.exists(path):
             raise FileNotFoundError(
                 "%s not built: run ./build.sh (or python -c 'import __graft_entry__ as g; g.build()')" % LIB_PATH)
-        _lib = C.CDLL(LIB_PATH)
+        _lib = C.CDLL(path)
         _lib.sm_last_error.restype = C.c_char_p
         _lib.sm_last_error.argtypes = [C.c_void_p]
         _lib.sm_destroy.argtypes = [C.c_void_p]

@@ -225,35 +225,46 @@ template <class A> SM_HD sm_f3 map_normal(A& a, int x, int y) {
 // Particle::cascade, particle.h:24-101.  DEPTH = how many nested re-cascades are compiled in.
 // ------------------------------------------------------------------------------------------------
 template <int DEPTH, class A> struct Cascade {
-  static SM_HD_NOINLINE void run(A& a, int cx, int cy, int transferloop) {
+  static SM_HD void run(A& a, int cx, int cy, int transferloop) {
     const int dimx = a.dimx(), dimy = a.dimy();
     const int SCALE = a.scale();
-    // neighbour order of particle.h:30-39
-    const int ox[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
-    const int oy[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
-    int sx[8], sy[8];
-    double sh[8];
-    int num = 0;
     a.cascade_prefetch(cx, cy);
-    SM_UNROLL1
-    for (int i = 0; i < 8; i++) {
-      int nx = cx + ox[i], ny = cy + oy[i];
-      if (nx >= dimx || ny >= dimy || nx < 0 || ny < 0) continue;   // :51-52
-      // stable insertion by height, highest first (std::sort on <= 8 elements == stable
-      // insertion sort in libstdc++; comparator a.h > b.h, particle.h:58-60)
-      double h = map_height(a, nx, ny);
-      int j = num;
-      SM_UNROLL1
-      while (j > 0 && h > sh[j - 1]) {
-        sh[j] = sh[j - 1]; sx[j] = sx[j - 1]; sy[j] = sy[j - 1];
-        j--;
-      }
-      sh[j] = h; sx[j] = nx; sy[j] = ny;
-      num++;
+    // Neighbour k = 0..7 in the order of particle.h:30-39; with kk = k + (k >= 4) the offset is
+    // (kk/3 - 1, kk%3 - 1).  The reference sorts the in-bounds neighbours by their height BEFORE any
+    // transfer, highest first, with std::sort = stable insertion sort on <= 8 elements
+    // (particle.h:58-60).  (height desc, k asc) is a total order, so the sorted sequence is unique:
+    // rank[k] = #{j : h[j] > h[k] or (h[j] == h[k] and j < k)}, all in registers.
+    double h[8];
+    int num = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int kk = k + (k >= 4 ? 1 : 0);
+      const int nx = cx + kk / 3 - 1, ny = cy + kk % 3 - 1;
+      const bool in = !(nx >= dimx || ny >= dimy || nx < 0 || ny < 0);   // :51-52
+      h[k] = in ? map_height(a, nx, ny) : -1.0e300;                      // out of bounds sorts last
+      num += in ? 1 : 0;
     }
+    int rank[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) rank[k] = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+#pragma unroll
+      for (int j = k + 1; j < 8; j++) {
+        const bool j_first = h[j] > h[k];          // strictly higher goes first; ties keep k before j
+        rank[k] += j_first ? 1 : 0;
+        rank[j] += j_first ? 0 : 1;
+      }
+    }
+    unsigned int order = 0;                         // nibble i = neighbour with rank i
+#pragma unroll
+    for (int k = 0; k < 8; k++) order |= (unsigned int)k << (4 * rank[k]);
+
     SM_UNROLL1
     for (int i = 0; i < num; i++) {
-      int nx = sx[i], ny = sy[i];
+      const int k = (int)((order >> (4 * i)) & 7u);
+      const int kk = k + (k >= 4 ? 1 : 0);
+      const int nx = cx + kk / 3 - 1, ny = cy + kk % 3 - 1;
       // :66  full height difference, narrowed to float
       float diff = (float)((map_height(a, cx, cy) - map_height(a, nx, ny)) * (float)SCALE / 80.0f);
       if (diff == 0) continue;
@@ -403,6 +414,7 @@ template <class A> SM_HD int wind_step(A& a, WindP& p) {
   // ---- interact, wind.h:94-136 ----
   const int nx = (int)roundf(p.px), ny = (int)roundf(p.py);         // :99
   a.target(nx, ny);
+  int ncascade = 0;
   if (p.height <= map_height_bilinear(a, p.px, p.py) * (float)SCALE / 80.0f) {   // :102
     if (param.transports == p.contains) {                           // :105
       float len = sqrtf(p.sx * p.sx + p.sy * p.sy + p.sz * p.sz);
@@ -411,7 +423,7 @@ template <class A> SM_HD int wind_step(A& a, WindP& p) {
       double diff = col_remove(a, *ir, param.suspension * force);   // :109
       a.dirty(ix, iy);
       p.sediment += (param.suspension * force - diff);              // :110
-      Cascade<1, A>::run(a, ix, iy, 1);                             // :112
+      ncascade = 1;                                                 // :112 cascade(ipos, 1)
     }
   } else if (param.suspension > 0.0) {                              // :119
     const float sc = a.soil(p.contains).suspension;
@@ -420,8 +432,10 @@ template <class A> SM_HD int wind_step(A& a, WindP& p) {
     a.dirty(nx, ny);
     col_add(a, *ir, 0.5f * sc * p.sediment, p.contains);            // :124
     a.dirty(ix, iy);
-    Cascade<1, A>::run(a, ix, iy, 1);                               // :126
-    Cascade<1, A>::run(a, nx, ny, 1);                               // :129
+    ncascade = 2;                                                   // :126,129 cascade(ipos,1); cascade(npos,1)
   }
+  SM_UNROLL1
+  for (int q = 0; q < ncascade; q++)                                // one call site for both
+    Cascade<1, A>::run(a, q == 0 ? ix : nx, q == 0 ? iy : ny, 1);
   return SM_ALIVE;
 }

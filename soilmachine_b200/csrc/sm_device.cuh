@@ -16,6 +16,16 @@
 #include <cuda_runtime.h>
 #include "sm_core.cuh"
 
+#ifdef SM_PROFILE
+#define SM_PROF_DECL unsigned long long prof_[16] = {0}; long long pt_ = clock64();
+#define SM_PROF(i) { long long t_ = clock64(); prof_[i] += (unsigned long long)(t_ - pt_); pt_ = t_; }
+#define SM_PROF_FLUSH(ctl) { for (int i_ = 0; i_ < 16; i_++) if (prof_[i_]) atomicAdd(&(ctl)->prof[i_], prof_[i_]); }
+#else
+#define SM_PROF_DECL
+#define SM_PROF(i)
+#define SM_PROF_FLUSH(ctl)
+#endif
+
 struct PoolRing {
   unsigned long long head;  // next entry to hand out (advanced only in sweeps of the other parity)
   unsigned long long tail;  // next entry to write   (advanced only in sweeps of this parity)
@@ -29,6 +39,7 @@ struct RunCtl {
   unsigned long long steps, sweeps, exit_oob, exit_evap, exit_stall, drops, alive;
   unsigned long long bump;      // pool high-water mark
   PoolRing ring[2];
+  unsigned long long prof[16];  // clock64() phase totals (built with -DSM_PROFILE only)
 };
 
 struct DevCtx {
@@ -153,6 +164,7 @@ struct WinAccess {
   uint32_t valid, dirtym;
   bool has_b;
   float f_freq, f_track;    // water: frequency/track at ipos | wind: wind frequency at ipos
+  long long t_begin = 0, t_target0 = 0, t_target1 = 0;
   __device__ __forceinline__ WinAccess(const DevCtx& ctx, const SoilDev* ss, unsigned int ph, Sec32* w)
       : c(ctx), s_soils(ss), win(w), phase(ph & 1u), ax(0), ay(0), bx(0), by(0), valid(0), dirtym(0),
         has_b(false), f_freq(0.f), f_track(0.f) {}
@@ -189,11 +201,20 @@ struct WinAccess {
     if (KIND_ == 0) { f_freq = c.wfreq[ind]; f_track = c.wtrack[ind]; }
     else { f_freq = c.windfreq[ind]; }
     cp_async_wait_all();
+#ifdef SM_PROFILE
+    t_begin = clock64();
+#endif
   }
   __device__ __forceinline__ void target(int nx, int ny) {
     bx = nx; by = ny; has_b = true;
+#ifdef SM_PROFILE
+    t_target0 = clock64();
+#endif
     issue_patch(nx, ny, 9, 0x1FFu);
     cp_async_wait_all();
+#ifdef SM_PROFILE
+    t_target1 = clock64();
+#endif
   }
   __device__ __forceinline__ void cascade_prefetch(int cx, int cy) {
     if (cx == ax && cy == ay) { issue_patch(ax, ay, 0, 0x1FFu); cp_async_wait_all(); }

@@ -165,6 +165,7 @@ __global__ void __launch_bounds__(256) k_run(DevCtx c, int n, const float* __res
   const int nslots = (gridDim.x * blockDim.x) >> lshift;
 
   unsigned long long n_steps = 0, n_oob = 0, n_evap = 0, n_stall = 0;
+  SM_PROF_DECL
 
   // ---- prologue: spawn (ctor bodies water.h:13-17 / wind.h:15-20) or resume, fill the bins ----
   {
@@ -220,16 +221,26 @@ __global__ void __launch_bounds__(256) k_run(DevCtx c, int n, const float* __res
     if (gtid == 0) st_volatile_u32(&ctl->alive_slot[(s + 2) % 3], 0u);
 
     unsigned int my_alive = 0;
+    SM_PROF(0)   // barrier exit -> loop top
     if (leader) {
       for (int pid = slot; pid < n; pid += nslots) {
         if (c.alive[pid] == 0) continue;
         P p;
         load_particle(c, pid, p);
         const int ix = (int)roundf(p.px), iy = (int)roundf(p.py);
+        SM_PROF(1)   // state load
         wait_blockers<KIND>(c, tag, pid, ix, iy);
+        SM_PROF(2)   // blocker scan + wait
         __threadfence();
+        SM_PROF(3)   // acquire fence
         WinAccess<KIND> a(c, s_soils, tag, my_win);
         const int r = do_step(a, p);
+#ifdef SM_PROFILE
+        { long long t_ = clock64();
+          if (a.t_target1) { prof_[8] += a.t_begin - pt_; prof_[9] += a.t_target0 - a.t_begin;
+                             prof_[10] += a.t_target1 - a.t_target0; prof_[11] += t_ - a.t_target1; } }
+#endif
+        SM_PROF(4)   // step
         a.flush();
         store_particle(c, pid, p);
         if (r == SM_ALIVE) {
@@ -246,8 +257,10 @@ __global__ void __launch_bounds__(256) k_run(DevCtx c, int n, const float* __res
           else if (r == SM_EXIT_STALL) n_stall++;
           else { n_steps++; n_evap++; }
         }
+        SM_PROF(5)   // write-back + bin insert
         __threadfence();
         st_volatile_u32(&c.done[pid], r == SM_ALIVE ? tag : 0xFFFFFFFFu);
+        SM_PROF(6)   // release fence + publish
       }
     }
     if (my_alive) atomicAdd(&s_alive, my_alive);
@@ -257,7 +270,9 @@ __global__ void __launch_bounds__(256) k_run(DevCtx c, int n, const float* __res
       s_alive = 0;
     }
     grid_barrier(&ctl->barrier, epoch);
+    SM_PROF(7)   // grid barrier
   }
+  if (leader && slot < n) SM_PROF_FLUSH(ctl)
 
   // ---- epilogue ----
   if (n_steps) atomicAdd(&ctl->steps, n_steps);
@@ -906,6 +921,16 @@ int sm_wind_state(sm_context* ctx, float* pos2, float* speed3, double* height, d
 }
 
 int sm_launch_count(sm_context* ctx, int64_t* n) { *n = ctx->launches; return SM_OK; }
+// debug (only meaningful in a -DSM_PROFILE build): clock64() totals per phase, summed over particles
+int sm_debug_profile(sm_context* ctx, uint64_t* out16, int reset) {
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  RunCtl h;
+  CK(cudaMemcpy(&h, ctx->d.ctl, sizeof(RunCtl), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 16; i++) out16[i] = h.prof[i];
+  if (reset) CK(cudaMemset(&ctx->d.ctl->prof[0], 0, sizeof(h.prof)));
+  return SM_OK;
+}
 int sm_device_alloc(sm_context* ctx, int64_t bytes, void** dptr) {
   CK(cudaSetDevice(ctx->cfg.device));
   CK(cudaMalloc(dptr, (size_t)bytes));

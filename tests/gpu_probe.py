@@ -26,6 +26,7 @@ def run(soil, dim, nw, nd, lanes=None, iters=1, label=""):
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which == "profile": which = "none"
     if which in ("all", "single"):
         # single particles: sweep time = step latency (+ trivial barrier)
         run("rocksand", 1024, 1, 0, label="single")
@@ -35,3 +36,35 @@ if __name__ == "__main__":
         run("rocksand", 1024, 10000, 10000, label="mid")
     if which in ("all", "cfg3d"):
         run("rockgravelpebblessand", 1024, 1563, 1563, label="cfg3-density")
+
+
+def profile(soil, dim, n, kind, lanes=None):
+    """Phase breakdown (needs a -DSM_PROFILE build)."""
+    import ctypes as C
+    if lanes: os.environ["SM_LANES"] = str(lanes)
+    r = refapi.get().init(soil, seed=42, dimx=dim, dimy=dim, poolsize=dim*dim*4+2000000)
+    ctx = smb.Context(r.dimx, r.dimy, r.scale, max_particles=max(n, 1))
+    ctx.set_soils(r.soils())
+    cols = r.columns()
+    ctx.upload_columns(cols["offsets"], cols["type"], cols["size"], cols["saturation"])
+    r.lib.smref_srand(42)
+    xy = r.spawn_list(n)
+    out = (C.c_uint64 * 16)()
+    ctx.lib.sm_debug_profile(ctx.h, out, 1)
+    g = ctx.water_run(xy) if kind == "water" else ctx.wind_run(xy)
+    ctx.lib.sm_debug_profile(ctx.h, out, 1)
+    names = ["looptop", "stateload", "wait", "fence_acq", "step", "writeback", "fence_rel", "barrier",
+             "  step.begin(fetchA)", "  step.move", "  step.fetchB", "  step.interact"]
+    tot = sum(out[i] for i in range(8))
+    print("PROFILE", soil, dim, kind, "n=%d lanes=%s steps=%d sweeps=%d ms=%.2f us/sweep=%.2f" % (n, lanes, g.steps, g.sweeps, g.device_ms, g.device_ms*1e3/max(g.sweeps,1)))
+    for i, nm in enumerate(names):
+        print("   %-22s %8.0f cycles/step  %5.1f%%" % (nm, out[i] / max(g.steps, 1), 100.0 * out[i] / max(tot, 1)))
+    ctx.close()
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "profile":
+    profile("rocksand", 1024, 1, "water")
+    profile("rocksand", 1024, 64, "water")
+    profile("rocksand", 1024, 64, "wind")
+    profile("rockgravelpebblessand", 1024, 1563, "water")
+    profile("rockgravelpebblessand", 1024, 1563, "wind")
