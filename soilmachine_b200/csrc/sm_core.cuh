@@ -235,15 +235,41 @@ template <int DEPTH, class A> struct Cascade {
     // (particle.h:58-60).  (height desc, k asc) is a total order, so the sorted sequence is unique:
     // rank[k] = #{j : h[j] > h[k] or (h[j] == h[k] and j < k)}, all in registers.
     double h[8];
+    uint32_t nty[8];
     int num = 0;
+    unsigned int inb = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
       const int kk = k + (k >= 4 ? 1 : 0);
       const int nx = cx + kk / 3 - 1, ny = cy + kk % 3 - 1;
       const bool in = !(nx >= dimx || ny >= dimy || nx < 0 || ny < 0);   // :51-52
-      h[k] = in ? map_height(a, nx, ny) : -1.0e300;                      // out of bounds sorts last
-      num += in ? 1 : 0;
+      h[k] = -1.0e300;                                                   // out of bounds sorts last
+      nty[k] = 0u;
+      if (in) {
+        const Sec32* r = a.rec(nx, ny);
+        h[k] = rec_height(*r);
+        nty[k] = rec_surface(*r);
+        inb |= 1u << k;
+        num++;
+      }
     }
+    // Speculative pass (all eight neighbours at once, instruction-level parallel): which
+    // neighbours would transfer if the loop below met them with the map in its CURRENT state?
+    // Until the first transfer happens nothing changes, so the loop may skip the others; after a
+    // transfer every neighbour is evaluated exactly as the reference does.
+    unsigned int active = 0;
+    {
+      const Sec32* cr = a.rec(cx, cy);
+      const double hc = rec_height(*cr);
+      const uint32_t cty = rec_surface(*cr);
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const float diff = (float)((hc - h[k]) * (float)SCALE / 80.0f);
+        const float excess = fabsf(diff) - a.soil(diff > 0 ? cty : nty[k]).maxdiff;
+        if (((inb >> k) & 1u) && !(diff == 0) && !(excess <= 0)) active |= 1u << k;
+      }
+    }
+    if (active == 0) return;
     int rank[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) rank[k] = 0;
@@ -260,9 +286,11 @@ template <int DEPTH, class A> struct Cascade {
 #pragma unroll
     for (int k = 0; k < 8; k++) order |= (unsigned int)k << (4 * rank[k]);
 
+    bool changed = false;
     SM_UNROLL1
     for (int i = 0; i < num; i++) {
       const int k = (int)((order >> (4 * i)) & 7u);
+      if (!changed && !((active >> k) & 1u)) continue;
       const int kk = k + (k >= 4 ? 1 : 0);
       const int nx = cx + kk / 3 - 1, ny = cy + kk % 3 - 1;
       // :66  full height difference, narrowed to float
@@ -279,6 +307,7 @@ template <int DEPTH, class A> struct Cascade {
       double tsize = (tr->type == SM_EMPTY) ? 0.0 : tr->size;
       if (transfer > tsize) transfer = (float)tsize;                // :87-88 (f64 -> f32 narrowing)
       bool recascade = false;
+      changed = true;
       if (col_remove(a, *tr, (double)transfer) != 0) recascade = true;   // :90-91
       a.dirty(tx, ty);
       col_add(a, *a.rec(bx, by), (double)transfer, sp.cascades);    // :92
