@@ -134,6 +134,12 @@ int sm_wind_sweeps(sm_context* ctx, int32_t k, sm_stats* stats);
 int sm_wind_state(sm_context* ctx, float* pos2, float* speed3, double* height, double* sediment,
                   int32_t* contains, int32_t* alive);
 
+/* CUDA-event stopwatch on the context's stream (the stream every kernel of this context is
+ * launched on): start records an event, stop records another, synchronises and returns the elapsed
+ * device time between them. */
+int sm_timer_start(sm_context* ctx);
+int sm_timer_stop(sm_context* ctx, double* elapsed_ms);
+
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int sm_launch_count(sm_context* ctx, int64_t* n);
 /* Device pointer helpers so a caller can keep spawn lists resident. */

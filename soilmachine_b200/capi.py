@@ -33,7 +33,7 @@ SYMBOLS = [
     "sm_height_bilinear", "sm_water_run", "sm_wind_run", "sm_water_run_device", "sm_wind_run_device",
     "sm_last_stats", "sm_water_begin", "sm_water_sweeps", "sm_water_state", "sm_wind_begin",
     "sm_wind_sweeps", "sm_wind_state", "sm_launch_count", "sm_device_alloc", "sm_device_free",
-    "sm_device_upload",
+    "sm_device_upload", "sm_timer_start", "sm_timer_stop",
 ]
 
 
@@ -279,6 +279,14 @@ class Context:
         st = Stats()
         self._ck(self.lib.sm_last_stats(self.h, C.byref(st)))
         return st
+
+    def timer_start(self):
+        self._ck(self.lib.sm_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._ck(self.lib.sm_timer_stop(self.h, C.byref(ms)))
+        return ms.value
 
     def launch_count(self):
         n = C.c_int64()

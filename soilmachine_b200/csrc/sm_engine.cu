@@ -15,6 +15,7 @@
 #include <algorithm>
 #include "../../include/soilmachine_b200.h"
 #include "sm_device.cuh"
+#include "sm_noise.cuh"
 
 #define KIND_WATER 0
 #define KIND_WIND 1
@@ -337,6 +338,25 @@ __global__ void k_height_sum2(const double* __restrict__ partial, double* __rest
   if (threadIdx.x == 0) *out = sh[0];
 }
 
+// Layermap::initialize, layermap.h:163-216: one thread per cell replays add() for every layer
+#define SM_MAX_LAYERS 16
+struct LayerSet { LayerDev L[SM_MAX_LAYERS]; int zslice[SM_MAX_LAYERS]; int n; };
+__global__ void k_initialize(DevCtx c, LayerSet ls) {
+  DevAccess a(c, nullptr, 0u);
+  const size_t cells = (size_t)c.dimx * c.dimy;
+  for (size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x; cell < cells;
+       cell += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(cell / c.dimy), j = (int)(cell % c.dimy);
+    Sec32 r;
+    rec_set_empty(r);
+    for (int l = 0; l < ls.n; l++) {
+      const double h = layer_value(ls.L[l], i, j, ls.zslice[l], c.dimx, c.dimy);
+      col_add(a, r, h, ls.L[l].type);
+    }
+    c.top[cell] = r;
+  }
+}
+
 // single-cell operations for the facade's legacy Layermap calls: op 0 add, 1 remove, 2 cascade,
 // 3 query (height, surface, normal), 4 bilinear height
 struct CellOp { int op; int x, y; float fx, fy; double v; int t; };
@@ -366,7 +386,7 @@ struct sm_context {
   DevCtx d;
   std::string err;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr;
   size_t cells = 0;
   int max_particles = 0;
   int nsoils = 0;
@@ -423,6 +443,8 @@ void sm_destroy(sm_context* ctx) {
   if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->evt0) cudaEventDestroy(ctx->evt0);
+  if (ctx->evt1) cudaEventDestroy(ctx->evt1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -460,6 +482,8 @@ int sm_create(const sm_config* cfg, sm_context** out) {
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&ctx->ev0));
     CK(cudaEventCreate(&ctx->ev1));
+    CK(cudaEventCreate(&ctx->evt0));
+    CK(cudaEventCreate(&ctx->evt1));
     DevCtx& d = ctx->d;
     d.dimx = cfg->dimx; d.dimy = cfg->dimy; d.scale = cfg->scale;
     ctx->cells = (size_t)cfg->dimx * cfg->dimy;
@@ -920,6 +944,20 @@ int sm_wind_state(sm_context* ctx, float* pos2, float* speed3, double* height, d
   return SM_OK;
 }
 
+int sm_timer_start(sm_context* ctx) {
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaEventRecord(ctx->evt0, ctx->stream));
+  return SM_OK;
+}
+int sm_timer_stop(sm_context* ctx, double* elapsed_ms) {
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaEventRecord(ctx->evt1, ctx->stream));
+  CK(cudaEventSynchronize(ctx->evt1));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, ctx->evt0, ctx->evt1));
+  if (elapsed_ms) *elapsed_ms = ms;
+  return SM_OK;
+}
 int sm_launch_count(sm_context* ctx, int64_t* n) { *n = ctx->launches; return SM_OK; }
 // debug (only meaningful in a -DSM_PROFILE build): clock64() totals per phase, summed over particles
 int sm_debug_profile(sm_context* ctx, uint64_t* out16, int reset) {
@@ -948,8 +986,36 @@ int sm_device_upload(sm_context* ctx, void* dptr, const void* host, int64_t byte
   return SM_OK;
 }
 
-int sm_initialize(sm_context* ctx, int32_t, const sm_layer*, int32_t) {
-  return fail(ctx, SM_ERR_INVALID, "sm_initialize: not built yet");
+int sm_initialize(sm_context* ctx, int32_t seed, const sm_layer* layers, int32_t nlayers) {
+  if (!layers || nlayers < 1 || nlayers > SM_MAX_LAYERS)
+    return fail(ctx, SM_ERR_INVALID, "sm_initialize: 1..16 layers");
+  CK(cudaSetDevice(ctx->cfg.device));
+  LayerSet ls;
+  ls.n = nlayers;
+  for (int l = 0; l < nlayers; l++) {
+    if (layers[l].type < 0 || (ctx->nsoils > 0 && layers[l].type >= ctx->nsoils))
+      return fail(ctx, SM_ERR_INVALID, "sm_initialize: layer type out of range");
+    LayerDev& L = ls.L[l];
+    L.type = (uint32_t)layers[l].type; L.min = layers[l].min; L.bias = layers[l].bias;
+    L.scale = layers[l].scale; L.octaves = (int)layers[l].octaves; L.lacunarity = layers[l].lacunarity;
+    L.gain = layers[l].gain; L.frequency = layers[l].frequency;
+    L.bounding = fnl_fractal_bounding(L.octaves, L.gain);
+    ls.zslice[l] = layer_zslice(seed, l, nlayers);
+  }
+  const unsigned long long need = (unsigned long long)ctx->cells * (unsigned long long)(nlayers - 1);
+  if (ctx->cfg.pool_capacity > 0) {
+    if (need > ctx->d.pool_cap) return fail(ctx, SM_ERR_POOL, "sm_initialize: pool_capacity too small");
+  } else {
+    int rc = alloc_pool(ctx, need + (unsigned long long)ctx->cells + (4ull << 20));
+    if (rc != SM_OK) return rc;
+  }
+  int rc = reset_pool_ctl(ctx, 0);
+  if (rc != SM_OK) return rc;
+  k_initialize<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(ctx->d, ls);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SM_OK;
 }
 
 }  // extern "C"

@@ -9,6 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "hostsim", "hostsim.cpp")
 LIB = os.path.join(HERE, "hostsim", "libhostsim.so")
 CORE = os.path.join(HERE, "..", "soilmachine_b200", "csrc", "sm_core.cuh")
+NOISE = os.path.join(HERE, "..", "soilmachine_b200", "csrc", "sm_noise.cuh")
 
 SOILDEV = np.dtype([("friction", "<f4"), ("solubility", "<f4"), ("equrate", "<f4"), ("erosionrate", "<f4"),
                     ("maxdiff", "<f4"), ("settling", "<f4"), ("suspension", "<f4"), ("porosity", "<f4"),
@@ -21,7 +22,7 @@ class Stats(C.Structure):
 
 
 def build():
-    if (not os.path.exists(LIB)) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(CORE)):
+    if (not os.path.exists(LIB)) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(CORE), os.path.getmtime(NOISE)):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", SRC, "-o", LIB])
     return LIB
 
@@ -53,6 +54,10 @@ class HostSim:
         self.dimx, self.dimy = dimx, dimy
         sd = soildev_from(soils)
         self.lib.hs_init(dimx, dimy, scale, len(sd), sd.ctypes.data_as(C.c_void_p))
+
+    def initialize(self, seed, layers):
+        lay = np.ascontiguousarray(layers)
+        self.lib.hs_initialize(int(seed), len(lay), lay.ctypes.data_as(C.c_void_p))
 
     def set_columns(self, cols):
         off = np.ascontiguousarray(cols["offsets"], np.int64)

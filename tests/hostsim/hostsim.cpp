@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include "../../soilmachine_b200/csrc/sm_core.cuh"
+#include "../../soilmachine_b200/csrc/sm_noise.cuh"
 
 namespace {
 struct HostMap {
@@ -54,6 +55,23 @@ void hs_init(int dimx, int dimy, int scale, int nsoils, const SoilDev* soils) {
   M.top.resize((size_t)dimx * dimy);
   for (auto& r : M.top) rec_set_empty(r);
   M.wfreq.assign((size_t)dimx * dimy, 0.f); M.wtrack = M.wfreq; M.windfreq = M.wfreq;
+}
+struct LayerPOD { int32_t type; float min, bias, scale, octaves, lacunarity, gain, frequency; };
+// Layermap::initialize (layermap.h:163-216) through the product's noise restatement
+void hs_initialize(int seed, int nlayers, const LayerPOD* lay) {
+  HostAccess a;
+  for (auto& r : M.top) rec_set_empty(r);
+  M.pool.clear(); M.freelist.clear();
+  for (int l = 0; l < nlayers; l++) {
+    LayerDev L{(uint32_t)lay[l].type, lay[l].min, lay[l].bias, lay[l].scale, (int)lay[l].octaves,
+               lay[l].lacunarity, lay[l].gain, lay[l].frequency, 0.f};
+    L.bounding = fnl_fractal_bounding(L.octaves, L.gain);
+    const int zs = layer_zslice(seed, l, nlayers);
+    for (int i = 0; i < M.dimx; i++) for (int j = 0; j < M.dimy; j++) {
+      double h = layer_value(L, i, j, zs, M.dimx, M.dimy);
+      col_add(a, M.top[(size_t)i * M.dimy + j], h, L.type);
+    }
+  }
 }
 void hs_set_columns(const int64_t* off, const int32_t* type, const double* size, const double* sat) {
   HostAccess a;

@@ -116,3 +116,36 @@ def test_determinism(ref):
                       np.zeros(ctx.cells, np.float32))
     ctx.water_run(xy)
     _same(h1, ctx.heights(), "height (run twice)")
+
+
+@pytest.mark.parametrize("soil,dim,seed", [("rockgravelpebblessand", 160, 42), ("bigbutte", 128, 7),
+                                           ("default", 100, 12345)])
+def test_initialize_matches_reference_terrain(ref, soil, dim, seed):
+    """sm_initialize (CUDA OpenSimplex2/FBm) == Layermap::initialize (layermap.h:163-216)."""
+    import soilmachine_b200 as smb
+    ref.init(soil, seed=seed, dimx=dim, dimy=dim + 16)
+    ctx = smb.Context(ref.dimx, ref.dimy, ref.scale)
+    ctx.set_soils(ref.soils())
+    ctx.initialize(seed, ref.layers())
+    c1, c2 = ref.columns(), ctx.download_columns()
+    for k in c1:
+        _same(c1[k], c2[k], "init columns." + k)
+
+
+def test_presets_match_reference_loader(ref):
+    from soilmachine_b200 import presets
+    for name in presets.names():
+        ref.init(name, seed=0, dimx=8, dimy=8, poolsize=1000)
+        pre = presets.load(name)
+        rs, rl = ref.soils(), ref.layers()
+        assert len(rs) == len(pre["soils"]) and len(rl) == len(pre["layers"])
+        for k in pre["soils"].dtype.names:
+            _same(rs[k], pre["soils"][k], name + ".soils." + k)
+        for k in pre["layers"].dtype.names:
+            _same(rl[k], pre["layers"][k], name + ".layers." + k)
+        assert ref.scale == pre["world"]["scale"]
+
+
+def test_smoke_entry():
+    import __graft_entry__ as g
+    g.smoke()
