@@ -29,6 +29,7 @@ template <int KIND> struct Reach {
   static constexpr int STEP = (KIND == KIND_WATER) ? 2 : 3;   // max |npos - ipos|_inf
 };
 #define SM_MIN_BIN 8
+#define SM_BLOCK 128   // threads per block of the sweep kernel
 #define SM_SWEEPS_NONE 0x40000000   // internal: run the prologue only
 
 // ---------------------------------------------------------------------------------------------
@@ -46,18 +47,18 @@ __device__ __forceinline__ void bin_insert(const DevCtx& c, unsigned int tag, in
                                 ((uint32_t)ix << 16) | (uint32_t)iy);
 }
 
-// Wait until every lower-index live particle whose conflict box overlaps mine has finished sweep
-// `tag`.  Lists were completed before the grid barrier that opened this sweep.
-//
-// Two phases so that the hand-off from the last blocker to this particle is O(1):
-//   scan (non-blocking): walk the 3x3 bins once; remember (a) pred[k] = the largest lower index in
-//        bin k at ANY distance and (b) up to K lower-index particles that are really in range.
-//   wait: if the in-range set fitted (sparse case) wait for exactly those plus the own-bin
-//        predecessor; otherwise (crowded pit) wait for the 9 per-bin predecessors only.
+// Conflict detection for one particle and one sweep.  Lists were completed before the grid barrier
+// that opened this sweep.  scan_blockers walks the 3x3 bins once (non-blocking) and returns at most 9
+// particle indices whose completion of sweep `tag` implies that EVERY lower-index particle with an
+// overlapping conflict box has completed it:
+//   sparse case : the (<= K) lower-index particles really in range, plus the own-bin predecessor;
+//   crowded case: the 9 per-bin predecessors (largest lower index in each bin, at any distance).
 // Every particle always waits for its own-bin predecessor, hence "X done" implies "every lower index
-// in X's bin is done", which makes the per-bin predecessors a complete (conservative) blocker set.
+// in X's bin is done", which makes the per-bin predecessors a complete (conservative) blocker set and
+// the hand-off from the last blocker to this particle O(1).
 template <int KIND>
-__device__ __forceinline__ void wait_blockers(const DevCtx& c, unsigned int tag, int pid, int ix, int iy) {
+__device__ __forceinline__ unsigned int scan_blockers(const DevCtx& c, unsigned int tag, int pid, int ix, int iy,
+                                                      uint32_t (&list)[9]) {
   const unsigned int par = tag & 1u;
   const int G = Reach<KIND>::G, D = Reach<KIND>::D;
   const int nbx = (c.dimx + G - 1) / G, nby = (c.dimy + G - 1) / G;
@@ -74,6 +75,8 @@ __device__ __forceinline__ void wait_blockers(const DevCtx& c, unsigned int tag,
   uint32_t pred[9];
   int nnear = 0;
   bool crowded = false;
+#pragma unroll
+  for (int q = 0; q < K; q++) near_[q] = SM_NIL;
 #pragma unroll
   for (int k = 0; k < 9; k++) {
     pred[k] = SM_NIL;
@@ -100,18 +103,25 @@ __device__ __forceinline__ void wait_blockers(const DevCtx& c, unsigned int tag,
     }
     pred[k] = best;
   }
-  if (!crowded) {
+  unsigned int mask = 0;
 #pragma unroll
-    for (int q = 0; q < K; q++) {
-      if (q < nnear) { while (ld_volatile_u32(&c.done[near_[q]]) < tag) { __nanosleep(20); } }
-    }
-    if (pred[4] != SM_NIL) { while (ld_volatile_u32(&c.done[pred[4]]) < tag) { __nanosleep(20); } }
-  } else {
+  for (int k = 0; k < 9; k++) {
+    list[k] = crowded ? pred[k] : (k < K ? near_[k] : (k == K ? pred[4] : SM_NIL));
+    if (list[k] != SM_NIL) mask |= 1u << k;
+  }
+  return mask;
+}
+
+// poll the still-unfinished blockers once; returns the mask of those not yet done
+__device__ __forceinline__ unsigned int poll_blockers(const DevCtx& c, unsigned int tag, const uint32_t (&list)[9],
+                                                      unsigned int mask) {
 #pragma unroll
-    for (int k = 0; k < 9; k++) {
-      if (pred[k] != SM_NIL) { while (ld_volatile_u32(&c.done[pred[k]]) < tag) { __nanosleep(20); } }
+  for (int k = 0; k < 9; k++) {
+    if ((mask >> k) & 1u) {
+      if (ld_volatile_u32(&c.done[list[k]]) >= tag) mask &= ~(1u << k);
     }
   }
+  return mask;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -146,7 +156,7 @@ template <class A> __device__ __forceinline__ int do_step(A& a, WindP& p) { retu
 // the persistent sweep kernel
 // ---------------------------------------------------------------------------------------------
 template <int KIND>
-__global__ void __launch_bounds__(256) k_run(DevCtx c, int n, const float* __restrict__ spawn,
+__global__ void __launch_bounds__(SM_BLOCK) k_run(DevCtx c, int n, const float* __restrict__ spawn,
                                             int max_sweeps, int lshift) {
   typedef typename PType<KIND>::T P;
   __shared__ SoilDev s_soils[SM_MAX_SOILS];
@@ -164,6 +174,7 @@ __global__ void __launch_bounds__(256) k_run(DevCtx c, int n, const float* __res
   const bool leader = (gtid & ((1 << lshift) - 1)) == 0;
   const int slot = gtid >> lshift;
   const int nslots = (gridDim.x * blockDim.x) >> lshift;
+  const int trips = (n + nslots - 1) / nslots;
 
   unsigned long long n_steps = 0, n_oob = 0, n_evap = 0, n_stall = 0;
   SM_PROF_DECL
@@ -223,45 +234,64 @@ __global__ void __launch_bounds__(256) k_run(DevCtx c, int n, const float* __res
 
     unsigned int my_alive = 0;
     SM_PROF(0)   // barrier exit -> loop top
-    if (leader) {
-      for (int pid = slot; pid < n; pid += nslots) {
-        if (c.alive[pid] == 0) continue;
-        P p;
+    // Warp-converged rounds: every lane scans its blockers once, then the warp loops - each round
+    // the lanes whose blockers have all published this sweep execute their particle-step TOGETHER
+    // (SIMT), the others poll again.
+    for (int trip = 0; trip < trips; trip++) {
+      const int pid = slot + trip * nslots;
+      const bool has = leader && pid < n && c.alive[pid] != 0;
+      P p;
+      int ix = 0, iy = 0;
+      uint32_t list[9];
+      unsigned int waitmask = 0;
+      if (has) {
         load_particle(c, pid, p);
-        const int ix = (int)roundf(p.px), iy = (int)roundf(p.py);
+        ix = (int)roundf(p.px); iy = (int)roundf(p.py);
         SM_PROF(1)   // state load
-        wait_blockers<KIND>(c, tag, pid, ix, iy);
-        SM_PROF(2)   // blocker scan + wait
-        __threadfence();
-        SM_PROF(3)   // acquire fence
-        WinAccess<KIND> a(c, s_soils, tag, my_win);
-        const int r = do_step(a, p);
+        waitmask = scan_blockers<KIND>(c, tag, pid, ix, iy, list);
+        SM_PROF(2)   // blocker scan
+      }
+      bool pending = has;
+      for (;;) {
+        if (pending && waitmask) waitmask = poll_blockers(c, tag, list, waitmask);
+        const bool ready = pending && waitmask == 0;
+        if (__ballot_sync(0xffffffffu, pending) == 0u) break;
+        if (__ballot_sync(0xffffffffu, ready) == 0u) { __nanosleep(32); continue; }
+        if (ready) {
+          SM_PROF(12)  // waiting for blockers
+          __threadfence();
+          SM_PROF(3)   // acquire fence
+          WinAccess<KIND> a(c, s_soils, tag, my_win);
+          const int r = do_step(a, p);
 #ifdef SM_PROFILE
-        { long long t_ = clock64();
-          if (a.t_target1) { prof_[8] += a.t_begin - pt_; prof_[9] += a.t_target0 - a.t_begin;
-                             prof_[10] += a.t_target1 - a.t_target0; prof_[11] += t_ - a.t_target1; } }
+          { long long t_ = clock64();
+            if (a.t_target1) { prof_[8] += a.t_begin - pt_; prof_[9] += a.t_target0 - a.t_begin;
+                               prof_[10] += a.t_target1 - a.t_target0; prof_[11] += t_ - a.t_target1; } }
 #endif
-        SM_PROF(4)   // step
-        a.flush();
-        store_particle(c, pid, p);
-        if (r == SM_ALIVE) {
-          n_steps++;
-          const int jx = (int)roundf(p.px), jy = (int)roundf(p.py);
-          int ddx = jx - ix, ddy = jy - iy;
-          ddx = ddx < 0 ? -ddx : ddx; ddy = ddy < 0 ? -ddy : ddy;
-          if (ddx > Reach<KIND>::STEP || ddy > Reach<KIND>::STEP) atomicOr(&ctl->err, 1u << 4);  // SM_ERR_REACH
-          bin_insert<KIND>(c, tag + 1u, pid, jx, jy);
-          my_alive++;
-        } else {
-          c.alive[pid] = 0;
-          if (r == SM_EXIT_OOB) n_oob++;
-          else if (r == SM_EXIT_STALL) n_stall++;
-          else { n_steps++; n_evap++; }
+          SM_PROF(4)   // step
+          a.flush();
+          store_particle(c, pid, p);
+          if (r == SM_ALIVE) {
+            n_steps++;
+            const int jx = (int)roundf(p.px), jy = (int)roundf(p.py);
+            int ddx = jx - ix, ddy = jy - iy;
+            ddx = ddx < 0 ? -ddx : ddx; ddy = ddy < 0 ? -ddy : ddy;
+            if (ddx > Reach<KIND>::STEP || ddy > Reach<KIND>::STEP) atomicOr(&ctl->err, 1u << 4);  // SM_ERR_REACH
+            bin_insert<KIND>(c, tag + 1u, pid, jx, jy);
+            my_alive++;
+          } else {
+            c.alive[pid] = 0;
+            if (r == SM_EXIT_OOB) n_oob++;
+            else if (r == SM_EXIT_STALL) n_stall++;
+            else { n_steps++; n_evap++; }
+          }
+          SM_PROF(5)   // write-back + bin insert
+          __threadfence();
+          st_volatile_u32(&c.done[pid], r == SM_ALIVE ? tag : 0xFFFFFFFFu);
+          SM_PROF(6)   // release fence + publish
+          pending = false;
         }
-        SM_PROF(5)   // write-back + bin insert
-        __threadfence();
-        st_volatile_u32(&c.done[pid], r == SM_ALIVE ? tag : 0xFFFFFFFFu);
-        SM_PROF(6)   // release fence + publish
+        __syncwarp();
       }
     }
     if (my_alive) atomicAdd(&s_alive, my_alive);
@@ -524,8 +554,8 @@ int sm_create(const sm_config* cfg, sm_context** out) {
     int rcp = alloc_pool(ctx, cfg->pool_capacity > 0 ? (unsigned long long)cfg->pool_capacity
                                                      : (unsigned long long)C + (4ull << 20));
     if (rcp != SM_OK) return rcp;
-    CK(cudaFuncSetAttribute(k_run<KIND_WATER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * SM_WIN_BYTES));
-    CK(cudaFuncSetAttribute(k_run<KIND_WIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * SM_WIN_BYTES));
+    CK(cudaFuncSetAttribute(k_run<KIND_WATER>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BLOCK * SM_WIN_BYTES));
+    CK(cudaFuncSetAttribute(k_run<KIND_WIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BLOCK * SM_WIN_BYTES));
     CK(cudaStreamSynchronize(ctx->stream));
     return SM_OK;
   }();
@@ -782,7 +812,7 @@ static int launch_run(sm_context* ctx, int kind, int n, const float* d_spawn, in
   if (ctx->nsoils < 1) return fail(ctx, SM_ERR_INVALID, "soil table not set");
   if (n < 0 || n > ctx->max_particles) return fail(ctx, SM_ERR_INVALID, "batch larger than max_particles");
   CK(cudaSetDevice(ctx->cfg.device));
-  const int threads = 256;
+  const int threads = SM_BLOCK;
   // lanes per particle (a power of two): only the first lane of each group carries a particle, which
   // keeps divergent particle-steps out of each other's warps and shrinks the window footprint
   int lshift = 0, blocks = 1;

@@ -54,8 +54,8 @@ def profile(soil, dim, n, kind, lanes=None):
     g = ctx.water_run(xy) if kind == "water" else ctx.wind_run(xy)
     ctx.lib.sm_debug_profile(ctx.h, out, 1)
     names = ["looptop", "stateload", "wait", "fence_acq", "step", "writeback", "fence_rel", "barrier",
-             "  step.begin(fetchA)", "  step.move", "  step.fetchB", "  step.interact"]
-    tot = sum(out[i] for i in range(8))
+             "  step.begin(fetchA)", "  step.move", "  step.fetchB", "  step.interact", "blocked(waiting)"]
+    tot = sum(out[i] for i in range(8)) + out[12]
     print("PROFILE", soil, dim, kind, "n=%d lanes=%s steps=%d sweeps=%d ms=%.2f us/sweep=%.2f" % (n, lanes, g.steps, g.sweeps, g.device_ms, g.device_ms*1e3/max(g.sweeps,1)))
     for i, nm in enumerate(names):
         print("   %-22s %8.0f cycles/step  %5.1f%%" % (nm, out[i] / max(g.steps, 1), 100.0 * out[i] / max(tot, 1)))
