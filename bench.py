@@ -97,7 +97,7 @@ def cpu_arm(steps, warmup, sample):
     """The reference's CPU loop on a bounded sample of the workload.  Returns (value, info)."""
     from oracle import refapi
     W = WORKLOAD
-    r = refapi.get().init(W["soil"], seed=W["seed"], dimx=W["dim"], dimy=W["dim"], poolsize=34000000)
+    r = refapi.get().init(W["soil"], seed=W["seed"], dimx=W["dim"], dimy=W["dim"], poolsize=int(W["dim"] * W["dim"] * 2 + 2000000))
     r.lib.smref_srand(W["seed"])
     tot_steps, tot_s = 0, 0.0
     per = []

@@ -1,0 +1,69 @@
+"""CPU: the C-ABI library loads and exports what include/soilmachine_b200.h declares, fails loudly
+without a GPU, presets match the reference loader, host-side spawn lists match the reference's
+constructor draws, and bench.py's reference arm runs end to end."""
+import json
+import os
+import re
+import subprocess
+import sys
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from soilmachine_b200 import capi
+    hdr = open(os.path.join(ROOT, "include", "soilmachine_b200.h")).read()
+    declared = set(re.findall(r"\b(sm_[a-z_0-9]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = capi.load()
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, "declared but not exported: %s" % missing
+    assert set(capi.SYMBOLS) == declared
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import soilmachine_b200 as smb
+    with pytest.raises(smb.SoilMachineError) as e:
+        smb.Context(64, 64)
+    assert e.value.code == smb.capi.SM_ERR_NOGPU
+
+
+def test_presets_match_reference_loader(ref):
+    from soilmachine_b200 import presets
+    names = presets.names()
+    assert "rockgravelpebblessand" in names and len(names) == 11
+    for name in names:
+        ref.init(name, seed=0, dimx=8, dimy=8, poolsize=1000)
+        pre = presets.load(name)
+        rs, rl = ref.soils(), ref.layers()
+        assert len(rs) == len(pre["soils"]) and len(rl) == len(pre["layers"])
+        for k in pre["soils"].dtype.names:
+            assert np.array_equal(rs[k], pre["soils"][k]), (name, k)
+        for k in pre["layers"].dtype.names:
+            assert np.array_equal(rl[k], pre["layers"][k]), (name, k)
+        assert ref.scale == pre["world"]["scale"]
+
+
+def test_spawn_lists_match_reference_ctor_draws(ref):
+    from soilmachine_b200 import host
+    ref.init("default", seed=5, dimx=100, dimy=70)
+    a = ref.spawn_list(64, seed=5)
+    host.srand(5)
+    b = host.spawn_list(64, 100, 70)
+    assert np.array_equal(a, b)
+
+
+def test_bench_reference_arm_runs():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--dim", "96",
+                          "--particles", "200", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] == 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0

@@ -1,0 +1,78 @@
+"""CPU: the oracle restatement (oracle/sm_oracle.cpp) against the golden vectors generated from the
+reference itself, and - where oracle/_ref is built - against the reference directly."""
+import numpy as np
+import pytest
+import _golden
+from oracle import portapi, refapi
+
+
+def stats5(st):
+    return (st.steps, st.sweeps, st.exit_oob, st.exit_evap, st.exit_stall)
+
+
+@pytest.fixture(scope="module")
+def port():
+    return portapi.Port()
+
+
+@pytest.mark.parametrize("case", _golden.FRAME_CASES)
+def test_port_replays_golden_frame(port, case):
+    g = _golden.load(case)
+    port.init(int(g["dimx"]), int(g["dimy"]), int(g["scale"]), g["soils"])
+    port.set_columns(_golden.cols(g, "init"))
+    _golden.same_cols(port.columns(), _golden.cols(g, "init"), "init columns")
+    _golden.replay_frame(g, port, stats5)
+
+
+def test_port_column_ops_truth_table(port):
+    g = _golden.load("column_ops")
+    port.init(8, 8, int(g["scale"]), g["soils"])
+    for (kind, x, y, v, t), want in zip(g["ops"], g["remove_results"]):
+        if kind == 0:
+            port.add(int(x), int(y), v, int(t))
+        else:
+            got = port.remove(int(x), int(y), v)
+            assert np.float64(got).tobytes() == np.float64(want).tobytes()
+    _golden.same_cols(port.columns(), _golden.cols(g, "final"), "columns after add/remove")
+    _golden.same(port.heights(), g["heights"], "heights")
+    normals = np.array([port.normal(x, y) for x in range(8) for y in range(8)], np.float32)
+    _golden.same(normals, g["normals"], "normals")
+    bil = np.array([port.height(float(p[0]), float(p[1])) for p in g["bilinear_pts"]])
+    _golden.same(bil, g["bilinear"], "bilinear heights")
+    for x, y, loop in g["cascades"]:
+        port.cascade(x, y, int(loop))
+    _golden.same_cols(port.columns(), _golden.cols(g, "after_cascade"), "columns after cascades")
+
+
+def test_port_edge_cases(port):
+    """empty map, empty batches, particles spawned on the border / on empty columns."""
+    g = _golden.load("column_ops")
+    port.init(8, 8, int(g["scale"]), g["soils"])
+    st = port.water_run(np.zeros((0, 2), np.float32))
+    assert stats5(st) == (0, 0, 0, 0, 0)
+    xy = np.array([[0, 0], [7, 7], [3, 4], [0, 7]], np.float32)   # all-empty map: normal is NaN -> out of bounds
+    st = port.water_run(xy)
+    assert st.steps == 0 and st.exit_oob + st.exit_stall == 4
+    assert port.lib.smo_nsections() == 0
+    assert port.remove(2, 2, 0.5) == 0.0                           # remove on an empty column
+
+
+@pytest.mark.parametrize("soil,dim,n", [("rocksand", 72, 300), ("rockgravelpebblessand", 80, 300)])
+def test_port_matches_reference_live(port, ref, soil, dim, n):
+    ref.init(soil, seed=11, dimx=dim, dimy=dim - 8)
+    port.init(ref.dimx, ref.dimy, ref.scale, ref.soils())
+    port.set_columns(ref.columns())
+    xw = ref.spawn_list(n, seed=11); xd = ref.spawn_list(n // 2)
+    a, b = ref.water_run(xw), port.water_run(xw)
+    assert stats5(a) == stats5(b)
+    a, b = ref.wind_run(xd), port.wind_run(xd)
+    assert (a.steps, a.exit_oob) == (b.steps, b.exit_oob)
+    _golden.same_cols(ref.columns(), port.columns(), "columns")
+    # sequential mode (the reference's own loop order) as well
+    ref.init(soil, seed=11, dimx=dim, dimy=dim - 8)
+    port.init(ref.dimx, ref.dimy, ref.scale, ref.soils()); port.set_columns(ref.columns())
+    a, b = ref.water_seq(0, xw), port.water_seq(xw)
+    assert stats5(a)[0] == stats5(b)[0]
+    a, b = ref.wind_seq(0, xd), port.wind_seq(xd)
+    assert a.steps == b.steps
+    _golden.same_cols(ref.columns(), port.columns(), "columns (sequential)")
