@@ -67,3 +67,19 @@ def test_bench_reference_arm_runs():
     assert line["impl"] == "reference" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] == 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_cpp_facade_compiles_and_links():
+    """include/soilmachine/soilmachine.hpp (the reference's class names over the C ABI) + the frame loop
+    of SoilMachine.cpp written against it; without a GPU it must fail loudly (no fallback)."""
+    exe = os.path.join(ROOT, "tests", "hostsim", "facade_demo")
+    libdir = os.path.join(ROOT, "soilmachine_b200", "lib")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", os.path.join(ROOT, "tests", "facade_demo.cpp"),
+                           "-o", exe, "-L" + libdir, "-lsoilmachine_b200", "-Wl,-rpath," + libdir])
+    import torch
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    if torch.cuda.is_available():
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert "legacy ops ok" in out.stdout
+    else:
+        assert out.returncode == 77 and "no CUDA device" in out.stdout

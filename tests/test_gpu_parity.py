@@ -202,3 +202,15 @@ def test_gpu_edge_cases():
     assert st.steps == 0 and ctx.section_count() == 0
     with pytest.raises(smb.SoilMachineError):
         ctx.water_run(np.zeros((70001, 2), np.float32))   # larger than max_particles
+
+
+def test_cpp_facade_frame_loop_runs():
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "hostsim", "facade_demo")
+    libdir = os.path.join(root, "soilmachine_b200", "lib")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", os.path.join(root, "tests", "facade_demo.cpp"), "-o", exe,
+                           "-L" + libdir, "-lsoilmachine_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "frame 1:" in out.stdout and "legacy ops ok" in out.stdout
