@@ -239,7 +239,7 @@ def main():
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     h2d = (W["nwater"] + W["nwind"]) * 8
-    d2h = 2 * 248                                  # two RunCtl read-backs per step
+    d2h = 2 * 312                                  # two RunCtl read-backs per step
 
     # max over ranks / sums over ranks
     t = torch.tensor([ev_ms, e2e_ms, float(steps_w + steps_d), float(e_steps)], dtype=torch.float64, device="cuda")

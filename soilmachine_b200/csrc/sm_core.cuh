@@ -229,6 +229,7 @@ template <int DEPTH, class A> struct Cascade {
     const int dimx = a.dimx(), dimy = a.dimy();
     const int SCALE = a.scale();
     a.cascade_prefetch(cx, cy);
+    a.mark(3);
     // Neighbour k = 0..7 in the order of particle.h:30-39; with kk = k + (k >= 4) the offset is
     // (kk/3 - 1, kk%3 - 1).  The reference sorts the in-bounds neighbours by their height BEFORE any
     // transfer, highest first, with std::sort = stable insertion sort on <= 8 elements
@@ -253,6 +254,7 @@ template <int DEPTH, class A> struct Cascade {
         num++;
       }
     }
+    a.mark(4);
     // Speculative pass (all eight neighbours at once, instruction-level parallel): which
     // neighbours would transfer if the loop below met them with the map in its CURRENT state?
     // Until the first transfer happens nothing changes, so the loop may skip the others; after a
@@ -269,6 +271,7 @@ template <int DEPTH, class A> struct Cascade {
         if (((inb >> k) & 1u) && !(diff == 0) && !(excess <= 0)) active |= 1u << k;
       }
     }
+    a.mark(5);
     if (active == 0) return;
     int rank[8];
 #pragma unroll
@@ -377,6 +380,7 @@ template <class A> SM_HD int water_step(A& a, WaterP& p) {
                 (double)SCALE / 80.0;                               // :78
   if (c_eq < 0.0) c_eq = 0.0;
   if (c_eq > 1.0) c_eq = 1.0;
+  a.mark(1);
   if ((double)(a.soil(p.contains).erosionrate) < freq)              // :83-84
     p.contains = a.soil(p.contains).erodes;
   double cdiff = c_eq - p.sediment;                                 // :87
@@ -393,7 +397,9 @@ template <class A> SM_HD int water_step(A& a, WaterP& p) {
     col_add(a, *ir, -eq * cdiff * p.volume, p.contains);
     a.dirty(ix, iy);
   }
+  a.mark(2);
   Cascade<0, A>::run(a, nx, ny, 0);                                 // :113
+  a.mark(6);
   p.sediment /= (1.0 - evaprate);                                   // :116-119
   if (p.sediment > 1.0) p.sediment = 1.0;
   p.volume *= (1.0 - evaprate);
@@ -463,6 +469,7 @@ template <class A> SM_HD int wind_step(A& a, WindP& p) {
     a.dirty(ix, iy);
     ncascade = 2;                                                   // :126,129 cascade(ipos,1); cascade(npos,1)
   }
+  a.mark(2);
   SM_UNROLL1
   for (int q = 0; q < ncascade; q++)                                // one call site for both
     Cascade<1, A>::run(a, q == 0 ? ix : nx, q == 0 ? iy : ny, 1);

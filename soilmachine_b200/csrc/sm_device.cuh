@@ -40,6 +40,7 @@ struct RunCtl {
   unsigned long long bump;      // pool high-water mark
   PoolRing ring[2];
   unsigned long long prof[16];  // clock64() phase totals (built with -DSM_PROFILE only)
+  unsigned long long marks[8];  // finer marks inside interact()
 };
 
 struct DevCtx {
@@ -104,6 +105,7 @@ struct DevAccess {
   __device__ __forceinline__ void target(int, int) {}
   __device__ __forceinline__ void dirty(int, int) {}
   __device__ __forceinline__ void cascade_prefetch(int, int) {}
+  __device__ __forceinline__ void mark(int) {}
   __device__ __forceinline__ Sec32 pool_load(uint32_t i) { return c.pool[i]; }
   __device__ __forceinline__ void pool_store(uint32_t i, const Sec32& r) { c.pool[i] = r; }
   __device__ uint32_t pool_alloc() {
@@ -165,6 +167,12 @@ struct WinAccess {
   bool has_b;
   float f_freq, f_track;    // water: frequency/track at ipos | wind: wind frequency at ipos
   long long t_begin = 0, t_target0 = 0, t_target1 = 0;
+#ifdef SM_PROFILE
+  long long t_last = 0; unsigned long long t_mark[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  __device__ __forceinline__ void mark(int i) { long long t = clock64(); t_mark[i] += (unsigned long long)(t - t_last); t_last = t; }
+#else
+  __device__ __forceinline__ void mark(int) {}
+#endif
   __device__ __forceinline__ WinAccess(const DevCtx& ctx, const SoilDev* ss, unsigned int ph, Sec32* w)
       : c(ctx), s_soils(ss), win(w), phase(ph & 1u), ax(0), ay(0), bx(0), by(0), valid(0), dirtym(0),
         has_b(false), f_freq(0.f), f_track(0.f) {}
@@ -213,7 +221,7 @@ struct WinAccess {
     issue_patch(nx, ny, 9, 0x1FFu);
     cp_async_wait_all();
 #ifdef SM_PROFILE
-    t_target1 = clock64();
+    t_target1 = clock64(); t_last = t_target1;
 #endif
   }
   __device__ __forceinline__ void cascade_prefetch(int cx, int cy) {

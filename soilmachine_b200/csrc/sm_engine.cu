@@ -24,10 +24,26 @@
 // ipos+-5, so two steps commute unless |dipos|_inf <= 6 (water) / 10 (wind).  Bin edge >= reach*2
 // keeps every possible blocker inside the 3x3 bins around a particle.
 template <int KIND> struct Reach {
-  static constexpr int D = (KIND == KIND_WATER) ? 6 : 10;
+  static constexpr int D = (KIND == KIND_WATER) ? 6 : 10;       // largest possible sum of two reaches
   static constexpr int G = (KIND == KIND_WATER) ? 8 : 16;
-  static constexpr int STEP = (KIND == KIND_WATER) ? 2 : 3;   // max |npos - ipos|_inf
+  static constexpr int STEP = (KIND == KIND_WATER) ? 2 : 3;     // max |npos - ipos|_inf of any step
+  static constexpr int RING = (KIND == KIND_WATER) ? 1 : 2;     // cells the cascade reaches beyond npos
 };
+
+// Footprint half-width R of the NEXT step of a particle: everything the step reads or writes lies in
+// ipos +- R.  Water: |speed| = sqrt(2) after normalisation => npos within ipos+-2, cascade 3x3 => R = 3.
+// Wind: the new horizontal speed is 0.8*m + 0.2*pspeed with |m| <= |speed| in both branches of wind.h:73-78
+// (gravity only changes y; contact: m = 0.2 s - 0.8 s_tangential), so each component moves by at most
+// rho = 0.8*|speed| + 0.4 and npos lies within ipos +- floor(1 + rho); cascade(.,1) with one nested
+// re-cascade reaches 2 further.  Slow particles therefore claim +-3 instead of +-5.
+__device__ __forceinline__ int particle_reach(const WaterP&) { return 3; }
+__device__ __forceinline__ int particle_reach(const WindP& p) {
+  const float len = sqrtf(p.sx * p.sx + p.sy * p.sy + p.sz * p.sz);
+  int r = (int)floorf(1.0f + 0.8f * len + 0.4f + 0.01f);
+  r = r < 1 ? 1 : (r > 3 ? 3 : r);          // NaN speed -> r = 1; the step then dies out of bounds
+  return r + 2;
+}
+#define SM_PACK_NODE(x, y, R) (((uint32_t)(x) << 18) | ((uint32_t)(y) << 4) | (uint32_t)(R))
 #define SM_MIN_BIN 8
 #define SM_BLOCK 128   // threads per block of the sweep kernel
 #define SM_SWEEPS_NONE 0x40000000   // internal: run the prologue only
@@ -36,7 +52,7 @@ template <int KIND> struct Reach {
 // bins
 // ---------------------------------------------------------------------------------------------
 template <int KIND>
-__device__ __forceinline__ void bin_insert(const DevCtx& c, unsigned int tag, int pid, int ix, int iy) {
+__device__ __forceinline__ void bin_insert(const DevCtx& c, unsigned int tag, int pid, int ix, int iy, int R) {
   const unsigned int par = tag & 1u;
   const int G = Reach<KIND>::G;
   const int nby = (c.dimy + G - 1) / G;
@@ -44,7 +60,7 @@ __device__ __forceinline__ void bin_insert(const DevCtx& c, unsigned int tag, in
   unsigned long long old =
       atomicExch(&c.head[par][b], ((unsigned long long)tag << 32) | (unsigned long long)(uint32_t)pid);
   c.node[par][pid] = make_uint2(((unsigned int)(old >> 32) == tag) ? (uint32_t)old : SM_NIL,
-                                ((uint32_t)ix << 16) | (uint32_t)iy);
+                                SM_PACK_NODE(ix, iy, R));
 }
 
 // Conflict detection for one particle and one sweep.  Lists were completed before the grid barrier
@@ -58,9 +74,9 @@ __device__ __forceinline__ void bin_insert(const DevCtx& c, unsigned int tag, in
 // the hand-off from the last blocker to this particle O(1).
 template <int KIND>
 __device__ __forceinline__ unsigned int scan_blockers(const DevCtx& c, unsigned int tag, int pid, int ix, int iy,
-                                                      uint32_t (&list)[9]) {
+                                                      int R, uint32_t (&list)[9]) {
   const unsigned int par = tag & 1u;
-  const int G = Reach<KIND>::G, D = Reach<KIND>::D;
+  const int G = Reach<KIND>::G;
   const int nbx = (c.dimx + G - 1) / G, nby = (c.dimy + G - 1) / G;
   const int bx = ix / G, by = iy / G;
   unsigned long long heads[9];
@@ -88,7 +104,8 @@ __device__ __forceinline__ unsigned int scan_blockers(const DevCtx& c, unsigned 
       const uint2 nd = c.node[par][j];
       if (j < (uint32_t)pid) {
         if (best == SM_NIL || j > best) best = j;
-        int dx = (int)(nd.y >> 16) - ix, dy = (int)(nd.y & 0xFFFFu) - iy;
+        int dx = (int)(nd.y >> 18) - ix, dy = (int)((nd.y >> 4) & 0x3FFFu) - iy;
+        const int D = R + (int)(nd.y & 0xFu);       // the two footprints can meet iff |d| <= R_A + R_B
         dx = dx < 0 ? -dx : dx;
         dy = dy < 0 ? -dy : dy;
         if (dx <= D && dy <= D) {
@@ -155,6 +172,11 @@ template <class A> __device__ __forceinline__ int do_step(A& a, WindP& p) { retu
 // ---------------------------------------------------------------------------------------------
 // the persistent sweep kernel
 // ---------------------------------------------------------------------------------------------
+#ifdef SM_PROFILE
+__device__ __forceinline__ void ctl_marks(RunCtl* ctl, const unsigned long long* m) {
+  for (int i = 1; i < 8; i++) if (m[i]) atomicAdd(&ctl->marks[i], m[i]);
+}
+#endif
 template <int KIND>
 __global__ void __launch_bounds__(SM_BLOCK) k_run(DevCtx c, int n, const float* __restrict__ spawn,
                                             int max_sweeps, int lshift) {
@@ -209,8 +231,9 @@ __global__ void __launch_bounds__(SM_BLOCK) k_run(DevCtx c, int n, const float* 
           alive = c.alive[pid] != 0;
         }
         if (alive) {
-          float4 pa = c.pa[pid];
-          bin_insert<KIND>(c, tag0, pid, (int)roundf(pa.x), (int)roundf(pa.y));
+          P q;
+          load_particle(c, pid, q);
+          bin_insert<KIND>(c, tag0, pid, (int)roundf(q.px), (int)roundf(q.py), particle_reach(q));
           my_alive++;
         }
       }
@@ -241,14 +264,15 @@ __global__ void __launch_bounds__(SM_BLOCK) k_run(DevCtx c, int n, const float* 
       const int pid = slot + trip * nslots;
       const bool has = leader && pid < n && c.alive[pid] != 0;
       P p;
-      int ix = 0, iy = 0;
+      int ix = 0, iy = 0, myR = 0;
       uint32_t list[9];
       unsigned int waitmask = 0;
       if (has) {
         load_particle(c, pid, p);
         ix = (int)roundf(p.px); iy = (int)roundf(p.py);
         SM_PROF(1)   // state load
-        waitmask = scan_blockers<KIND>(c, tag, pid, ix, iy, list);
+        myR = particle_reach(p);
+        waitmask = scan_blockers<KIND>(c, tag, pid, ix, iy, myR, list);
         SM_PROF(2)   // blocker scan
       }
       bool pending = has;
@@ -266,7 +290,8 @@ __global__ void __launch_bounds__(SM_BLOCK) k_run(DevCtx c, int n, const float* 
 #ifdef SM_PROFILE
           { long long t_ = clock64();
             if (a.t_target1) { prof_[8] += a.t_begin - pt_; prof_[9] += a.t_target0 - a.t_begin;
-                               prof_[10] += a.t_target1 - a.t_target0; prof_[11] += t_ - a.t_target1; } }
+                               prof_[10] += a.t_target1 - a.t_target0; prof_[11] += t_ - a.t_target1;
+                               ctl_marks(ctl, a.t_mark); } }
 #endif
           SM_PROF(4)   // step
           a.flush();
@@ -276,8 +301,9 @@ __global__ void __launch_bounds__(SM_BLOCK) k_run(DevCtx c, int n, const float* 
             const int jx = (int)roundf(p.px), jy = (int)roundf(p.py);
             int ddx = jx - ix, ddy = jy - iy;
             ddx = ddx < 0 ? -ddx : ddx; ddy = ddy < 0 ? -ddy : ddy;
-            if (ddx > Reach<KIND>::STEP || ddy > Reach<KIND>::STEP) atomicOr(&ctl->err, 1u << 4);  // SM_ERR_REACH
-            bin_insert<KIND>(c, tag + 1u, pid, jx, jy);
+            const int lim = myR - Reach<KIND>::RING;      // the step promised to stay within ipos +- lim
+            if (ddx > lim || ddy > lim) atomicOr(&ctl->err, 1u << 4);  // SM_ERR_REACH
+            bin_insert<KIND>(c, tag + 1u, pid, jx, jy, particle_reach(p));
             my_alive++;
           } else {
             c.alive[pid] = 0;
@@ -492,7 +518,7 @@ static int alloc_pool(sm_context* ctx, unsigned long long cap) {
 }
 
 int sm_create(const sm_config* cfg, sm_context** out) {
-  if (!cfg || !out || cfg->dimx < 2 || cfg->dimy < 2 || cfg->dimx > 65535 || cfg->dimy > 65535) {
+  if (!cfg || !out || cfg->dimx < 2 || cfg->dimy < 2 || cfg->dimx > 16384 || cfg->dimy > 16384) {
     g_create_err = "sm_create: invalid configuration";
     return SM_ERR_INVALID;
   }
@@ -996,7 +1022,9 @@ int sm_debug_profile(sm_context* ctx, uint64_t* out16, int reset) {
   RunCtl h;
   CK(cudaMemcpy(&h, ctx->d.ctl, sizeof(RunCtl), cudaMemcpyDeviceToHost));
   for (int i = 0; i < 16; i++) out16[i] = h.prof[i];
-  if (reset) CK(cudaMemset(&ctx->d.ctl->prof[0], 0, sizeof(h.prof)));
+  for (int i = 1; i < 4; i++) out16[12 + i] = h.marks[i] + (i == 3 ? h.marks[4] + h.marks[5] + h.marks[6] : 0);
+  out16[13] = h.marks[1]; out16[14] = h.marks[2]; out16[15] = h.marks[3] + h.marks[4] + h.marks[5] + h.marks[6];
+  if (reset) { CK(cudaMemset(&ctx->d.ctl->prof[0], 0, sizeof(h.prof))); CK(cudaMemset(&ctx->d.ctl->marks[0], 0, sizeof(h.marks))); }
   return SM_OK;
 }
 int sm_device_alloc(sm_context* ctx, int64_t bytes, void** dptr) {

@@ -54,7 +54,8 @@ def profile(soil, dim, n, kind, lanes=None):
     g = ctx.water_run(xy) if kind == "water" else ctx.wind_run(xy)
     ctx.lib.sm_debug_profile(ctx.h, out, 1)
     names = ["looptop", "stateload", "wait", "fence_acq", "step", "writeback", "fence_rel", "barrier",
-             "  step.begin(fetchA)", "  step.move", "  step.fetchB", "  step.interact", "blocked(waiting)"]
+             "  step.begin(fetchA)", "  step.move", "  step.fetchB", "  step.interact", "blocked(waiting)",
+             "    interact.bilinear+c_eq", "    interact.erode/deposit", "    interact.cascade(+tail)"]
     tot = sum(out[i] for i in range(8)) + out[12]
     print("PROFILE", soil, dim, kind, "n=%d lanes=%s steps=%d sweeps=%d ms=%.2f us/sweep=%.2f" % (n, lanes, g.steps, g.sweeps, g.device_ms, g.device_ms*1e3/max(g.sweeps,1)))
     for i, nm in enumerate(names):
