@@ -46,6 +46,7 @@ __device__ __forceinline__ int particle_reach(const WindP& p) {
 #define SM_PACK_NODE(x, y, R) (((uint32_t)(x) << 18) | ((uint32_t)(y) << 4) | (uint32_t)(R))
 #define SM_MIN_BIN 8
 #define SM_BLOCK 128   // threads per block of the sweep kernel
+#define SM_ASYNC_DELTA 4   // sweeps per super-step of the barrier-free wind kernel
 #define SM_SWEEPS_NONE 0x40000000   // internal: run the prologue only
 
 // ---------------------------------------------------------------------------------------------
@@ -199,6 +200,7 @@ __global__ void __launch_bounds__(SM_BLOCK) k_run(DevCtx c, int n, const float* 
   const int trips = (n + nslots - 1) / nslots;
 
   unsigned long long n_steps = 0, n_oob = 0, n_evap = 0, n_stall = 0;
+  bool any_doa = false;
   SM_PROF_DECL
 
   // ---- prologue: spawn (ctor bodies water.h:13-17 / wind.h:15-20) or resume, fill the bins ----
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(SM_BLOCK) k_run(DevCtx c, int n, const float* 
             // wind.h:56-57: a particle whose load cannot be suspended dies in its first move()
             // without touching anything
             alive = !(s_soils[w.contains].suspension == 0.0);
-            if (!alive) n_oob++;
+            if (!alive) { n_oob++; any_doa = true; }
           }
           c.alive[pid] = alive ? 1 : 0;
           c.done[pid] = alive ? (tag0 - 1u) : 0xFFFFFFFFu;
@@ -338,10 +340,262 @@ __global__ void __launch_bounds__(SM_BLOCK) k_run(DevCtx c, int n, const float* 
   if (n_stall) atomicAdd(&ctl->exit_stall, n_stall);
   // tag_base was read by every block before its first barrier; barrier/alive_slot are reset by the
   // host before the next launch
+  if (any_doa) atomicMax(&ctl->sweeps, 1ull);
   if (gtid == 0) {
-    ctl->sweeps += (unsigned long long)s;
+    atomicMax(&ctl->sweeps, (unsigned long long)s);
     ctl->alive = total_alive;
     ctl->tag_base = tag0 + (unsigned int)s + 2u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_run_async: the sweep kernel without a grid barrier per sweep (used for wind batches).
+//
+// A wind batch is sparse (half the particles die at spawn, the rest drift for up to ~13 000 sweeps) and
+// almost never conflicts, but with one barrier per sweep every sweep costs (chain depth) x (slowest
+// step) for everybody.  Here a SUPER-STEP of DELTA sweeps runs between two grid barriers:
+//   * at its start every particle collects, from the bins, the ids of all particles that can come
+//     within conflict range during the super-step (Verlet list: |dipos| <= 10 + 6*(DELTA-1));
+//   * then each particle advances through its own sweeps.  Before executing sweep s it checks every
+//     candidate B's published state (last completed sweep, position, reach - ONE 64-bit word):
+//     all of B's steps that precede (s, A) in the canonical order - sweeps <= s for B < A, <= s-1
+//     for B > A - must either be complete, or be unable to reach A's footprint even if B moved
+//     3 cells per missing sweep.  The step with the smallest (sweep, index) is always ready, so
+//     there is no deadlock; steps whose footprints can meet are executed in canonical order, so the
+//     result is bit-identical to the lockstep order.
+// Requires one thread slot per particle (all particles resident).
+template <int KIND, int DELTA>
+__global__ void __launch_bounds__(SM_BLOCK) k_run_async(DevCtx c, int n, const float* __restrict__ spawn,
+                                                        int max_sweeps, int lshift) {
+  typedef typename PType<KIND>::T P;
+  __shared__ SoilDev s_soils[SM_MAX_SOILS];
+  __shared__ unsigned int s_alive;
+  extern __shared__ __align__(32) unsigned char s_win[];
+  for (int i = threadIdx.x; i < c.nsoils; i += blockDim.x) s_soils[i] = c.soils[i];
+  if (threadIdx.x == 0) s_alive = 0;
+  __syncthreads();
+  Sec32* my_win = (Sec32*)(s_win + (size_t)(threadIdx.x >> lshift) * SM_WIN_BYTES);
+
+  RunCtl* ctl = c.ctl;
+  unsigned int epoch = 0;
+  const unsigned int tag0 = ctl->tag_base;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool leader = (gtid & ((1 << lshift) - 1)) == 0;
+  const int pid = gtid >> lshift;
+  const bool mine = leader && pid < n;
+  const int G = Reach<KIND>::G;
+  const int nbx = (c.dimx + G - 1) / G, nby = (c.dimy + G - 1) / G;
+  const unsigned long long DEAD = 0xFFFFFFFFull << 32;
+
+  unsigned long long n_steps = 0, n_oob = 0, n_evap = 0, n_stall = 0;
+  unsigned int last_sweep = 0;   // 1 + index of the last sweep this particle took part in
+  bool live = false;
+  P p;
+
+  // ---- prologue ----
+  if (mine) {
+    if (spawn != nullptr) {
+      DevAccess a(c, s_soils, 0u);
+      const float x = spawn[2 * pid], y = spawn[2 * pid + 1];
+      if (KIND == KIND_WATER) {
+        WaterP w{x, y, 0.0f, 0.0f, 1.0, 0.0, 0u};
+        w.contains = spawn_contains(a, x, y);
+        store_particle(c, pid, w);
+        live = true;
+      } else {
+        WindP w{x, y, -2.0f, 0.0f, 1.0f, 0.0, 0.0, 0u};
+        w.contains = spawn_contains(a, x, y);
+        store_particle(c, pid, w);
+        live = !(s_soils[w.contains].suspension == 0.0);   // wind.h:56-57
+        if (!live) { n_oob++; last_sweep = 1u; }           // it dies inside the first sweep
+      }
+      c.alive[pid] = live ? 1 : 0;
+    } else {
+      live = c.alive[pid] != 0;
+    }
+    load_particle(c, pid, p);
+    const int ix = (int)roundf(p.px), iy = (int)roundf(p.py);
+    const int R = particle_reach(p);
+    c.pstate[pid] = live ? (((unsigned long long)(tag0 - 1u) << 32) | SM_PACK_NODE(ix, iy, R)) : DEAD;
+    if (live) {
+      // super-step parity 0 bins, tagged tag0
+      const int b = (ix / G) * nby + (iy / G);
+      unsigned long long old = atomicExch(&c.head[0][b], ((unsigned long long)tag0 << 32) | (unsigned long long)(uint32_t)pid);
+      c.node[0][pid] = make_uint2(((unsigned int)(old >> 32) == tag0) ? (uint32_t)old : SM_NIL, SM_PACK_NODE(ix, iy, R));
+      atomicAdd(&s_alive, 1u);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_alive) atomicAdd(&ctl->alive_slot[0], s_alive);
+    s_alive = 0;
+  }
+  grid_barrier(&ctl->barrier, epoch);
+
+  int swept = 0;                 // sweeps completed by the batch so far
+  unsigned int total_alive = 0;
+  for (int ss = 0;; ss++) {
+    const unsigned int S0 = tag0 + (unsigned int)swept;
+    total_alive = ld_volatile_u32(&ctl->alive_slot[ss % 3]);
+    int q = DELTA;
+    if (max_sweeps >= 0 && max_sweeps - swept < q) q = max_sweeps - swept;
+    if (total_alive == 0 || q <= 0) break;
+    if (gtid == 0) st_volatile_u32(&ctl->alive_slot[(ss + 2) % 3], 0u);
+    const unsigned int par = (unsigned int)ss & 1u;
+
+    // ---- candidates: everybody who can get within range during this super-step ----
+    const int K = 12;
+    uint32_t cand[K];
+    int ncand = 0;
+    bool overflow = false;
+    int ix = 0, iy = 0, myR = 0;
+    const int Rc = 2 * 5 + 2 * (q - 1) * Reach<KIND>::STEP;
+    const int nb = (Rc + G - 1) / G;
+    if (live) {
+      ix = (int)roundf(p.px); iy = (int)roundf(p.py); myR = particle_reach(p);
+#pragma unroll
+      for (int k = 0; k < K; k++) cand[k] = SM_NIL;
+      const int bx = ix / G, by = iy / G;
+      for (int cx = bx - nb; cx <= bx + nb; cx++) {
+        if (cx < 0 || cx >= nbx) continue;
+        for (int cy = by - nb; cy <= by + nb; cy++) {
+          if (cy < 0 || cy >= nby) continue;
+          const unsigned long long h = *((volatile unsigned long long*)&c.head[par][cx * nby + cy]);
+          if ((unsigned int)(h >> 32) != S0) continue;
+          uint32_t j = (uint32_t)h;
+          while (j != SM_NIL) {
+            const uint2 nd = c.node[par][j];
+            if (j != (uint32_t)pid) {
+              int dx = (int)(nd.y >> 18) - ix, dy = (int)((nd.y >> 4) & 0x3FFFu) - iy;
+              dx = dx < 0 ? -dx : dx; dy = dy < 0 ? -dy : dy;
+              if (dx <= Rc && dy <= Rc) {
+                if (ncand < K) {
+#pragma unroll
+                  for (int k = 0; k < K; k++) if (k == ncand) cand[k] = j;
+                  ncand++;
+                } else overflow = true;
+              }
+            }
+            j = nd.x;
+          }
+        }
+      }
+    }
+
+    // ---- this particle's sweeps S0 .. S0+q-1, in warp-converged rounds ----
+    unsigned int s = S0;
+    const unsigned int s_end = S0 + (unsigned int)q;
+    for (;;) {
+      const bool pending = live && (int)(s - s_end) < 0;
+      bool ready = false;
+      if (pending) {
+        ready = true;
+        // one candidate: are all of its steps that precede (s, pid) complete or out of reach?
+#define SM_CHECK_CAND(J)                                                                           \
+        {                                                                                          \
+          const unsigned long long st_ = *((volatile unsigned long long*)&c.pstate[J]);            \
+          const unsigned int prog_ = (unsigned int)(st_ >> 32);                                    \
+          const unsigned int smax_ = ((J) < (uint32_t)pid) ? s : s - 1u;                           \
+          if (prog_ != 0xFFFFFFFFu && (int)(prog_ - smax_) < 0) {                                  \
+            const int lag_ = (int)(smax_ - prog_) - 1;                                             \
+            const uint32_t w_ = (uint32_t)st_;                                                     \
+            int dx_ = (int)(w_ >> 18) - ix, dy_ = (int)((w_ >> 4) & 0x3FFFu) - iy;                 \
+            dx_ = dx_ < 0 ? -dx_ : dx_; dy_ = dy_ < 0 ? -dy_ : dy_;                                \
+            const int thr_ = myR + (lag_ == 0 ? (int)(w_ & 0xFu) : 5) + lag_ * Reach<KIND>::STEP;  \
+            if (dx_ <= thr_ && dy_ <= thr_) ready = false;                                         \
+          }                                                                                        \
+        }
+        if (!overflow) {
+#pragma unroll
+          for (int k = 0; k < K; k++) {
+            if (k < ncand) SM_CHECK_CAND(cand[k])
+          }
+        } else {
+          // crowded neighbourhood: enumerate the candidates from the (static) bins every time
+          const uint32_t w0 = c.node[par][pid].y;                        // my position at S0
+          const int ox = (int)(w0 >> 18), oy = (int)((w0 >> 4) & 0x3FFFu);
+          const int bx = ox / G, by = oy / G;
+          for (int cx = bx - nb; cx <= bx + nb && ready; cx++) {
+            if (cx < 0 || cx >= nbx) continue;
+            for (int cy = by - nb; cy <= by + nb && ready; cy++) {
+              if (cy < 0 || cy >= nby) continue;
+              const unsigned long long h = *((volatile unsigned long long*)&c.head[par][cx * nby + cy]);
+              if ((unsigned int)(h >> 32) != S0) continue;
+              uint32_t j = (uint32_t)h;
+              while (j != SM_NIL && ready) {
+                const uint2 nd = c.node[par][j];
+                if (j != (uint32_t)pid) {
+                  int dx = (int)(nd.y >> 18) - ox, dy = (int)((nd.y >> 4) & 0x3FFFu) - oy;
+                  dx = dx < 0 ? -dx : dx; dy = dy < 0 ? -dy : dy;
+                  if (dx <= Rc && dy <= Rc) SM_CHECK_CAND(j)
+                }
+                j = nd.x;
+              }
+            }
+          }
+        }
+#undef SM_CHECK_CAND
+      }
+      if (__ballot_sync(0xffffffffu, pending) == 0u) break;
+      if (__ballot_sync(0xffffffffu, ready) == 0u) { __nanosleep(32); continue; }
+      if (ready) {
+        __threadfence();
+        WinAccess<KIND> a(c, s_soils, (unsigned int)ss, my_win);
+        const int r = do_step(a, p);
+        a.flush();
+        store_particle(c, pid, p);
+        last_sweep = (s - tag0) + 1u;
+        unsigned long long st;
+        if (r == SM_ALIVE) {
+          n_steps++;
+          const int jx = (int)roundf(p.px), jy = (int)roundf(p.py);
+          int ddx = jx - ix, ddy = jy - iy;
+          ddx = ddx < 0 ? -ddx : ddx; ddy = ddy < 0 ? -ddy : ddy;
+          const int lim = myR - Reach<KIND>::RING;
+          if (ddx > lim || ddy > lim) atomicOr(&ctl->err, 1u << 4);   // SM_ERR_REACH
+          ix = jx; iy = jy; myR = particle_reach(p);
+          st = ((unsigned long long)s << 32) | SM_PACK_NODE(ix, iy, myR);
+        } else {
+          live = false;
+          c.alive[pid] = 0;
+          if (r == SM_EXIT_OOB) n_oob++;
+          else if (r == SM_EXIT_STALL) n_stall++;
+          else { n_steps++; n_evap++; }
+          st = DEAD;
+        }
+        __threadfence();
+        *((volatile unsigned long long*)&c.pstate[pid]) = st;
+        s++;
+      }
+      __syncwarp();
+    }
+
+    // ---- end of super-step: bins for the next one, survivors, barrier ----
+    swept += q;
+    if (live) {
+      const unsigned int tagn = tag0 + (unsigned int)swept;
+      const int b = (ix / G) * nby + (iy / G);
+      unsigned long long old = atomicExch(&c.head[par ^ 1u][b], ((unsigned long long)tagn << 32) | (unsigned long long)(uint32_t)pid);
+      c.node[par ^ 1u][pid] = make_uint2(((unsigned int)(old >> 32) == tagn) ? (uint32_t)old : SM_NIL, SM_PACK_NODE(ix, iy, myR));
+      atomicAdd(&s_alive, 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (s_alive) atomicAdd(&ctl->alive_slot[(ss + 1) % 3], s_alive);
+      s_alive = 0;
+    }
+    grid_barrier(&ctl->barrier, epoch);
+  }
+
+  // ---- epilogue ----
+  if (n_steps) atomicAdd(&ctl->steps, n_steps);
+  if (n_oob) atomicAdd(&ctl->exit_oob, n_oob);
+  if (n_evap) atomicAdd(&ctl->exit_evap, n_evap);
+  if (n_stall) atomicAdd(&ctl->exit_stall, n_stall);
+  if (last_sweep) atomicMax(&ctl->sweeps, (unsigned long long)last_sweep);
+  if (gtid == 0) {
+    ctl->alive = total_alive;
+    ctl->tag_base = tag0 + (unsigned int)swept + 2u;
   }
 }
 
@@ -493,7 +747,7 @@ void sm_destroy(sm_context* ctx) {
   DevCtx& d = ctx->d;
   cudaFree(d.top); cudaFree(d.pool); cudaFree(d.ringbuf[0]); cudaFree(d.ringbuf[1]);
   cudaFree(d.wfreq); cudaFree(d.wtrack); cudaFree(d.windfreq); cudaFree(ctx->d_soils);
-  cudaFree(d.ctl); cudaFree(d.pa); cudaFree(d.pb); cudaFree(d.pc); cudaFree(d.alive); cudaFree(d.done);
+  cudaFree(d.ctl); cudaFree(d.pa); cudaFree(d.pb); cudaFree(d.pc); cudaFree(d.alive); cudaFree(d.done); cudaFree(d.pstate);
   for (int i = 0; i < 2; i++) { cudaFree(d.head[i]); cudaFree(d.node[i]); }
   cudaFree(ctx->d_spawn); cudaFree(ctx->d_scratch); cudaFree(ctx->d_iscratch); cudaFree(ctx->d_cellres);
   if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
@@ -555,7 +809,7 @@ int sm_create(const sm_config* cfg, sm_context** out) {
     CK(cudaMalloc(&d.ctl, sizeof(RunCtl)));
     CK(cudaMemsetAsync(d.ctl, 0, sizeof(RunCtl), ctx->stream));
     CK(cudaMalloc(&d.pa, N * sizeof(float4))); CK(cudaMalloc(&d.pb, N * sizeof(double2)));
-    CK(cudaMalloc(&d.pc, N * sizeof(uint2))); CK(cudaMalloc(&d.alive, N)); CK(cudaMalloc(&d.done, N * 4));
+    CK(cudaMalloc(&d.pc, N * sizeof(uint2))); CK(cudaMalloc(&d.alive, N)); CK(cudaMalloc(&d.done, N * 4)); CK(cudaMalloc(&d.pstate, N * 8));
     d.nbx = (cfg->dimx + SM_MIN_BIN - 1) / SM_MIN_BIN; d.nby = (cfg->dimy + SM_MIN_BIN - 1) / SM_MIN_BIN;
     for (int i = 0; i < 2; i++) {
       CK(cudaMalloc(&d.head[i], (size_t)d.nbx * d.nby * 8));
@@ -582,6 +836,7 @@ int sm_create(const sm_config* cfg, sm_context** out) {
     if (rcp != SM_OK) return rcp;
     CK(cudaFuncSetAttribute(k_run<KIND_WATER>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BLOCK * SM_WIN_BYTES));
     CK(cudaFuncSetAttribute(k_run<KIND_WIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BLOCK * SM_WIN_BYTES));
+    CK(cudaFuncSetAttribute(k_run_async<KIND_WIND, SM_ASYNC_DELTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BLOCK * SM_WIN_BYTES));
     CK(cudaStreamSynchronize(ctx->stream));
     return SM_OK;
   }();
@@ -862,6 +1117,18 @@ static int launch_run(sm_context* ctx, int kind, int n, const float* d_spawn, in
     }
     if (blocks < 1) blocks = 1;
   }
+  // wind: barrier-free super-steps when every particle can own a thread slot
+  bool use_async = false;
+  if (kind == KIND_WIND) {
+    const char* e = getenv("SM_ASYNC");
+    if (!(e && atoi(e) == 0)) {
+      int occ = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run_async<KIND_WIND, SM_ASYNC_DELTA>, threads, smem));
+      const long long need_threads = (long long)std::max(n, 1) << lshift;
+      const long long nb_ = (need_threads + threads - 1) / threads;
+      if (occ >= 1 && nb_ <= (long long)ctx->num_sms * occ) { use_async = true; blocks = (int)std::max<long long>(nb_, 1); }
+    }
+  }
   DevCtx d = ctx->d;
   if (max_sweeps <= 0) max_sweeps = -1;            // run until every particle is dead
   if (max_sweeps == SM_SWEEPS_NONE) max_sweeps = 0;  // prologue only (the *_begin calls)
@@ -870,6 +1137,8 @@ static int launch_run(sm_context* ctx, int kind, int n, const float* d_spawn, in
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   if (kind == KIND_WATER)
     CK(cudaLaunchCooperativeKernel((void*)k_run<KIND_WATER>, dim3(blocks), dim3(threads), args, smem, ctx->stream));
+  else if (use_async)
+    CK(cudaLaunchCooperativeKernel((void*)k_run_async<KIND_WIND, SM_ASYNC_DELTA>, dim3(blocks), dim3(threads), args, smem, ctx->stream));
   else
     CK(cudaLaunchCooperativeKernel((void*)k_run<KIND_WIND>, dim3(blocks), dim3(threads), args, smem, ctx->stream));
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
