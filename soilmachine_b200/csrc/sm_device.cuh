@@ -110,13 +110,17 @@ struct DevAccess {
   __device__ __forceinline__ Sec32 pool_load(uint32_t i) { return c.pool[i]; }
   __device__ __forceinline__ void pool_store(uint32_t i, const Sec32& r) { c.pool[i] = r; }
   __device__ uint32_t pool_alloc() {
+    // Pop from the ring that was filled during the previous phase (its tail is stable now).  No CAS
+    // loop: under contention a CAS loop lets only one popper succeed per L2 round trip.  Instead every
+    // popper takes a ticket with one atomicAdd; tickets >= tail are overshoots, undone with an
+    // atomicMin(head, tail) (the head never drops below tail, so tickets < tail are unique), and served
+    // from the bump allocator.
     PoolRing* R = &c.ctl->ring[phase ^ 1u];
-    unsigned long long t = R->tail;   // stable during this sweep
-    unsigned long long h = *((volatile unsigned long long*)&R->head);
-    while (h < t) {
-      unsigned long long old = atomicCAS(&R->head, h, h + 1ull);
-      if (old == h) return c.ringbuf[phase ^ 1u][h % c.pool_cap];
-      h = old;
+    const unsigned long long t = R->tail;
+    if (*((volatile unsigned long long*)&R->head) < t) {
+      const unsigned long long h = atomicAdd(&R->head, 1ull);
+      if (h < t) return c.ringbuf[phase ^ 1u][h % c.pool_cap];
+      atomicMin(&R->head, t);
     }
     unsigned long long b = atomicAdd(&c.ctl->bump, 1ull);
     if (b < c.pool_cap) return (uint32_t)b;

@@ -26,7 +26,7 @@ def run(soil, dim, nw, nd, lanes=None, iters=1, label=""):
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
-    if which == "profile": which = "none"
+    if which == "profile" or which.startswith("cfg3:"): which = "none"
     if which in ("all", "single"):
         # single particles: sweep time = step latency (+ trivial barrier)
         run("rocksand", 1024, 1, 0, label="single")
@@ -69,3 +69,22 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "profile":
     profile("rocksand", 1024, 64, "wind")
     profile("rockgravelpebblessand", 1024, 1563, "water")
     profile("rockgravelpebblessand", 1024, 1563, "wind")
+
+
+def cfg3(kind="wind", frames=2):
+    """config-3 batches through the product's own terrain init (no oracle)."""
+    from soilmachine_b200 import host
+    sim = host.Simulation("rockgravelpebblessand", seed=42, dimx=4096, dimy=4096, max_particles=25000)
+    for f in range(frames):
+        xw = host.spawn_list(25000, 4096, 4096); xd = host.spawn_list(25000, 4096, 4096)
+        if kind in ("water", "both"):
+            g = sim.ctx.water_run(xw)
+            print("cfg3 water lanes=%s async=%s: steps=%d sweeps=%d ms=%.1f -> %.3e steps/s" % (os.environ.get("SM_LANES"), os.environ.get("SM_ASYNC"), g.steps, g.sweeps, g.device_ms, g.steps / g.device_ms * 1e3), flush=True)
+        if kind in ("wind", "both"):
+            g = sim.ctx.wind_run(xd)
+            print("cfg3 wind  lanes=%s async=%s: steps=%d sweeps=%d ms=%.1f -> %.3e steps/s" % (os.environ.get("SM_LANES"), os.environ.get("SM_ASYNC"), g.steps, g.sweeps, g.device_ms, g.steps / g.device_ms * 1e3), flush=True)
+    sim.close()
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1].startswith("cfg3:"):
+    cfg3(sys.argv[1].split(":")[1], int(sys.argv[2]) if len(sys.argv) > 2 else 1)
