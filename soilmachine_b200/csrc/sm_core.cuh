@@ -264,11 +264,19 @@ template <int DEPTH, class A> struct Cascade {
       const Sec32* cr = a.rec(cx, cy);
       const double hc = rec_height(*cr);
       const uint32_t cty = rec_surface(*cr);
+      const float cmax = a.soil(cty).maxdiff;
 #pragma unroll
       for (int k = 0; k < 8; k++) {
-        const float diff = (float)((hc - h[k]) * (float)SCALE / 80.0f);
-        const float excess = fabsf(diff) - a.soil(diff > 0 ? cty : nty[k]).maxdiff;
-        if (((inb >> k) & 1u) && !(diff == 0) && !(excess <= 0)) active |= 1u << k;
+        // diff = (float)(dd / 80.0f); its sign is dd's.  |dd| < 80*maxdiff*(1 - 2^-20) already proves
+        // |diff| <= maxdiff (rounding is monotone), i.e. no excess: the IEEE double division is only
+        // paid for neighbours near or above the threshold.
+        const double dd = (hc - h[k]) * (float)SCALE;
+        const float md = (dd > 0) ? cmax : a.soil(nty[k]).maxdiff;
+        if (!(fabs(dd) < 80.0 * (double)md * (1.0 - 9.5367431640625e-07))) {
+          const float diff = (float)(dd / 80.0f);
+          const float excess = fabsf(diff) - md;
+          if (((inb >> k) & 1u) && !(diff == 0) && !(excess <= 0)) active |= 1u << k;
+        }
       }
     }
     a.mark(5);

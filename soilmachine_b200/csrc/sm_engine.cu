@@ -46,6 +46,9 @@ __device__ __forceinline__ int particle_reach(const WindP& p) {
 #define SM_PACK_NODE(x, y, R) (((uint32_t)(x) << 18) | ((uint32_t)(y) << 4) | (uint32_t)(R))
 #define SM_MIN_BIN 8
 #define SM_BLOCK 128   // threads per block of the sweep kernel
+#ifndef SM_MINBLOCKS
+#define SM_MINBLOCKS 3  // resident blocks per SM the sweep kernels are compiled for (register cap)
+#endif
 #define SM_ASYNC_DELTA 4   // sweeps per super-step of the barrier-free wind kernel
 #define SM_SWEEPS_NONE 0x40000000   // internal: run the prologue only
 
@@ -179,7 +182,7 @@ __device__ __forceinline__ void ctl_marks(RunCtl* ctl, const unsigned long long*
 }
 #endif
 template <int KIND>
-__global__ void __launch_bounds__(SM_BLOCK) k_run(DevCtx c, int n, const float* __restrict__ spawn,
+__global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run(DevCtx c, int n, const float* __restrict__ spawn,
                                             int max_sweeps, int lshift) {
   typedef typename PType<KIND>::T P;
   __shared__ SoilDev s_soils[SM_MAX_SOILS];
@@ -296,7 +299,12 @@ __global__ void __launch_bounds__(SM_BLOCK) k_run(DevCtx c, int n, const float* 
                                ctl_marks(ctl, a.t_mark); } }
 #endif
           SM_PROF(4)   // step
+          // hand-off first: the map writes are all the successors of this step wait for
           a.flush();
+          __threadfence();
+          st_volatile_u32(&c.done[pid], r == SM_ALIVE ? tag : 0xFFFFFFFFu);
+          SM_PROF(6)   // write-back + release fence + publish
+          // own state and next sweep's bins are only needed after the grid barrier
           store_particle(c, pid, p);
           if (r == SM_ALIVE) {
             n_steps++;
@@ -313,10 +321,7 @@ __global__ void __launch_bounds__(SM_BLOCK) k_run(DevCtx c, int n, const float* 
             else if (r == SM_EXIT_STALL) n_stall++;
             else { n_steps++; n_evap++; }
           }
-          SM_PROF(5)   // write-back + bin insert
-          __threadfence();
-          st_volatile_u32(&c.done[pid], r == SM_ALIVE ? tag : 0xFFFFFFFFu);
-          SM_PROF(6)   // release fence + publish
+          SM_PROF(5)   // state store + bin insert
           pending = false;
         }
         __syncwarp();
@@ -365,7 +370,7 @@ __global__ void __launch_bounds__(SM_BLOCK) k_run(DevCtx c, int n, const float* 
 //     result is bit-identical to the lockstep order.
 // Requires one thread slot per particle (all particles resident).
 template <int KIND, int DELTA>
-__global__ void __launch_bounds__(SM_BLOCK) k_run_async(DevCtx c, int n, const float* __restrict__ spawn,
+__global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run_async(DevCtx c, int n, const float* __restrict__ spawn,
                                                         int max_sweeps, int lshift) {
   typedef typename PType<KIND>::T P;
   __shared__ SoilDev s_soils[SM_MAX_SOILS];
