@@ -26,7 +26,7 @@ def run(soil, dim, nw, nd, lanes=None, iters=1, label=""):
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
-    if which == "profile" or which.startswith("cfg3:"): which = "none"
+    if which in ("profile", "one") or which.startswith("cfg3:"): which = "none"
     if which in ("all", "single"):
         # single particles: sweep time = step latency (+ trivial barrier)
         run("rocksand", 1024, 1, 0, label="single")
@@ -88,3 +88,7 @@ def cfg3(kind="wind", frames=2):
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1].startswith("cfg3:"):
     cfg3(sys.argv[1].split(":")[1], int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "one":
+    run("rocksand", 1024, 1 if sys.argv[2] == "water" else 0, 0 if sys.argv[2] == "water" else 2, label="one")
