@@ -74,6 +74,15 @@ __device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) {
 __device__ __forceinline__ void st_volatile_u32(unsigned int* p, unsigned int v) {
   *((volatile unsigned int*)p) = v;
 }
+// acquire / release at gpu scope (the hand-off between dependent particle-steps)
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 // Grid-wide barrier for a co-resident (cooperative) grid: one arrival per block on a monotone
 // counter.  `epoch` is a per-thread copy of how many barriers this launch has passed.

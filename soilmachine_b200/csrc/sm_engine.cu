@@ -45,7 +45,9 @@ __device__ __forceinline__ int particle_reach(const WindP& p) {
 }
 #define SM_PACK_NODE(x, y, R) (((uint32_t)(x) << 18) | ((uint32_t)(y) << 4) | (uint32_t)(R))
 #define SM_MIN_BIN 8
+#ifndef SM_BLOCK
 #define SM_BLOCK 128   // threads per block of the sweep kernel
+#endif
 #ifndef SM_MINBLOCKS
 #define SM_MINBLOCKS 3  // resident blocks per SM the sweep kernels are compiled for (register cap)
 #endif
@@ -139,7 +141,11 @@ __device__ __forceinline__ unsigned int poll_blockers(const DevCtx& c, unsigned 
 #pragma unroll
   for (int k = 0; k < 9; k++) {
     if ((mask >> k) & 1u) {
+#ifdef SM_ACQREL
+      if (ld_acquire_u32(&c.done[list[k]]) >= tag) mask &= ~(1u << k);
+#else
       if (ld_volatile_u32(&c.done[list[k]]) >= tag) mask &= ~(1u << k);
+#endif
     }
   }
   return mask;
@@ -285,10 +291,16 @@ __global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run(DevCtx c, int n,
         if (pending && waitmask) waitmask = poll_blockers(c, tag, list, waitmask);
         const bool ready = pending && waitmask == 0;
         if (__ballot_sync(0xffffffffu, pending) == 0u) break;
+#ifdef SM_NOSLEEP
+        if (__ballot_sync(0xffffffffu, ready) == 0u) continue;
+#else
         if (__ballot_sync(0xffffffffu, ready) == 0u) { __nanosleep(32); continue; }
+#endif
         if (ready) {
           SM_PROF(12)  // waiting for blockers
+#ifndef SM_ACQREL
           __threadfence();
+#endif
           SM_PROF(3)   // acquire fence
           WinAccess<KIND> a(c, s_soils, tag, my_win);
           const int r = do_step(a, p);
@@ -301,8 +313,12 @@ __global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run(DevCtx c, int n,
           SM_PROF(4)   // step
           // hand-off first: the map writes are all the successors of this step wait for
           a.flush();
+#ifdef SM_ACQREL
+          st_release_u32(&c.done[pid], r == SM_ALIVE ? tag : 0xFFFFFFFFu);
+#else
           __threadfence();
           st_volatile_u32(&c.done[pid], r == SM_ALIVE ? tag : 0xFFFFFFFFu);
+#endif
           SM_PROF(6)   // write-back + release fence + publish
           // own state and next sweep's bins are only needed after the grid barrier
           store_particle(c, pid, p);

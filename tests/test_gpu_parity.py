@@ -214,3 +214,40 @@ def test_cpp_facade_frame_loop_runs():
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "frame 1:" in out.stdout and "legacy ops ok" in out.stdout
+
+
+def test_batch_larger_than_resident_threads(ref):
+    """more particles than thread slots: every thread carries several particles per sweep (the
+    config-5 regime, 200k particles)."""
+    import soilmachine_b200 as smb
+    ref.init("rocksand", seed=3, dimx=512, dimy=512, poolsize=512 * 512 * 4 + 2000000)
+    ctx = smb.Context(ref.dimx, ref.dimy, ref.scale, max_particles=80000)
+    ctx.set_soils(ref.soils())
+    cols = ref.columns()
+    ctx.upload_columns(cols["offsets"], cols["type"], cols["size"], cols["saturation"])
+    xy = ref.spawn_list(70000, seed=3)
+    r = ref.water_run(xy, max_sweeps=12)
+    g = ctx.water_run(xy, max_sweeps=12)
+    assert (g.steps, g.sweeps, g.alive) == (r.steps, r.sweeps, int(ref.water_state()["alive"].sum()))
+    _compare_maps(ref, ctx)
+    xd = ref.spawn_list(70000, seed=4)
+    r = ref.wind_run(xd, max_sweeps=10)
+    g = ctx.wind_run(xd, max_sweeps=10)
+    assert g.steps == r.steps
+    _compare_maps(ref, ctx)
+
+
+def test_nonsquare_map_and_async_wind(ref, monkeypatch):
+    """dimx != dimy (frequency maps are indexed transposed, water.h:53) and the opt-in barrier-free
+    wind kernel."""
+    import soilmachine_b200 as smb
+    monkeypatch.setenv("SM_ASYNC", "1")
+    ref.init("rockgravelpebblessand", seed=9, dimx=200, dimy=136)
+    ctx = smb.Context(ref.dimx, ref.dimy, ref.scale)
+    ctx.set_soils(ref.soils())
+    ctx.initialize(9, ref.layers())
+    xw = ref.spawn_list(800, seed=9); xd = ref.spawn_list(900)
+    r1, g1 = ref.water_run(xw), ctx.water_run(xw)
+    r2, g2 = ref.wind_run(xd), ctx.wind_run(xd)
+    assert (r1.steps, r2.steps, r2.sweeps) == (g1.steps, g2.steps, g2.sweeps)
+    _compare_maps(ref, ctx)
