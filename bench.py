@@ -93,6 +93,19 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def aggregate(ev_ms, e2e_ms, steps, e_steps, device=None):
+    """Whole-job numbers from per-rank ones: time = MAX over ranks, particle-steps = SUM over ranks.
+    Works on any initialised torch.distributed backend (NCCL on the GPUs, gloo in the CPU tests)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([ev_ms, e2e_ms, float(steps), float(e_steps)], dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm_ = t.clone(); dist.all_reduce(sm_, op=dist.ReduceOp.SUM)
+        return mx[0].item(), mx[1].item(), sm_[2].item(), sm_[3].item()
+    return float(ev_ms), float(e2e_ms), float(steps), float(e_steps)
+
+
 def cpu_arm(steps, warmup, sample):
     """The reference's CPU loop on a bounded sample of the workload.  Returns (value, info)."""
     from oracle import refapi
@@ -242,14 +255,7 @@ def main():
     d2h = 2 * 312                                  # two RunCtl read-backs per step
 
     # max over ranks / sums over ranks
-    t = torch.tensor([ev_ms, e2e_ms, float(steps_w + steps_d), float(e_steps)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm_ = t.clone(); dist.all_reduce(sm_, op=dist.ReduceOp.SUM)
-        ev_ms, e2e_ms = mx[0].item(), mx[1].item()
-        tot_steps, tot_e = sm_[2].item(), sm_[3].item()
-    else:
-        tot_steps, tot_e = float(steps_w + steps_d), float(e_steps)
+    ev_ms, e2e_ms, tot_steps, tot_e = aggregate(ev_ms, e2e_ms, steps_w + steps_d, e_steps, device="cuda")
     value = tot_steps / (ev_ms * 1e-3)
     e2e_val = tot_e / (e2e_ms * 1e-3)
 

@@ -1,0 +1,42 @@
+"""CPU, world_size 2 over gloo: the N>1 path of bench.py.  The hot path itself runs as independent
+replicas per rank ('replicas only'), so what N>1 adds is the aggregation - device
+time is the MAX over ranks, particle-steps the SUM - and the rank-0-only reference arm."""
+import json
+import os
+import subprocess
+import sys
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bench
+    ev, e2e, steps, esteps = bench.aggregate(100.0 + 50.0 * rank, 200.0 - 30.0 * rank, 1000 * (rank + 1), 10 * (rank + 1))
+    if rank == 0:
+        with open(out, "w") as f:
+            json.dump([ev, e2e, steps, esteps], f)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_aggregate_max_time_sum_steps(tmp_path):
+    out = str(tmp_path / "agg.json")
+    mp.spawn(_worker, args=(2, 29531, out), nprocs=2, join=True)
+    ev, e2e, steps, esteps = json.load(open(out))
+    assert ev == 150.0 and e2e == 200.0          # max over ranks
+    assert steps == 3000.0 and esteps == 30.0    # sum over ranks
+
+
+def test_reference_arm_only_rank0_prints():
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+                          "--dim", "64", "--particles", "50", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
