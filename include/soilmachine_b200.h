@@ -102,6 +102,21 @@ int sm_set_frequency(sm_context* ctx, const float* water_frequency, const float*
 /* mapfrequency + resetfrequency (water.h:353-365; SoilMachine.cpp:313-320) */
 int sm_frequency_update(sm_context* ctx);
 
+/* ---- meshing / export (renderer side of the boundary) ---------------------------------------------- */
+/* SurfParam::color per soil (surface.h:17; io.h:158-159), rgba, n = number of soils. */
+int sm_set_soil_colors(sm_context* ctx, const float* rgba, int32_t n);
+/* Layermap::update(Vertexpool&) (layermap.h:551-555 = update(ivec2,...) :475-549 for every cell): one
+ * 44-byte Vertex {position[3], normal[3], color[4], index} per cell in cell order, sliced at the plane
+ * SLICE (SoilMachine.cpp:12).  The vertices stay in device memory (sm_mesh_device_ptr, e.g. for GL
+ * interop); host_vertices may be NULL or a buffer of cells*11 floats. */
+int sm_mesh_update(sm_context* ctx, int32_t slice, float* host_vertices);
+int sm_mesh_device_ptr(sm_context* ctx, void** dptr);
+/* exportheight / exportcolor (io.h:234-252): the values the reference writes to the PNGs, as floats:
+ * height[cell] = position.y / SCALE / sqrt(2); color[cell*4..] = (b, g, r, 1) of the vertex colour.
+ * Both read the mesh of the last sm_mesh_update. */
+int sm_export_height(sm_context* ctx, float* height);
+int sm_export_color(sm_context* ctx, float* bgra);
+
 /* ---- single-cell operations (what the facade's legacy Layermap calls forward to) -------------- */
 int sm_cell_add(sm_context* ctx, int32_t x, int32_t y, double size, int32_t type); /* layermap.h:230 */
 int sm_cell_remove(sm_context* ctx, int32_t x, int32_t y, double h, double* leftover); /* :310 */

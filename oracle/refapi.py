@@ -144,6 +144,16 @@ class Ref:
     def frequency_update(self):
         self.lib.smref_frequency_update()
 
+    def mesh(self, slice_):
+        out = np.zeros((self.cells, 11), np.float32)
+        self.lib.smref_mesh(int(slice_), _p(out, C.c_float))
+        return out
+
+    def export(self):
+        h = np.zeros(self.cells, np.float32); c = np.zeros((self.cells, 4), np.float32)
+        self.lib.smref_export(_p(h, C.c_float), _p(c, C.c_float))
+        return h, c
+
     # ---- KAT entry points ----------------------------------------------------------------------
     def height(self, x, y):
         if isinstance(x, (int, np.integer)) and isinstance(y, (int, np.integer)):

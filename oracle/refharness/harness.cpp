@@ -259,6 +259,28 @@ void smref_frequency_update() {
   WaterParticle::resetfrequency(*g.lmap);
 }
 
+// Layermap::update(Vertexpool&) (layermap.h:551-555) into the stub vertex buffer; 11 floats per cell
+void smref_mesh(int slice, float* out) {
+  SLICE = slice;
+  g.lmap->update(*g.vp);
+  for (size_t i = 0; i < g.vp->buf.size(); i++) {
+    const Vertex& v = g.vp->buf[i];
+    float* o = out + 11 * i;
+    o[0] = v.position[0]; o[1] = v.position[1]; o[2] = v.position[2];
+    o[3] = v.normal[0]; o[4] = v.normal[1]; o[5] = v.normal[2];
+    o[6] = v.color[0]; o[7] = v.color[1]; o[8] = v.color[2]; o[9] = v.color[3]; o[10] = v.index;
+  }
+}
+// the per-pixel values exportheight / exportcolor compute (io.h:236-240, 247-250)
+void smref_export(float* height, float* bgra) {
+  for (int x = 0; x < SIZEX; x++) for (int y = 0; y < SIZEY; y++) {
+    Vertex* v = g.vp->get(g.lmap->section, x * SIZEY + y);
+    size_t i = (size_t)x * SIZEY + y;
+    if (height) { vec4 c = vec4(v->position[1]/SCALE/sqrt(2), v->position[1]/SCALE/sqrt(2), v->position[1]/SCALE/sqrt(2), 1); height[i] = c.x; }
+    if (bgra) { vec4 color = vec4(v->color[2], v->color[1], v->color[0], 1); bgra[4*i] = color.x; bgra[4*i+1] = color.y; bgra[4*i+2] = color.z; bgra[4*i+3] = color.w; }
+  }
+}
+
 // ---- single-call KAT entry points onto the reference's Layermap ---------------------------------
 double smref_height_i(int x, int y) { return g.lmap->height(ivec2(x, y)); }
 double smref_height_f(float x, float y) { return g.lmap->height(vec2(x, y)); }

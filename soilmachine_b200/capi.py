@@ -33,7 +33,8 @@ SYMBOLS = [
     "sm_height_bilinear", "sm_water_run", "sm_wind_run", "sm_water_run_device", "sm_wind_run_device",
     "sm_last_stats", "sm_water_begin", "sm_water_sweeps", "sm_water_state", "sm_wind_begin",
     "sm_wind_sweeps", "sm_wind_state", "sm_launch_count", "sm_device_alloc", "sm_device_free",
-    "sm_device_upload", "sm_timer_start", "sm_timer_stop",
+    "sm_device_upload", "sm_timer_start", "sm_timer_stop", "sm_set_soil_colors", "sm_mesh_update",
+    "sm_mesh_device_ptr", "sm_export_height", "sm_export_color",
 ]
 
 
@@ -179,6 +180,26 @@ class Context:
 
     def frequency_update(self):
         self._ck(self.lib.sm_frequency_update(self.h))
+
+    def set_soil_colors(self, rgba):
+        rgba = np.ascontiguousarray(rgba, np.float32).reshape(-1, 4)
+        self._ck(self.lib.sm_set_soil_colors(self.h, _p(rgba, C.c_float), len(rgba)))
+
+    def mesh_update(self, slice_, download=True):
+        """Layermap::update(Vertexpool&): (cells, 11) float32 = position3, normal3, color4, index."""
+        out = np.zeros((self.cells, 11), np.float32) if download else None
+        self._ck(self.lib.sm_mesh_update(self.h, int(slice_), _p(out, C.c_float)))
+        return out
+
+    def export_height(self):
+        out = np.zeros(self.cells, np.float32)
+        self._ck(self.lib.sm_export_height(self.h, _p(out, C.c_float)))
+        return out
+
+    def export_color(self):
+        out = np.zeros((self.cells, 4), np.float32)
+        self._ck(self.lib.sm_export_color(self.h, _p(out, C.c_float)))
+        return out
 
     def sync(self):
         self._ck(self.lib.sm_sync(self.h))

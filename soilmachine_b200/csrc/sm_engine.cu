@@ -688,6 +688,63 @@ __global__ void k_initialize(DevCtx c, LayerSet ls) {
   }
 }
 
+// Layermap::update(ivec2, Vertexpool&), layermap.h:475-549, for every cell: the mesh the renderer and
+// the PNG exporters read.  HBM-bound: per cell one 32-byte top record (+4 neighbours, L2-resident rows)
+// in, one 44-byte vertex out.
+struct DirectMap {   // read-only accessor over global records for map_normal()
+  const DevCtx& c;
+  __device__ __forceinline__ int dimx() const { return c.dimx; }
+  __device__ __forceinline__ int dimy() const { return c.dimy; }
+  __device__ __forceinline__ int scale() const { return c.scale; }
+  __device__ __forceinline__ const Sec32* rec(int x, int y) const { return &c.top[(size_t)x * c.dimy + y]; }
+};
+__global__ void k_mesh(DevCtx c, int slice, const float4* __restrict__ colors, float* __restrict__ verts) {
+  const size_t cells = (size_t)c.dimx * c.dimy;
+  const float plane = (float)slice / (float)c.scale;             // (float)SLICE/(float)SCALE
+  for (size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x; cell < cells;
+       cell += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(cell / c.dimy), y = (int)(cell % c.dimy);
+    Sec32 r = c.top[cell];
+    bool none = (r.type == SM_EMPTY);
+    while (!none && r.floor > plane) {                            // :478-479 walk down to the slice plane
+      if (r.below == SM_NIL) none = true;
+      else r = c.pool[r.below];
+    }
+    float px = (float)x, py, pz = (float)y, nx = 0.f, ny = 1.f, nz = 0.f;
+    float4 col;
+    int index;
+    if (none) {                                                   // :481-488
+      py = 0.f; col = colors[0]; index = 0;
+    } else if (r.floor + r.size > plane) {                        // :490-510 cut by the plane
+      py = (float)slice;
+      if (r.floor + r.size * r.saturation > plane) {
+        const float4 a = colors[0], b = colors[r.type];
+        col = make_float4((float)((double)a.x * (1.0 - 0.6) + (double)b.x * 0.6), (float)((double)a.y * (1.0 - 0.6) + (double)b.y * 0.6),
+                          (float)((double)a.z * (1.0 - 0.6) + (double)b.z * 0.6), (float)((double)a.w * (1.0 - 0.6) + (double)b.w * 0.6));
+        index = 0;
+      } else { col = colors[r.type]; index = (int)r.type; }
+    } else {                                                      // :512-530 the surface itself
+      py = (float)(c.scale * (r.floor + r.size));
+      DirectMap m{c};
+      const sm_f3 n = map_normal(m, x, y);
+      nx = n.x; ny = n.y; nz = n.z;
+      col = colors[r.type]; index = (int)r.type;
+    }
+    float* v = verts + cell * 11;
+    v[0] = px; v[1] = py; v[2] = pz; v[3] = nx; v[4] = ny; v[5] = nz;
+    v[6] = col.x; v[7] = col.y; v[8] = col.z; v[9] = col.w; v[10] = (float)index;
+  }
+}
+// exportheight / exportcolor, io.h:234-252
+__global__ void k_export(const float* __restrict__ verts, size_t cells, int scale, float* __restrict__ height,
+                         float* __restrict__ bgra) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (size_t)gridDim.x * blockDim.x) {
+    const float* v = verts + i * 11;
+    if (height) height[i] = (float)(v[1] / scale / sqrt(2.0));
+    if (bgra) { bgra[4 * i] = v[8]; bgra[4 * i + 1] = v[7]; bgra[4 * i + 2] = v[6]; bgra[4 * i + 3] = 1.0f; }
+  }
+}
+
 // single-cell operations for the facade's legacy Layermap calls: op 0 add, 1 remove, 2 cascade,
 // 3 query (height, surface, normal), 4 bilinear height
 struct CellOp { int op; int x, y; float fx, fy; double v; int t; };
@@ -726,6 +783,9 @@ struct sm_context {
   double* d_scratch = nullptr;    // height download / partial sums
   int32_t* d_iscratch = nullptr;
   CellRes* d_cellres = nullptr;
+  float* d_verts = nullptr;       // 11 floats per cell, allocated on first sm_mesh_update
+  float4* d_colors = nullptr;
+  bool mesh_valid = false;
   RunCtl* h_ctl = nullptr;        // pinned
   int64_t launches = 0;
   int cur_kind = -1, cur_n = 0;
@@ -770,6 +830,7 @@ void sm_destroy(sm_context* ctx) {
   cudaFree(d.wfreq); cudaFree(d.wtrack); cudaFree(d.windfreq); cudaFree(ctx->d_soils);
   cudaFree(d.ctl); cudaFree(d.pa); cudaFree(d.pb); cudaFree(d.pc); cudaFree(d.alive); cudaFree(d.done); cudaFree(d.pstate);
   for (int i = 0; i < 2; i++) { cudaFree(d.head[i]); cudaFree(d.node[i]); }
+  cudaFree(ctx->d_verts); cudaFree(ctx->d_colors);
   cudaFree(ctx->d_spawn); cudaFree(ctx->d_scratch); cudaFree(ctx->d_iscratch); cudaFree(ctx->d_cellres);
   if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -1293,6 +1354,58 @@ int sm_wind_state(sm_context* ctx, float* pos2, float* speed3, double* height, d
   return SM_OK;
 }
 
+int sm_set_soil_colors(sm_context* ctx, const float* rgba, int32_t n) {
+  if (!rgba || n < 1 || n > SM_MAX_SOILS) return fail(ctx, SM_ERR_INVALID, "sm_set_soil_colors: 1..64 soils");
+  CK(cudaSetDevice(ctx->cfg.device));
+  if (!ctx->d_colors) CK(cudaMalloc(&ctx->d_colors, SM_MAX_SOILS * sizeof(float4)));
+  CK(cudaMemcpy(ctx->d_colors, rgba, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice));
+  return SM_OK;
+}
+int sm_mesh_update(sm_context* ctx, int32_t slice, float* host_vertices) {
+  if (!ctx->d_colors) return fail(ctx, SM_ERR_INVALID, "sm_mesh_update: soil colours not set");
+  CK(cudaSetDevice(ctx->cfg.device));
+  if (!ctx->d_verts) CK(cudaMalloc(&ctx->d_verts, ctx->cells * 11 * sizeof(float)));
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  k_mesh<<<ctx->num_sms * 16, 256, 0, ctx->stream>>>(ctx->d, slice, ctx->d_colors, ctx->d_verts);
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->launches++;
+  ctx->timing_pending = true;
+  ctx->mesh_valid = true;
+  CK(cudaGetLastError());
+  if (host_vertices) {
+    CK(cudaMemcpyAsync(host_vertices, ctx->d_verts, ctx->cells * 11 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return SM_OK;
+}
+int sm_mesh_device_ptr(sm_context* ctx, void** dptr) {
+  if (!ctx->mesh_valid) return fail(ctx, SM_ERR_INVALID, "no mesh yet: call sm_mesh_update");
+  *dptr = ctx->d_verts;
+  return SM_OK;
+}
+static int export_maps(sm_context* ctx, float* height, float* bgra) {
+  if (!ctx->mesh_valid) return fail(ctx, SM_ERR_INVALID, "no mesh yet: call sm_mesh_update");
+  CK(cudaSetDevice(ctx->cfg.device));
+  float* d_out = nullptr;
+  const size_t n = ctx->cells * (height ? 1 : 4);
+  CK(cudaMalloc(&d_out, n * sizeof(float)));
+  k_export<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(ctx->d_verts, ctx->cells, ctx->d.scale, height ? d_out : nullptr,
+                                                     height ? nullptr : d_out);
+  ctx->launches++;
+  cudaError_t e = cudaMemcpyAsync(height ? height : bgra, d_out, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_out);
+  if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return SM_ERR_CUDA; }
+  return SM_OK;
+}
+int sm_export_height(sm_context* ctx, float* height) {
+  if (!height) return fail(ctx, SM_ERR_INVALID, "null buffer");
+  return export_maps(ctx, height, nullptr);
+}
+int sm_export_color(sm_context* ctx, float* bgra) {
+  if (!bgra) return fail(ctx, SM_ERR_INVALID, "null buffer");
+  return export_maps(ctx, nullptr, bgra);
+}
 int sm_timer_start(sm_context* ctx) {
   CK(cudaSetDevice(ctx->cfg.device));
   CK(cudaEventRecord(ctx->evt0, ctx->stream));

@@ -53,6 +53,7 @@ class Simulation:
         self.ctx = capi.Context(self.dimx, self.dimy, self.scale, device=device,
                                 pool_capacity=pool_capacity, max_particles=max_particles)
         self.ctx.set_soils(self.preset["soils"])
+        self.ctx.set_soil_colors(self.preset["colors"])
         self.ctx.initialize(self.seed, self.preset["layers"])   # Layermap(SEED, dim), SoilMachine.cpp:83
 
     def frame(self, nwater, nwind, water_xy=None, wind_xy=None):

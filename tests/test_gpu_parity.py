@@ -251,3 +251,24 @@ def test_nonsquare_map_and_async_wind(ref, monkeypatch):
     r2, g2 = ref.wind_run(xd), ctx.wind_run(xd)
     assert (r1.steps, r2.steps, r2.sweeps) == (g1.steps, g2.steps, g2.sweeps)
     _compare_maps(ref, ctx)
+
+
+@pytest.mark.parametrize("slice_", [160, 45])
+def test_mesh_and_export_match_reference(ref, slice_):
+    """Layermap::update(Vertexpool&) (layermap.h:475-555) and the exportheight/exportcolor pixel values
+    (io.h:234-252), after a frame, with and without the slice plane cutting the terrain."""
+    import soilmachine_b200 as smb
+    ref.init("rockgravelpebblessand", seed=21, dimx=96, dimy=80)
+    ctx = smb.Context(ref.dimx, ref.dimy, ref.scale)
+    ctx.set_soils(ref.soils())
+    ctx.set_soil_colors(ref.soils()["color"])
+    ctx.initialize(21, ref.layers())
+    xw = ref.spawn_list(300, seed=21); xd = ref.spawn_list(200)
+    ref.water_run(xw); ctx.water_run(xw)
+    ref.wind_run(xd); ctx.wind_run(xd)
+    want = ref.mesh(slice_)
+    got = ctx.mesh_update(slice_)
+    _same(want, got, "mesh vertices")
+    h, c = ref.export()
+    _same(h, ctx.export_height(), "exportheight values")
+    _same(c, ctx.export_color(), "exportcolor values")
