@@ -626,7 +626,21 @@ __global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run_async(DevCtx c, 
 // mapfrequency + resetfrequency, water.h:353-365 (one fused pass: 16 B per cell)
 __global__ void k_frequency_update(float* __restrict__ freq, float* __restrict__ track, size_t n) {
   const float lrate = 0.01f, K = 50.0f;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+  // 16-byte vectors over the bulk (cudaMalloc'd arrays are 256-byte aligned), scalars over the tail
+  const size_t n4 = n / 4;
+  float4* f4 = (float4*)freq;
+  float4* t4 = (float4*)track;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 t = t4[i];
+    float4 f = f4[i];
+    f.x = (1.0f - lrate) * f.x + lrate * K * t.x / (1.0f + K * t.x);
+    f.y = (1.0f - lrate) * f.y + lrate * K * t.y / (1.0f + K * t.y);
+    f.z = (1.0f - lrate) * f.z + lrate * K * t.z / (1.0f + K * t.z);
+    f.w = (1.0f - lrate) * f.w + lrate * K * t.w / (1.0f + K * t.w);
+    f4[i] = f;
+    t4[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  }
+  for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float t = track[i];
     freq[i] = (1.0f - lrate) * freq[i] + lrate * K * t / (1.0f + K * t);
     track[i] = 0.0f;
@@ -691,48 +705,79 @@ __global__ void k_initialize(DevCtx c, LayerSet ls) {
 // Layermap::update(ivec2, Vertexpool&), layermap.h:475-549, for every cell: the mesh the renderer and
 // the PNG exporters read.  HBM-bound: per cell one 32-byte top record (+4 neighbours, L2-resident rows)
 // in, one 44-byte vertex out.
-struct DirectMap {   // read-only accessor over global records for map_normal()
+struct MeshMap {   // read-only accessor for map_normal(): heights through the read-only (nc) path
   const DevCtx& c;
+  struct H { double size, floor; uint32_t type; };
   __device__ __forceinline__ int dimx() const { return c.dimx; }
   __device__ __forceinline__ int dimy() const { return c.dimy; }
   __device__ __forceinline__ int scale() const { return c.scale; }
-  __device__ __forceinline__ const Sec32* rec(int x, int y) const { return &c.top[(size_t)x * c.dimy + y]; }
 };
-__global__ void k_mesh(DevCtx c, int slice, const float4* __restrict__ colors, float* __restrict__ verts) {
+__device__ __forceinline__ Sec32 ldg_rec(const Sec32* p) {
+  const double2 a = __ldg((const double2*)p);
+  const double2 b = __ldg(((const double2*)p) + 1);
+  Sec32 r;
+  r.size = a.x; r.floor = a.y; r.saturation = b.x;
+  const unsigned long long w = (unsigned long long)__double_as_longlong(b.y);
+  r.type = (uint32_t)w; r.below = (uint32_t)(w >> 32);
+  return r;
+}
+struct MeshAccess {   // adapts MeshMap to the accessor interface map_normal() expects
+  const DevCtx& c;
+  Sec32 tmp;
+  __device__ __forceinline__ int dimx() const { return c.dimx; }
+  __device__ __forceinline__ int dimy() const { return c.dimy; }
+  __device__ __forceinline__ int scale() const { return c.scale; }
+  __device__ __forceinline__ const Sec32* rec(int x, int y) { tmp = ldg_rec(&c.top[(size_t)x * c.dimy + y]); return &tmp; }
+};
+#define MESH_BLOCK 256
+__global__ void __launch_bounds__(MESH_BLOCK) k_mesh(DevCtx c, int slice, const float4* __restrict__ colors,
+                                                     float* __restrict__ verts) {
+  __shared__ __align__(16) float s_v[MESH_BLOCK * 11];   // staged so the 44-byte vertices leave as 16-byte rows
   const size_t cells = (size_t)c.dimx * c.dimy;
   const float plane = (float)slice / (float)c.scale;             // (float)SLICE/(float)SCALE
-  for (size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x; cell < cells;
-       cell += (size_t)gridDim.x * blockDim.x) {
-    const int x = (int)(cell / c.dimy), y = (int)(cell % c.dimy);
-    Sec32 r = c.top[cell];
-    bool none = (r.type == SM_EMPTY);
-    while (!none && r.floor > plane) {                            // :478-479 walk down to the slice plane
-      if (r.below == SM_NIL) none = true;
-      else r = c.pool[r.below];
+  for (size_t base = (size_t)blockIdx.x * MESH_BLOCK; base < cells; base += (size_t)gridDim.x * MESH_BLOCK) {
+    const size_t cell = base + threadIdx.x;
+    if (cell < cells) {
+      const int x = (int)(cell / c.dimy), y = (int)(cell % c.dimy);
+      Sec32 r = ldg_rec(&c.top[cell]);
+      bool none = (r.type == SM_EMPTY);
+      while (!none && r.floor > plane) {                            // :478-479 walk down to the slice plane
+        if (r.below == SM_NIL) none = true;
+        else r = ldg_rec(&c.pool[r.below]);
+      }
+      float px = (float)x, py, pz = (float)y, nx = 0.f, ny = 1.f, nz = 0.f;
+      float4 col;
+      int index;
+      if (none) {                                                   // :481-488
+        py = 0.f; col = colors[0]; index = 0;
+      } else if (r.floor + r.size > plane) {                        // :490-510 cut by the plane
+        py = (float)slice;
+        if (r.floor + r.size * r.saturation > plane) {
+          const float4 a = colors[0], b = colors[r.type];
+          col = make_float4((float)((double)a.x * (1.0 - 0.6) + (double)b.x * 0.6), (float)((double)a.y * (1.0 - 0.6) + (double)b.y * 0.6),
+                            (float)((double)a.z * (1.0 - 0.6) + (double)b.z * 0.6), (float)((double)a.w * (1.0 - 0.6) + (double)b.w * 0.6));
+          index = 0;
+        } else { col = colors[r.type]; index = (int)r.type; }
+      } else {                                                      // :512-530 the surface itself
+        py = (float)(c.scale * (r.floor + r.size));
+        MeshAccess m{c, Sec32{}};
+        const sm_f3 n = map_normal(m, x, y);
+        nx = n.x; ny = n.y; nz = n.z;
+        col = colors[r.type]; index = (int)r.type;
+      }
+      float* v = s_v + threadIdx.x * 11;
+      v[0] = px; v[1] = py; v[2] = pz; v[3] = nx; v[4] = ny; v[5] = nz;
+      v[6] = col.x; v[7] = col.y; v[8] = col.z; v[9] = col.w; v[10] = (float)index;
     }
-    float px = (float)x, py, pz = (float)y, nx = 0.f, ny = 1.f, nz = 0.f;
-    float4 col;
-    int index;
-    if (none) {                                                   // :481-488
-      py = 0.f; col = colors[0]; index = 0;
-    } else if (r.floor + r.size > plane) {                        // :490-510 cut by the plane
-      py = (float)slice;
-      if (r.floor + r.size * r.saturation > plane) {
-        const float4 a = colors[0], b = colors[r.type];
-        col = make_float4((float)((double)a.x * (1.0 - 0.6) + (double)b.x * 0.6), (float)((double)a.y * (1.0 - 0.6) + (double)b.y * 0.6),
-                          (float)((double)a.z * (1.0 - 0.6) + (double)b.z * 0.6), (float)((double)a.w * (1.0 - 0.6) + (double)b.w * 0.6));
-        index = 0;
-      } else { col = colors[r.type]; index = (int)r.type; }
-    } else {                                                      // :512-530 the surface itself
-      py = (float)(c.scale * (r.floor + r.size));
-      DirectMap m{c};
-      const sm_f3 n = map_normal(m, x, y);
-      nx = n.x; ny = n.y; nz = n.z;
-      col = colors[r.type]; index = (int)r.type;
+    __syncthreads();
+    const size_t nvalid = (cells - base < MESH_BLOCK) ? (cells - base) : MESH_BLOCK;
+    const size_t nfl = nvalid * 11;
+    float* dst = verts + base * 11;                                 // base*44 bytes: 16-byte aligned (MESH_BLOCK*44 % 16 == 0)
+    for (size_t i = threadIdx.x * 4; i < nfl; i += MESH_BLOCK * 4) {
+      if (i + 4 <= nfl) *((float4*)(dst + i)) = *((const float4*)(s_v + i));
+      else for (size_t k = i; k < nfl; k++) dst[k] = s_v[k];
     }
-    float* v = verts + cell * 11;
-    v[0] = px; v[1] = py; v[2] = pz; v[3] = nx; v[4] = ny; v[5] = nz;
-    v[6] = col.x; v[7] = col.y; v[8] = col.z; v[9] = col.w; v[10] = (float)index;
+    __syncthreads();
   }
 }
 // exportheight / exportcolor, io.h:234-252
@@ -1366,7 +1411,7 @@ int sm_mesh_update(sm_context* ctx, int32_t slice, float* host_vertices) {
   CK(cudaSetDevice(ctx->cfg.device));
   if (!ctx->d_verts) CK(cudaMalloc(&ctx->d_verts, ctx->cells * 11 * sizeof(float)));
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  k_mesh<<<ctx->num_sms * 16, 256, 0, ctx->stream>>>(ctx->d, slice, ctx->d_colors, ctx->d_verts);
+  k_mesh<<<ctx->num_sms * 16, MESH_BLOCK, 0, ctx->stream>>>(ctx->d, slice, ctx->d_colors, ctx->d_verts);
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->launches++;
   ctx->timing_pending = true;

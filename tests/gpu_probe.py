@@ -26,7 +26,7 @@ def run(soil, dim, nw, nd, lanes=None, iters=1, label=""):
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
-    if which in ("profile", "one") or which.startswith("cfg3:"): which = "none"
+    if which in ("profile", "one", "mesh") or which.startswith("cfg3:"): which = "none"
     if which in ("all", "single"):
         # single particles: sweep time = step latency (+ trivial barrier)
         run("rocksand", 1024, 1, 0, label="single")
@@ -92,3 +92,15 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1].startswith("cfg3
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "one":
     run("rocksand", 1024, 1 if sys.argv[2] == "water" else 0, 0 if sys.argv[2] == "water" else 2, label="one")
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "mesh":
+    from soilmachine_b200 import host
+    sim = host.Simulation("rockgravelpebblessand", seed=42, dimx=4096, dimy=4096, max_particles=1024)
+    for it in range(5):
+        sim.ctx.mesh_update(240, download=False)
+        st = sim.ctx.last_stats()
+        cells = 4096 * 4096
+        print("k_mesh 4096^2: %.3f ms, %.1f GB/s algorithmic (32 B in + 44 B out per cell)" % (st.device_ms, cells * 76 / st.device_ms / 1e6), flush=True)
+    sim.ctx.timer_start(); sim.ctx.frequency_update(); ms = sim.ctx.timer_stop()
+    print("k_frequency_update 4096^2: %.3f ms, %.1f GB/s (16 B/cell)" % (ms, cells * 16 / ms / 1e6))
