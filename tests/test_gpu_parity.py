@@ -272,3 +272,58 @@ def test_mesh_and_export_match_reference(ref, slice_):
     h, c = ref.export()
     _same(h, ctx.export_height(), "exportheight values")
     _same(c, ctx.export_color(), "exportcolor values")
+
+
+def test_config2_full_size_parity_and_statistics(ref):
+    """BASELINE config 2 (1024^2 rocksand, 10 000 water): bit parity against the lockstep reference at
+    full size, and the sequential reference loop (the order upstream really runs) agrees statistically
+    (the field is chaotic under reordering, its statistics are not)."""
+    import soilmachine_b200 as smb
+    dim, n = 1024, 10000
+    ref.init("rocksand", seed=42, dimx=dim, dimy=dim, poolsize=dim * dim * 3 + 2000000)
+    ctx = smb.Context(dim, dim, ref.scale, max_particles=n)
+    ctx.set_soils(ref.soils())
+    ctx.initialize(42, ref.layers())
+    h0 = ctx.heights().copy()
+    _same(ref.heights(), h0, "initial heights")
+    xy = ref.spawn_list(n, seed=42)
+    r = ref.water_run(xy)
+    g = ctx.water_run(xy)
+    assert (g.steps, g.sweeps, g.exit_oob, g.exit_evap, g.exit_stall) == \
+        (r.steps, r.sweeps, r.exit_oob, r.exit_evap, r.exit_stall)
+    h_lock = ctx.heights().copy()
+    _same(ref.heights(), h_lock, "heights after the batch")
+    # sequential order on a fresh copy of the same terrain, same spawn list
+    ref.init("rocksand", seed=42, dimx=dim, dimy=dim, poolsize=dim * dim * 3 + 2000000)
+    s = ref.water_seq(0, xy)
+    h_seq = ref.heights()
+    d_lock, d_seq = h_lock - h0, h_seq - h0
+    assert abs(s.steps - g.steps) / g.steps < 0.02                      # same amount of work
+    assert abs(d_lock.sum() - d_seq.sum()) < 0.02 * abs(d_seq).sum()    # same net mass change
+    assert abs(np.abs(d_lock).sum() - np.abs(d_seq).sum()) < 0.05 * np.abs(d_seq).sum()   # same amount moved
+    assert abs(h_lock.mean() - h_seq.mean()) < 1e-6 and abs(h_lock.std() - h_seq.std()) < 1e-5
+
+
+@pytest.mark.parametrize("soil,dim,nw,nd", [("bigbutte", 4096, 50000, 0), ("rockgravelpebbles_big", 2048, 60000, 2000)])
+def test_large_configs_properties(soil, dim, nw, nd):
+    """BASELINE configs 4/5 shapes at sizes the oracle cannot replay in seconds: size-independent
+    properties - run-twice determinism of the whole field (Σheight and an order-sensitive checksum), no
+    pool drops, no reach violations, inert wind on a soil without suspension (wind.h:56-57)."""
+    from soilmachine_b200 import host
+    sums = []
+    for rep in range(2):
+        sim = host.Simulation(soil, seed=42, dimx=dim, dimy=dim, max_particles=max(nw, nd, 1))
+        host.srand(42)
+        xw = host.spawn_list(nw, dim, dim)
+        ws = sim.ctx.water_run(xw, max_sweeps=60)
+        assert ws.pool_drops == 0 and ws.steps > 0
+        ds = None
+        if nd:
+            ds = sim.ctx.wind_run(host.spawn_list(nd, dim, dim))
+            assert ds.steps == 0 and ds.exit_oob == nd      # no soil has SUSPENSION > 0 on this preset
+        h = sim.ctx.heights()
+        w = (np.arange(h.size, dtype=np.float64) % 1021 + 1.0).reshape(h.shape)
+        sums.append((sim.ctx.height_sum(), float((h * w).sum()), ws.steps))
+        assert abs(sums[-1][0] - h.sum()) < 1e-6 * abs(h.sum())
+        sim.close()
+    assert sums[0] == sums[1]
