@@ -74,6 +74,28 @@ void sm_destroy(sm_context* ctx);
 const char* sm_last_error(const sm_context* ctx);   /* ctx may be NULL: last create error */
 int sm_sync(sm_context* ctx);
 
+/* ---- sharded maps (one context per rank; ranks = GPUs, or contexts sharing one GPU) ------------------- */
+/* The map is cut into nranks x-strips; rank q owns columns [x0, x1) (sm_shard_range) and executes the
+ * particles whose cell lies there.  Contexts reach each other's arrays through peer pointers: every rank
+ * exports a blob (sm_peer_export), the blobs are gathered (torch.distributed / MPI / same process) and
+ * every rank attaches all of them (sm_peer_attach; use_ipc = 1 opens CUDA-IPC mappings of another
+ * process's GPU memory, 0 takes the raw pointers of contexts living in the same process).  After that
+ * sm_initialize / sm_upload_columns / downloads work on the rank's own strip (cell order
+ * (x - x0)*dimy + y) and sm_*_run_device must be called on EVERY rank (the kernels meet in a cross-rank
+ * barrier every sweep); results are bit-identical to the unsharded run.  share = number of contexts
+ * that run their kernels concurrently on this device. */
+#define SM_PEER_ARRAYS 14
+typedef struct sm_peer_blob {
+  uint64_t ptr[16];
+  unsigned char ipc[16][64];
+  uint64_t pool_cap;
+  int32_t rank, device;
+} sm_peer_blob;
+int sm_create_sharded(const sm_config* cfg, int32_t nranks, int32_t rank, int32_t share, sm_context** out);
+int sm_shard_range(sm_context* ctx, int32_t* x0, int32_t* x1);
+int sm_peer_export(sm_context* ctx, sm_peer_blob* out);
+int sm_peer_attach(sm_context* ctx, const sm_peer_blob* blobs, int32_t nblobs, int32_t use_ipc);
+
 /* ---- tables: soils[] / layers (surface.h:41-57,104; io.h:7-230 fills them) -------------------- */
 int sm_set_soils(sm_context* ctx, const sm_soil* soils, int32_t n);
 

@@ -34,7 +34,8 @@ SYMBOLS = [
     "sm_last_stats", "sm_water_begin", "sm_water_sweeps", "sm_water_state", "sm_wind_begin",
     "sm_wind_sweeps", "sm_wind_state", "sm_launch_count", "sm_device_alloc", "sm_device_free",
     "sm_device_upload", "sm_timer_start", "sm_timer_stop", "sm_set_soil_colors", "sm_mesh_update",
-    "sm_mesh_device_ptr", "sm_export_height", "sm_export_color",
+    "sm_mesh_device_ptr", "sm_export_height", "sm_export_color", "sm_create_sharded", "sm_shard_range",
+    "sm_peer_export", "sm_peer_attach",
 ]
 
 
@@ -89,20 +90,43 @@ def soils_from(table):
     return out
 
 
-class Context:
-    """One sm_context (one GPU)."""
+class PeerBlob(C.Structure):
+    _fields_ = [("ptr", C.c_uint64 * 16), ("ipc", (C.c_ubyte * 64) * 16), ("pool_cap", C.c_uint64),
+                ("rank", C.c_int32), ("device", C.c_int32)]
 
-    def __init__(self, dimx, dimy, scale=80, device=0, pool_capacity=0, max_particles=0):
+
+class Context:
+    """One sm_context (one GPU, or one rank of a sharded map)."""
+
+    def __init__(self, dimx, dimy, scale=80, device=0, pool_capacity=0, max_particles=0,
+                 nranks=1, rank=0, share=1):
         self.lib = load()
         self.dimx, self.dimy, self.scale = int(dimx), int(dimy), int(scale)
-        self.cells = self.dimx * self.dimy
         cfg = Config(self.dimx, self.dimy, self.scale, int(device), int(pool_capacity), int(max_particles), 0)
         h = C.c_void_p()
-        rc = self.lib.sm_create(C.byref(cfg), C.byref(h))
+        if nranks == 1:
+            rc = self.lib.sm_create(C.byref(cfg), C.byref(h))
+        else:
+            rc = self.lib.sm_create_sharded(C.byref(cfg), int(nranks), int(rank), int(share), C.byref(h))
         if rc != SM_OK:
             raise SoilMachineError(rc, self.lib.sm_last_error(None).decode())
         self.h = h
+        self.nranks, self.rank = int(nranks), int(rank)
+        x0, x1 = C.c_int32(), C.c_int32()
+        self.lib.sm_shard_range(self.h, C.byref(x0), C.byref(x1))
+        self.x0, self.x1 = x0.value, x1.value
+        self.map_cells = self.dimx * self.dimy                 # whole map (frequency arrays)
+        self.cells = (self.x1 - self.x0) * self.dimy           # this rank's strip (columns, heights)
         self._n = {"water": 0, "wind": 0}
+
+    def peer_export(self):
+        b = PeerBlob()
+        self._ck(self.lib.sm_peer_export(self.h, C.byref(b)))
+        return b
+
+    def peer_attach(self, blobs, use_ipc):
+        arr = (PeerBlob * len(blobs))(*blobs)
+        self._ck(self.lib.sm_peer_attach(self.h, arr, len(blobs), int(use_ipc)))
 
     def close(self):
         if getattr(self, "h", None):
@@ -156,12 +180,12 @@ class Context:
     def heights(self):
         out = np.zeros(self.cells)
         self._ck(self.lib.sm_download_height(self.h, _p(out, C.c_double)))
-        return out.reshape(self.dimx, self.dimy)
+        return out.reshape(self.x1 - self.x0, self.dimy)
 
     def surfaces(self):
         out = np.zeros(self.cells, np.int32)
         self._ck(self.lib.sm_download_surface(self.h, _p(out, C.c_int32)))
-        return out.reshape(self.dimx, self.dimy)
+        return out.reshape(self.x1 - self.x0, self.dimy)
 
     def height_sum(self):
         s = C.c_double()
@@ -169,7 +193,7 @@ class Context:
         return s.value
 
     def frequency(self):
-        a = [np.zeros(self.cells, np.float32) for _ in range(3)]
+        a = [np.zeros(self.map_cells, np.float32) for _ in range(3)]
         self._ck(self.lib.sm_get_frequency(self.h, *[_p(x, C.c_float) for x in a]))
         return {"water_frequency": a[0], "water_track": a[1], "wind_frequency": a[2]}
 

@@ -67,6 +67,10 @@ struct WindP {  // WindParticle state (wind.h:29-40)
 
 enum { SM_ALIVE = 0, SM_EXIT_OOB = 1, SM_EXIT_STALL = 2, SM_EXIT_EVAP = 3 };
 
+// Accessor contract used below: rec(x,y) -> mutable top record; focus(x,y) names the column whose pool
+// the next col_* call may touch (columns of different owners keep their buried sections in different
+// pools when the map is sharded); dirty(x,y); begin/target/cascade_prefetch are staging hints; mark(i)
+// is a profiling hook.
 // ------------------------------------------------------------------------------------------------
 // record-level column operations
 // ------------------------------------------------------------------------------------------------
@@ -319,8 +323,10 @@ template <int DEPTH, class A> struct Cascade {
       if (transfer > tsize) transfer = (float)tsize;                // :87-88 (f64 -> f32 narrowing)
       bool recascade = false;
       changed = true;
+      a.focus(tx, ty);
       if (col_remove(a, *tr, (double)transfer) != 0) recascade = true;   // :90-91
       a.dirty(tx, ty);
+      a.focus(bx, by);
       col_add(a, *a.rec(bx, by), (double)transfer, sp.cascades);    // :92
       a.dirty(bx, by);
       if constexpr (DEPTH > 0) {
@@ -395,6 +401,7 @@ template <class A> SM_HD int water_step(A& a, WaterP& p) {
   if (cdiff > 0) {                                                  // :91-101
     p.sediment += param.equrate * cdiff;
     p.contains = a.soil(rec_surface(*ir)).transports;
+    a.focus(ix, iy);
     double diff = col_remove(a, *ir, param.equrate * cdiff * p.volume);
     SM_UNROLL1
     while (fabs(diff) > 1E-8) diff = col_remove(a, *ir, diff);
@@ -402,6 +409,7 @@ template <class A> SM_HD int water_step(A& a, WaterP& p) {
   } else if (cdiff < 0) {                                           // :105-110
     const float eq = a.soil(p.contains).equrate;
     p.sediment += eq * cdiff;
+    a.focus(ix, iy);
     col_add(a, *ir, -eq * cdiff * p.volume, p.contains);
     a.dirty(ix, iy);
   }
@@ -463,6 +471,7 @@ template <class A> SM_HD int wind_step(A& a, WindP& p) {
       float len = sqrtf(p.sx * p.sx + p.sy * p.sy + p.sz * p.sz);
       double force = len * (map_height(a, nx, ny) - p.height) * (float)SCALE / 80.0f *
                      (1.0f - p.sediment);                           // :107
+      a.focus(ix, iy);
       double diff = col_remove(a, *ir, param.suspension * force);   // :109
       a.dirty(ix, iy);
       p.sediment += (param.suspension * force - diff);              // :110
@@ -471,8 +480,10 @@ template <class A> SM_HD int wind_step(A& a, WindP& p) {
   } else if (param.suspension > 0.0) {                              // :119
     const float sc = a.soil(p.contains).suspension;
     p.sediment -= sc * p.sediment;                                  // :121
+    a.focus(nx, ny);
     col_add(a, *a.rec(nx, ny), 0.5f * sc * p.sediment, p.contains); // :123
     a.dirty(nx, ny);
+    a.focus(ix, iy);
     col_add(a, *ir, 0.5f * sc * p.sediment, p.contains);            // :124
     a.dirty(ix, iy);
     ncascade = 2;                                                   // :126,129 cascade(ipos,1); cascade(npos,1)

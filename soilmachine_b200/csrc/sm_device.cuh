@@ -41,6 +41,28 @@ struct RunCtl {
   PoolRing ring[2];
   unsigned long long prof[16];  // clock64() phase totals (built with -DSM_PROFILE only)
   unsigned long long marks[8];  // finer marks inside interact()
+  // sharded maps: cross-rank barrier (every rank writes its arrival into every peer's copy)
+  unsigned int xflag[8];        // xflag[r] = last global barrier epoch rank r arrived at
+  unsigned int xalive[2][8];    // live particles rank r reported with that arrival (by epoch parity)
+  unsigned int alive_total[2];  // sum over ranks, for the local blocks
+  unsigned int release;         // global epoch the local blocks may pass
+  unsigned int epoch_base;      // global epoch at the start of the next launch (never reset)
+};
+
+// Pointers of one rank's arrays, as seen from this rank (own arrays, same-process contexts, or CUDA-IPC
+// mappings of a peer GPU's memory over NVLink).
+#define SM_MAX_RANKS 8
+struct PeerPtrs {
+  Sec32* top;                    // that rank's strip of top records
+  Sec32* pool;
+  uint32_t* ringbuf[2];
+  unsigned long long pool_cap;
+  RunCtl* ctl;
+  float4* pa; double2* pb; uint2* pc;
+  unsigned char* alive;
+  unsigned int* done;
+  unsigned long long* head[2];
+  uint2* node[2];
 };
 
 struct DevCtx {
@@ -65,7 +87,23 @@ struct DevCtx {
   unsigned long long* head[2];   // bin heads per sweep parity
   uint2* node[2];                // per particle: .x = next particle in the bin list, .y = ipos x<<16|y
   int nbx, nby;                  // allocated bin grid (for the smallest bin edge)
+  // sharding by x-strips: rank q owns the columns x in [q*strip_w, min((q+1)*strip_w, dimx)); its `top`
+  // holds only that strip.  nranks == 1: one strip = the whole map.
+  int nranks, rank, strip_w;
+  PeerPtrs peer[SM_MAX_RANKS];
 };
+
+template <bool MULTI> __device__ __forceinline__ int owner_of_x(const DevCtx& c, int x) {
+  if (!MULTI) return 0;
+  const int q = x / c.strip_w;
+  return q < c.nranks ? q : c.nranks - 1;
+}
+// top record of the global cell (x, y)
+template <bool MULTI> __device__ __forceinline__ Sec32* cell_ptr(const DevCtx& c, int x, int y) {
+  if (!MULTI) return &c.top[(size_t)x * c.dimy + y];
+  const int q = owner_of_x<true>(c, x);
+  return c.peer[q].top + (size_t)(x - q * c.strip_w) * c.dimy + y;
+}
 
 // ---- memory helpers: everything mutable is read through L2 (the TU is compiled -dlcm=cg) ----------
 __device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) {
@@ -83,6 +121,15 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
 __device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// system scope: the other end may be a different GPU
+__device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 // Grid-wide barrier for a co-resident (cooperative) grid: one arrival per block on a monotone
 // counter.  `epoch` is a per-thread copy of how many barriers this launch has passed.
@@ -97,6 +144,48 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
     __threadfence();
   }
   __syncthreads();
+}
+
+// Barrier across the blocks of EVERY rank of a sharded map.  Local blocks arrive on the local counter
+// (reset by the host before each launch); block 0's thread 0 then publishes this rank's arrival and its
+// live-particle count into every peer's RunCtl, waits for all peers, sums the counts and releases the
+// local blocks.  Cross-rank words use a global epoch that is never reset, so no rank can erase another
+// rank's arrival.  Returns the number of live particles over all ranks.
+__device__ __forceinline__ unsigned int grid_barrier_multi(const DevCtx& c, unsigned int& epoch, unsigned int gbase,
+                                                           unsigned int local_alive_slot) {
+  RunCtl* ctl = c.ctl;
+  __syncthreads();
+  epoch++;
+  const unsigned int ge = gbase + epoch;           // global epoch of this barrier
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    atomicAdd(&ctl->barrier, 1u);
+    if (blockIdx.x == 0) {
+      const unsigned int target = epoch * gridDim.x;
+      while ((int)(ld_volatile_u32(&ctl->barrier) - target) < 0) { }
+      __threadfence_system();
+      const unsigned int mine = ld_volatile_u32(&ctl->alive_slot[local_alive_slot]);
+      for (int q = 0; q < c.nranks; q++) {
+        RunCtl* pc = c.peer[q].ctl;
+        st_volatile_u32(&pc->xalive[ge & 1u][c.rank], mine);
+      }
+      __threadfence_system();
+      for (int q = 0; q < c.nranks; q++) st_release_sys_u32(&c.peer[q].ctl->xflag[c.rank], ge);
+      unsigned int total = 0;
+      for (int q = 0; q < c.nranks; q++) {
+        while ((int)(ld_acquire_sys_u32(&ctl->xflag[q]) - ge) < 0) { }
+        total += ld_volatile_u32(&ctl->xalive[ge & 1u][q]);
+      }
+      st_volatile_u32(&ctl->alive_total[ge & 1u], total);
+      __threadfence_system();
+      st_release_sys_u32(&ctl->release, ge);
+    } else {
+      while ((int)(ld_acquire_sys_u32(&ctl->release) - ge) < 0) { }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  return ld_volatile_u32(&ctl->alive_total[ge & 1u]);
 }
 
 // ---- accessor: direct global records ------------------------------------------------------------
@@ -116,6 +205,7 @@ struct DevAccess {
   __device__ __forceinline__ void dirty(int, int) {}
   __device__ __forceinline__ void cascade_prefetch(int, int) {}
   __device__ __forceinline__ void mark(int) {}
+  __device__ __forceinline__ void focus(int, int) {}
   __device__ __forceinline__ Sec32 pool_load(uint32_t i) { return c.pool[i]; }
   __device__ __forceinline__ void pool_store(uint32_t i, const Sec32& r) { c.pool[i] = r; }
   __device__ uint32_t pool_alloc() {
@@ -170,7 +260,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
-template <int KIND_>
+template <int KIND_, bool MULTI = false>
 struct WinAccess {
   const DevCtx& c;
   const SoilDev* s_soils;
@@ -180,6 +270,7 @@ struct WinAccess {
   uint32_t valid, dirtym;
   bool has_b;
   float f_freq, f_track;    // water: frequency/track at ipos | wind: wind frequency at ipos
+  int cur_q = 0;            // owner rank of the column the next col_* call works on (focus())
   long long t_begin = 0, t_target0 = 0, t_target1 = 0;
 #ifdef SM_PROFILE
   long long t_last = 0; unsigned long long t_mark[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -208,7 +299,7 @@ struct WinAccess {
         if ((unsigned)dx < 3u && (unsigned)dy < 3u) need = false;   // resolves to patch A
       }
       if (need) {
-        const Sec32* src = &c.top[(size_t)x * c.dimy + y];
+        const Sec32* src = cell_ptr<MULTI>(c, x, y);
         cp_async16(&win[base + k], src);
         cp_async16(((char*)&win[base + k]) + 16, ((const char*)src) + 16);
         got |= 1u << k;
@@ -253,7 +344,7 @@ struct WinAccess {
   }
   __device__ __forceinline__ Sec32* rec(int x, int y) {
     const int s = slot_of(x, y);
-    Sec32* g = &c.top[(size_t)x * c.dimy + y];
+    Sec32* g = cell_ptr<MULTI>(c, x, y);
     if (s < 0) return g;
     if (!((valid >> s) & 1u)) { win[s] = *g; valid |= 1u << s; }
     return &win[s];
@@ -271,14 +362,39 @@ struct WinAccess {
       int x, y;
       if (s < 9) { x = ax + s / 3 - 1; y = ay + s % 3 - 1; }
       else { x = bx + (s - 9) / 3 - 1; y = by + (s - 9) % 3 - 1; }
-      c.top[(size_t)x * c.dimy + y] = win[s];
+      *cell_ptr<MULTI>(c, x, y) = win[s];
     }
     dirtym = 0;
   }
-  __device__ __forceinline__ Sec32 pool_load(uint32_t i) { return c.pool[i]; }
-  __device__ __forceinline__ void pool_store(uint32_t i, const Sec32& r) { c.pool[i] = r; }
-  __device__ uint32_t pool_alloc() { DevAccess d(c, s_soils, phase); return d.pool_alloc(); }
-  __device__ void pool_free(uint32_t i) { DevAccess d(c, s_soils, phase); d.pool_free(i); }
+  __device__ __forceinline__ void focus(int x, int) { if (MULTI) cur_q = owner_of_x<true>(c, x); }
+  __device__ __forceinline__ Sec32 pool_load(uint32_t i) { return MULTI ? c.peer[cur_q].pool[i] : c.pool[i]; }
+  __device__ __forceinline__ void pool_store(uint32_t i, const Sec32& r) {
+    if (MULTI) c.peer[cur_q].pool[i] = r; else c.pool[i] = r;
+  }
+  __device__ uint32_t pool_alloc() {
+    if (!MULTI) { DevAccess d(c, s_soils, phase); return d.pool_alloc(); }
+    // same ticket pop as DevAccess::pool_alloc, on the owner's rings / bump counter
+    const PeerPtrs& P = c.peer[cur_q];
+    PoolRing* R = &P.ctl->ring[phase ^ 1u];
+    const unsigned long long t = *((volatile unsigned long long*)&R->tail);
+    if (*((volatile unsigned long long*)&R->head) < t) {
+      const unsigned long long h = atomicAdd(&R->head, 1ull);
+      if (h < t) return P.ringbuf[phase ^ 1u][h % P.pool_cap];
+      atomicMin(&R->head, t);
+    }
+    unsigned long long b = atomicAdd(&P.ctl->bump, 1ull);
+    if (b < P.pool_cap) return (uint32_t)b;
+    atomicOr(&c.ctl->err, 1u << 3);
+    atomicAdd(&c.ctl->drops, 1ull);
+    return SM_NIL;
+  }
+  __device__ void pool_free(uint32_t i) {
+    if (!MULTI) { DevAccess d(c, s_soils, phase); d.pool_free(i); return; }
+    const PeerPtrs& P = c.peer[cur_q];
+    PoolRing* R = &P.ctl->ring[phase];
+    unsigned long long t = atomicAdd(&R->tail, 1ull);
+    P.ringbuf[phase][t % P.pool_cap] = i;
+  }
   __device__ __forceinline__ void track_add(int ind, double v) {     // water.h:348-351
     c.wtrack[ind] = (float)(f_track + v);
   }

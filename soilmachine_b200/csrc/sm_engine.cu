@@ -57,16 +57,18 @@ __device__ __forceinline__ int particle_reach(const WindP& p) {
 // ---------------------------------------------------------------------------------------------
 // bins
 // ---------------------------------------------------------------------------------------------
-template <int KIND>
-__device__ __forceinline__ void bin_insert(const DevCtx& c, unsigned int tag, int pid, int ix, int iy, int R) {
+template <int KIND, bool MULTI = false>
+__device__ __forceinline__ void bin_insert(const DevCtx& c, unsigned int tag, int pid, int ix, int iy, int R, int q = 0) {
+  // q = rank that owns the column x = ix (the bins, like the particle, live with the owner)
   const unsigned int par = tag & 1u;
   const int G = Reach<KIND>::G;
   const int nby = (c.dimy + G - 1) / G;
   const int b = (ix / G) * nby + (iy / G);
+  unsigned long long* head = MULTI ? c.peer[q].head[par] : c.head[par];
+  uint2* node = MULTI ? c.peer[q].node[par] : c.node[par];
   unsigned long long old =
-      atomicExch(&c.head[par][b], ((unsigned long long)tag << 32) | (unsigned long long)(uint32_t)pid);
-  c.node[par][pid] = make_uint2(((unsigned int)(old >> 32) == tag) ? (uint32_t)old : SM_NIL,
-                                SM_PACK_NODE(ix, iy, R));
+      atomicExch(&head[b], ((unsigned long long)tag << 32) | (unsigned long long)(uint32_t)pid);
+  node[pid] = make_uint2(((unsigned int)(old >> 32) == tag) ? (uint32_t)old : SM_NIL, SM_PACK_NODE(ix, iy, R));
 }
 
 // Conflict detection for one particle and one sweep.  Lists were completed before the grid barrier
@@ -78,7 +80,9 @@ __device__ __forceinline__ void bin_insert(const DevCtx& c, unsigned int tag, in
 // Every particle always waits for its own-bin predecessor, hence "X done" implies "every lower index
 // in X's bin is done", which makes the per-bin predecessors a complete (conservative) blocker set and
 // the hand-off from the last blocker to this particle O(1).
-template <int KIND>
+// Sharded maps: a neighbouring bin may belong to another rank; list entries carry that rank in bits 28-31
+// (the blocker's `done` word lives with the rank that executes it this sweep = the owner of its bin).
+template <int KIND, bool MULTI = false>
 __device__ __forceinline__ unsigned int scan_blockers(const DevCtx& c, unsigned int tag, int pid, int ix, int iy,
                                                       int R, uint32_t (&list)[9]) {
   const unsigned int par = tag & 1u;
@@ -89,8 +93,9 @@ __device__ __forceinline__ unsigned int scan_blockers(const DevCtx& c, unsigned 
 #pragma unroll
   for (int k = 0; k < 9; k++) {
     const int cx = bx + k / 3 - 1, cy = by + k % 3 - 1;
+    const unsigned long long* hp = MULTI ? c.peer[owner_of_x<MULTI>(c, (cx < 0 ? 0 : cx) * G)].head[par] : c.head[par];
     heads[k] = (cx >= 0 && cx < nbx && cy >= 0 && cy < nby)
-                   ? *((volatile unsigned long long*)&c.head[par][cx * nby + cy]) : 0ull;
+                   ? *((volatile const unsigned long long*)&hp[cx * nby + cy]) : 0ull;
   }
   const int K = 6;
   uint32_t near_[K];
@@ -106,10 +111,13 @@ __device__ __forceinline__ unsigned int scan_blockers(const DevCtx& c, unsigned 
     if ((unsigned int)(h >> 32) != tag) continue;
     uint32_t j = (uint32_t)h;
     uint32_t best = SM_NIL;
+    const int bq = MULTI ? owner_of_x<MULTI>(c, (bx + k / 3 - 1) * G) : 0;
+    const uint2* nodes = MULTI ? c.peer[bq].node[par] : c.node[par];
+    const uint32_t qtag = MULTI ? ((uint32_t)bq << 28) : 0u;
     while (j != SM_NIL) {
-      const uint2 nd = c.node[par][j];
+      const uint2 nd = nodes[j];
       if (j < (uint32_t)pid) {
-        if (best == SM_NIL || j > best) best = j;
+        if (best == SM_NIL || (j | qtag) > best) best = j | qtag;
         int dx = (int)(nd.y >> 18) - ix, dy = (int)((nd.y >> 4) & 0x3FFFu) - iy;
         const int D = R + (int)(nd.y & 0xFu);       // the two footprints can meet iff |d| <= R_A + R_B
         dx = dx < 0 ? -dx : dx;
@@ -117,7 +125,7 @@ __device__ __forceinline__ unsigned int scan_blockers(const DevCtx& c, unsigned 
         if (dx <= D && dy <= D) {
           if (nnear < K) {
 #pragma unroll
-            for (int q = 0; q < K; q++) if (q == nnear) near_[q] = j;
+            for (int q = 0; q < K; q++) if (q == nnear) near_[q] = j | qtag;
             nnear++;
           } else crowded = true;
         }
@@ -136,16 +144,21 @@ __device__ __forceinline__ unsigned int scan_blockers(const DevCtx& c, unsigned 
 }
 
 // poll the still-unfinished blockers once; returns the mask of those not yet done
+template <bool MULTI = false>
 __device__ __forceinline__ unsigned int poll_blockers(const DevCtx& c, unsigned int tag, const uint32_t (&list)[9],
                                                       unsigned int mask) {
 #pragma unroll
   for (int k = 0; k < 9; k++) {
     if ((mask >> k) & 1u) {
+      if (MULTI) {
+        if (ld_acquire_sys_u32(&c.peer[list[k] >> 28].done[list[k] & 0x0FFFFFFFu]) >= tag) mask &= ~(1u << k);
+      } else {
 #ifdef SM_ACQREL
-      if (ld_acquire_u32(&c.done[list[k]]) >= tag) mask &= ~(1u << k);
+        if (ld_acquire_u32(&c.done[list[k]]) >= tag) mask &= ~(1u << k);
 #else
-      if (ld_volatile_u32(&c.done[list[k]]) >= tag) mask &= ~(1u << k);
+        if (ld_volatile_u32(&c.done[list[k]]) >= tag) mask &= ~(1u << k);
 #endif
+      }
     }
   }
   return mask;
@@ -187,7 +200,13 @@ __device__ __forceinline__ void ctl_marks(RunCtl* ctl, const unsigned long long*
   for (int i = 1; i < 8; i++) if (m[i]) atomicAdd(&ctl->marks[i], m[i]);
 }
 #endif
-template <int KIND>
+// MULTI = the map is sharded by x-strips over several ranks (GPUs, or contexts sharing one GPU): a
+// rank executes the particles whose ipos lies in its strip, reads/writes halo records, bins and `done`
+// words of its neighbours through peer pointers, hands a particle that leaves the strip over to the new
+// owner (state, bin entry and alive flag are written into the owner's arrays before the barrier) and
+// synchronises sweeps with the cross-rank barrier.  The canonical order is unchanged, so an N-rank run
+// is bit-identical to the 1-rank run.
+template <int KIND, bool MULTI>
 __global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run(DevCtx c, int n, const float* __restrict__ spawn,
                                             int max_sweeps, int lshift) {
   typedef typename PType<KIND>::T P;
@@ -202,6 +221,7 @@ __global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run(DevCtx c, int n,
   RunCtl* ctl = c.ctl;
   unsigned int epoch = 0;
   const unsigned int tag0 = ctl->tag_base;   // constant during the launch (rewritten at the very end)
+  const unsigned int gbase = MULTI ? ctl->epoch_base : 0u;
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const bool leader = (gtid & ((1 << lshift) - 1)) == 0;
   const int slot = gtid >> lshift;
@@ -213,27 +233,30 @@ __global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run(DevCtx c, int n,
   SM_PROF_DECL
 
   // ---- prologue: spawn (ctor bodies water.h:13-17 / wind.h:15-20) or resume, fill the bins ----
+  unsigned int total_alive = 0;
   {
     unsigned int my_alive = 0;
     if (leader) {
       for (int pid = slot; pid < n; pid += nslots) {
-        P p;
         bool alive;
         if (spawn != nullptr) {
-          DevAccess a(c, s_soils, tag0);
           const float x = spawn[2 * pid], y = spawn[2 * pid + 1];
+          const int sx = (int)roundf(x), sy = (int)roundf(y);
+          if (MULTI && owner_of_x<MULTI>(c, sx) != c.rank) {     // another rank spawns this one
+            c.alive[pid] = 0;
+            continue;
+          }
+          const uint32_t contains = s_soils[rec_surface(*cell_ptr<MULTI>(c, sx, sy))].transports;
           if (KIND == KIND_WATER) {
-            WaterP w{x, y, 0.0f, 0.0f, 1.0, 0.0, 0u};
-            w.contains = spawn_contains(a, x, y);
+            WaterP w{x, y, 0.0f, 0.0f, 1.0, 0.0, contains};
             store_particle(c, pid, w);
             alive = true;
           } else {
-            WindP w{x, y, -2.0f, 0.0f, 1.0f, 0.0, 0.0, 0u};
-            w.contains = spawn_contains(a, x, y);
+            WindP w{x, y, -2.0f, 0.0f, 1.0f, 0.0, 0.0, contains};
             store_particle(c, pid, w);
             // wind.h:56-57: a particle whose load cannot be suspended dies in its first move()
             // without touching anything
-            alive = !(s_soils[w.contains].suspension == 0.0);
+            alive = !(s_soils[contains].suspension == 0.0);
             if (!alive) { n_oob++; any_doa = true; }
           }
           c.alive[pid] = alive ? 1 : 0;
@@ -244,7 +267,7 @@ __global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run(DevCtx c, int n,
         if (alive) {
           P q;
           load_particle(c, pid, q);
-          bin_insert<KIND>(c, tag0, pid, (int)roundf(q.px), (int)roundf(q.py), particle_reach(q));
+          bin_insert<KIND, MULTI>(c, tag0, pid, (int)roundf(q.px), (int)roundf(q.py), particle_reach(q), c.rank);
           my_alive++;
         }
       }
@@ -255,14 +278,14 @@ __global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run(DevCtx c, int n,
       if (s_alive) atomicAdd(&ctl->alive_slot[0], s_alive);
       s_alive = 0;
     }
-    grid_barrier(&ctl->barrier, epoch);
+    if (MULTI) total_alive = grid_barrier_multi(c, epoch, gbase, 0u);
+    else grid_barrier(&ctl->barrier, epoch);
   }
 
   int s = 0;
-  unsigned int total_alive = 0;
   for (;; s++) {
     const unsigned int tag = tag0 + (unsigned int)s;
-    total_alive = ld_volatile_u32(&ctl->alive_slot[s % 3]);
+    if (!MULTI) total_alive = ld_volatile_u32(&ctl->alive_slot[s % 3]);
     if (total_alive == 0 || (max_sweeps >= 0 && s >= max_sweeps)) break;
     if (gtid == 0) st_volatile_u32(&ctl->alive_slot[(s + 2) % 3], 0u);
 
@@ -283,12 +306,12 @@ __global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run(DevCtx c, int n,
         ix = (int)roundf(p.px); iy = (int)roundf(p.py);
         SM_PROF(1)   // state load
         myR = particle_reach(p);
-        waitmask = scan_blockers<KIND>(c, tag, pid, ix, iy, myR, list);
+        waitmask = scan_blockers<KIND, MULTI>(c, tag, pid, ix, iy, myR, list);
         SM_PROF(2)   // blocker scan
       }
       bool pending = has;
       for (;;) {
-        if (pending && waitmask) waitmask = poll_blockers(c, tag, list, waitmask);
+        if (pending && waitmask) waitmask = poll_blockers<MULTI>(c, tag, list, waitmask);
         const bool ready = pending && waitmask == 0;
         if (__ballot_sync(0xffffffffu, pending) == 0u) break;
 #ifdef SM_NOSLEEP
@@ -302,7 +325,7 @@ __global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run(DevCtx c, int n,
           __threadfence();
 #endif
           SM_PROF(3)   // acquire fence
-          WinAccess<KIND> a(c, s_soils, tag, my_win);
+          WinAccess<KIND, MULTI> a(c, s_soils, tag, my_win);
           const int r = do_step(a, p);
 #ifdef SM_PROFILE
           { long long t_ = clock64();
@@ -313,15 +336,18 @@ __global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run(DevCtx c, int n,
           SM_PROF(4)   // step
           // hand-off first: the map writes are all the successors of this step wait for
           a.flush();
+          if (MULTI) {
+            st_release_sys_u32(&c.done[pid], r == SM_ALIVE ? tag : 0xFFFFFFFFu);
+          } else {
 #ifdef SM_ACQREL
-          st_release_u32(&c.done[pid], r == SM_ALIVE ? tag : 0xFFFFFFFFu);
+            st_release_u32(&c.done[pid], r == SM_ALIVE ? tag : 0xFFFFFFFFu);
 #else
-          __threadfence();
-          st_volatile_u32(&c.done[pid], r == SM_ALIVE ? tag : 0xFFFFFFFFu);
+            __threadfence();
+            st_volatile_u32(&c.done[pid], r == SM_ALIVE ? tag : 0xFFFFFFFFu);
 #endif
+          }
           SM_PROF(6)   // write-back + release fence + publish
           // own state and next sweep's bins are only needed after the grid barrier
-          store_particle(c, pid, p);
           if (r == SM_ALIVE) {
             n_steps++;
             const int jx = (int)roundf(p.px), jy = (int)roundf(p.py);
@@ -329,9 +355,22 @@ __global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run(DevCtx c, int n,
             ddx = ddx < 0 ? -ddx : ddx; ddy = ddy < 0 ? -ddy : ddy;
             const int lim = myR - Reach<KIND>::RING;      // the step promised to stay within ipos +- lim
             if (ddx > lim || ddy > lim) atomicOr(&ctl->err, 1u << 4);  // SM_ERR_REACH
-            bin_insert<KIND>(c, tag + 1u, pid, jx, jy, particle_reach(p));
+            const int nq = owner_of_x<MULTI>(c, jx);
+            if (MULTI && nq != c.rank) {
+              // the particle leaves this strip: hand it to the new owner (its arrays, its bins)
+              DevCtx o = c;   // view of the owner's particle arrays
+              o.pa = c.peer[nq].pa; o.pb = c.peer[nq].pb; o.pc = c.peer[nq].pc;
+              store_particle(o, pid, p);
+              c.peer[nq].done[pid] = tag;            // it has completed this sweep, wherever it is asked
+              c.peer[nq].alive[pid] = 1;
+              c.alive[pid] = 0;
+            } else {
+              store_particle(c, pid, p);
+            }
+            bin_insert<KIND, MULTI>(c, tag + 1u, pid, jx, jy, particle_reach(p), nq);
             my_alive++;
           } else {
+            store_particle(c, pid, p);
             c.alive[pid] = 0;
             if (r == SM_EXIT_OOB) n_oob++;
             else if (r == SM_EXIT_STALL) n_stall++;
@@ -349,7 +388,8 @@ __global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run(DevCtx c, int n,
       if (s_alive) atomicAdd(&ctl->alive_slot[(s + 1) % 3], s_alive);
       s_alive = 0;
     }
-    grid_barrier(&ctl->barrier, epoch);
+    if (MULTI) total_alive = grid_barrier_multi(c, epoch, gbase, (unsigned int)((s + 1) % 3));
+    else grid_barrier(&ctl->barrier, epoch);
     SM_PROF(7)   // grid barrier
   }
   if (leader && slot < n) SM_PROF_FLUSH(ctl)
@@ -366,6 +406,7 @@ __global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run(DevCtx c, int n,
     atomicMax(&ctl->sweeps, (unsigned long long)s);
     ctl->alive = total_alive;
     ctl->tag_base = tag0 + (unsigned int)s + 2u;
+    if (MULTI) ctl->epoch_base = gbase + epoch;
   }
 }
 
@@ -688,10 +729,12 @@ __global__ void k_height_sum2(const double* __restrict__ partial, double* __rest
 struct LayerSet { LayerDev L[SM_MAX_LAYERS]; int zslice[SM_MAX_LAYERS]; int n; };
 __global__ void k_initialize(DevCtx c, LayerSet ls) {
   DevAccess a(c, nullptr, 0u);
-  const size_t cells = (size_t)c.dimx * c.dimy;
+  const int x0 = c.rank * c.strip_w;
+  const int x1 = (x0 + c.strip_w < c.dimx) ? x0 + c.strip_w : c.dimx;
+  const size_t cells = (size_t)(x1 - x0) * c.dimy;                 // this rank's strip
   for (size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x; cell < cells;
        cell += (size_t)gridDim.x * blockDim.x) {
-    const int i = (int)(cell / c.dimy), j = (int)(cell % c.dimy);
+    const int i = x0 + (int)(cell / c.dimy), j = (int)(cell % c.dimy);
     Sec32 r;
     rec_set_empty(r);
     for (int l = 0; l < ls.n; l++) {
@@ -820,7 +863,11 @@ struct sm_context {
   std::string err;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr;
-  size_t cells = 0;
+  size_t cells = 0;        // cells of the whole map (frequency arrays, bins)
+  size_t lcells = 0;       // cells of this rank's x-strip (top records); == cells when not sharded
+  int nranks = 1, rank = 0, x0 = 0, x1 = 0, share = 1;
+  bool peers_attached = false;
+  void* ipc_opened[SM_MAX_RANKS][16] = {};
   int max_particles = 0;
   int nsoils = 0;
   SoilDev* d_soils = nullptr;
@@ -870,6 +917,7 @@ void sm_destroy(sm_context* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
   cudaDeviceSynchronize();
+  for (int q = 0; q < SM_MAX_RANKS; q++) for (int i = 0; i < 16; i++) if (ctx->ipc_opened[q][i]) cudaIpcCloseMemHandle(ctx->ipc_opened[q][i]);
   DevCtx& d = ctx->d;
   cudaFree(d.top); cudaFree(d.pool); cudaFree(d.ringbuf[0]); cudaFree(d.ringbuf[1]);
   cudaFree(d.wfreq); cudaFree(d.wtrack); cudaFree(d.windfreq); cudaFree(ctx->d_soils);
@@ -889,6 +937,7 @@ void sm_destroy(sm_context* ctx) {
 static int alloc_pool(sm_context* ctx, unsigned long long cap) {
   DevCtx& d = ctx->d;
   if (d.pool && d.pool_cap >= cap) return SM_OK;
+  if (d.pool && ctx->nranks > 1) return fail(ctx, SM_ERR_POOL, "sharded context: pool_capacity is fixed at creation and too small");
   cudaFree(d.pool); cudaFree(d.ringbuf[0]); cudaFree(d.ringbuf[1]);
   d.pool = nullptr; d.ringbuf[0] = d.ringbuf[1] = nullptr;
   CK(cudaMalloc(&d.pool, cap * sizeof(Sec32)));
@@ -898,9 +947,17 @@ static int alloc_pool(sm_context* ctx, unsigned long long cap) {
   return SM_OK;
 }
 
-int sm_create(const sm_config* cfg, sm_context** out) {
-  if (!cfg || !out || cfg->dimx < 2 || cfg->dimy < 2 || cfg->dimx > 16384 || cfg->dimy > 16384) {
+static int create_impl(const sm_config* cfg, int nranks, int rank, int share, sm_context** out) {
+  if (!cfg || !out || cfg->dimx < 2 || cfg->dimy < 2 || cfg->dimx > 16384 || cfg->dimy > 16384 ||
+      nranks < 1 || nranks > SM_MAX_RANKS || rank < 0 || rank >= nranks || share < 1) {
     g_create_err = "sm_create: invalid configuration";
+    return SM_ERR_INVALID;
+  }
+  // x-strips of equal width (a multiple of the largest bin edge, 16 cells)
+  const int strip_w = (nranks == 1) ? cfg->dimx : ((((cfg->dimx + nranks - 1) / nranks) + 15) / 16) * 16;
+  const int sx0 = rank * strip_w, sx1 = std::min(cfg->dimx, sx0 + strip_w);
+  if (sx1 <= sx0) {
+    g_create_err = "sm_create_sharded: the map is too narrow for this many ranks (needs >= 16 columns per rank)";
     return SM_ERR_INVALID;
   }
   int ndev = 0;
@@ -924,9 +981,13 @@ int sm_create(const sm_config* cfg, sm_context** out) {
     DevCtx& d = ctx->d;
     d.dimx = cfg->dimx; d.dimy = cfg->dimy; d.scale = cfg->scale;
     ctx->cells = (size_t)cfg->dimx * cfg->dimy;
+    ctx->nranks = nranks; ctx->rank = rank; ctx->share = share; ctx->x0 = sx0; ctx->x1 = sx1;
+    ctx->lcells = (size_t)(sx1 - sx0) * cfg->dimy;
+    d.nranks = nranks; d.rank = rank; d.strip_w = strip_w;
     ctx->max_particles = cfg->max_particles > 0 ? cfg->max_particles : 262144;
     const size_t C = ctx->cells, N = (size_t)ctx->max_particles;
-    CK(cudaMalloc(&d.top, C * sizeof(Sec32)));
+    const size_t LC = ctx->lcells;
+    CK(cudaMalloc(&d.top, LC * sizeof(Sec32)));
     CK(cudaMalloc(&d.wfreq, C * 4)); CK(cudaMalloc(&d.wtrack, C * 4)); CK(cudaMalloc(&d.windfreq, C * 4));
     CK(cudaMemsetAsync(d.wfreq, 0, C * 4, ctx->stream));
     CK(cudaMemsetAsync(d.wtrack, 0, C * 4, ctx->stream));
@@ -953,16 +1014,19 @@ int sm_create(const sm_config* cfg, sm_context** out) {
     CK(cudaMemcpyAsync(d.ctl, &init, sizeof(RunCtl), cudaMemcpyHostToDevice, ctx->stream));
     // empty terrain
     {
-      std::vector<Sec32> empty(C);
+      std::vector<Sec32> empty(LC);
       for (auto& r : empty) rec_set_empty(r);
-      CK(cudaMemcpyAsync(d.top, empty.data(), C * sizeof(Sec32), cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(d.top, empty.data(), LC * sizeof(Sec32), cudaMemcpyHostToDevice, ctx->stream));
       CK(cudaStreamSynchronize(ctx->stream));
     }
+    // sharded contexts export their pool to the peers, so it is sized once and never re-allocated
     int rcp = alloc_pool(ctx, cfg->pool_capacity > 0 ? (unsigned long long)cfg->pool_capacity
-                                                     : (unsigned long long)C + (4ull << 20));
+                                                     : (unsigned long long)LC * (nranks > 1 ? 2 : 1) + (4ull << 20));
     if (rcp != SM_OK) return rcp;
-    CK(cudaFuncSetAttribute(k_run<KIND_WATER>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BLOCK * SM_WIN_BYTES));
-    CK(cudaFuncSetAttribute(k_run<KIND_WIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BLOCK * SM_WIN_BYTES));
+    CK(cudaFuncSetAttribute(k_run<KIND_WATER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BLOCK * SM_WIN_BYTES));
+    CK(cudaFuncSetAttribute(k_run<KIND_WIND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BLOCK * SM_WIN_BYTES));
+    CK(cudaFuncSetAttribute(k_run<KIND_WATER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BLOCK * SM_WIN_BYTES));
+    CK(cudaFuncSetAttribute(k_run<KIND_WIND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BLOCK * SM_WIN_BYTES));
     CK(cudaFuncSetAttribute(k_run_async<KIND_WIND, SM_ASYNC_DELTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BLOCK * SM_WIN_BYTES));
     CK(cudaStreamSynchronize(ctx->stream));
     return SM_OK;
@@ -973,6 +1037,80 @@ int sm_create(const sm_config* cfg, sm_context** out) {
     return rc;
   }
   *out = ctx;
+  return SM_OK;
+}
+
+int sm_create(const sm_config* cfg, sm_context** out) { return create_impl(cfg, 1, 0, 1, out); }
+int sm_create_sharded(const sm_config* cfg, int32_t nranks, int32_t rank, int32_t share, sm_context** out) {
+  return create_impl(cfg, nranks, rank, share, out);
+}
+int sm_shard_range(sm_context* ctx, int32_t* x0, int32_t* x1) {
+  if (x0) *x0 = ctx->x0;
+  if (x1) *x1 = ctx->x1;
+  return SM_OK;
+}
+
+// ---- peers of a sharded map ----------------------------------------------------------------------------
+static void own_ptrs(sm_context* ctx, void** p) {
+  DevCtx& d = ctx->d;
+  p[0] = d.top; p[1] = d.pool; p[2] = d.ringbuf[0]; p[3] = d.ringbuf[1]; p[4] = d.ctl; p[5] = d.pa; p[6] = d.pb;
+  p[7] = d.pc; p[8] = d.alive; p[9] = d.done; p[10] = d.head[0]; p[11] = d.head[1]; p[12] = d.node[0]; p[13] = d.node[1];
+}
+static void fill_peer(PeerPtrs& P, void* const* p, unsigned long long pool_cap) {
+  P.top = (Sec32*)p[0]; P.pool = (Sec32*)p[1]; P.ringbuf[0] = (uint32_t*)p[2]; P.ringbuf[1] = (uint32_t*)p[3];
+  P.ctl = (RunCtl*)p[4]; P.pa = (float4*)p[5]; P.pb = (double2*)p[6]; P.pc = (uint2*)p[7];
+  P.alive = (unsigned char*)p[8]; P.done = (unsigned int*)p[9]; P.head[0] = (unsigned long long*)p[10];
+  P.head[1] = (unsigned long long*)p[11]; P.node[0] = (uint2*)p[12]; P.node[1] = (uint2*)p[13];
+  P.pool_cap = pool_cap;
+}
+int sm_peer_export(sm_context* ctx, sm_peer_blob* out) {
+  if (!out) return fail(ctx, SM_ERR_INVALID, "null blob");
+  CK(cudaSetDevice(ctx->cfg.device));
+  memset(out, 0, sizeof(*out));
+  void* p[16] = {};
+  own_ptrs(ctx, p);
+  for (int i = 0; i < SM_PEER_ARRAYS; i++) {
+    out->ptr[i] = (uint64_t)(uintptr_t)p[i];
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, p[i]));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(out->ipc[i], &h, 64);
+  }
+  out->pool_cap = ctx->d.pool_cap;
+  out->rank = ctx->rank;
+  out->device = ctx->cfg.device;
+  return SM_OK;
+}
+int sm_peer_attach(sm_context* ctx, const sm_peer_blob* blobs, int32_t nblobs, int32_t use_ipc) {
+  if (!blobs || nblobs != ctx->nranks) return fail(ctx, SM_ERR_INVALID, "sm_peer_attach: one blob per rank");
+  CK(cudaSetDevice(ctx->cfg.device));
+  for (int q = 0; q < ctx->nranks; q++) {
+    const sm_peer_blob& b = blobs[q];
+    if (b.rank != q) return fail(ctx, SM_ERR_INVALID, "sm_peer_attach: blobs must be ordered by rank");
+    void* p[16] = {};
+    if (q == ctx->rank) {
+      own_ptrs(ctx, p);
+    } else if (!use_ipc) {
+      for (int i = 0; i < SM_PEER_ARRAYS; i++) p[i] = (void*)(uintptr_t)b.ptr[i];   // same process
+    } else {
+      if (b.device != ctx->cfg.device) {
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, ctx->cfg.device, b.device));
+        if (!can) return fail(ctx, SM_ERR_CUDA, "sm_peer_attach: no peer access between the devices");
+        cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { ctx->err = cudaGetErrorString(e); return SM_ERR_CUDA; }
+        cudaGetLastError();
+      }
+      for (int i = 0; i < SM_PEER_ARRAYS; i++) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, b.ipc[i], 64);
+        CK(cudaIpcOpenMemHandle(&p[i], h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->ipc_opened[q][i] = p[i];
+      }
+    }
+    fill_peer(ctx->d.peer[q], p, b.pool_cap);
+  }
+  ctx->peers_attached = true;
   return SM_OK;
 }
 
@@ -1028,7 +1166,7 @@ int sm_upload_columns(sm_context* ctx, const int64_t* offsets, const int32_t* ty
                       const double* saturation) {
   if (!offsets || !type || !size) return fail(ctx, SM_ERR_INVALID, "sm_upload_columns: null argument");
   CK(cudaSetDevice(ctx->cfg.device));
-  const size_t C = ctx->cells;
+  const size_t C = ctx->lcells;   // CSR of this rank's strip, cell order (x - x0)*dimy + y
   std::vector<Sec32> top(C), pool;
   pool.reserve((size_t)std::max<int64_t>(0, offsets[C] - (int64_t)C) + 16);
   HostBuild hb{&pool};
@@ -1044,7 +1182,7 @@ int sm_upload_columns(sm_context* ctx, const int64_t* offsets, const int32_t* ty
   if (ctx->cfg.pool_capacity > 0) {
     if (need > ctx->d.pool_cap) return fail(ctx, SM_ERR_POOL, "sm_upload_columns: pool_capacity too small");
   } else {
-    int rc = alloc_pool(ctx, need + (unsigned long long)C + (4ull << 20));
+    int rc = alloc_pool(ctx, ctx->nranks > 1 ? need : need + (unsigned long long)C + (4ull << 20));
     if (rc != SM_OK) return rc;
   }
   CK(cudaMemcpy(ctx->d.top, top.data(), C * sizeof(Sec32), cudaMemcpyHostToDevice));
@@ -1058,9 +1196,9 @@ static int fetch_image(sm_context* ctx, std::vector<Sec32>& top, std::vector<Sec
   RunCtl h;
   CK(cudaMemcpy(&h, ctx->d.ctl, sizeof(RunCtl), cudaMemcpyDeviceToHost));
   const size_t used = (size_t)std::min<unsigned long long>(h.bump, ctx->d.pool_cap);
-  top.resize(ctx->cells);
+  top.resize(ctx->lcells);
   pool.resize(used);
-  CK(cudaMemcpy(top.data(), ctx->d.top, ctx->cells * sizeof(Sec32), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(top.data(), ctx->d.top, ctx->lcells * sizeof(Sec32), cudaMemcpyDeviceToHost));
   if (used) CK(cudaMemcpy(pool.data(), ctx->d.pool, used * sizeof(Sec32), cudaMemcpyDeviceToHost));
   return SM_OK;
 }
@@ -1112,27 +1250,27 @@ int sm_download_columns(sm_context* ctx, int64_t capacity, int64_t* offsets, int
 
 int sm_download_height(sm_context* ctx, double* height) {
   CK(cudaSetDevice(ctx->cfg.device));
-  k_heights<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(ctx->d.top, ctx->d_scratch, nullptr, ctx->cells);
+  k_heights<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(ctx->d.top, ctx->d_scratch, nullptr, ctx->lcells);
   ctx->launches++;
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(height, ctx->d_scratch, ctx->cells * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(height, ctx->d_scratch, ctx->lcells * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return SM_OK;
 }
 
 int sm_download_surface(sm_context* ctx, int32_t* surface) {
   CK(cudaSetDevice(ctx->cfg.device));
-  k_heights<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(ctx->d.top, nullptr, ctx->d_iscratch, ctx->cells);
+  k_heights<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(ctx->d.top, nullptr, ctx->d_iscratch, ctx->lcells);
   ctx->launches++;
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(surface, ctx->d_iscratch, ctx->cells * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(surface, ctx->d_iscratch, ctx->lcells * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return SM_OK;
 }
 
 int sm_height_sum(sm_context* ctx, double* sum) {
   CK(cudaSetDevice(ctx->cfg.device));
-  k_height_sum1<<<SUM_BLOCKS, 256, 0, ctx->stream>>>(ctx->d.top, ctx->cells, ctx->d_scratch);
+  k_height_sum1<<<SUM_BLOCKS, 256, 0, ctx->stream>>>(ctx->d.top, ctx->lcells, ctx->d_scratch);
   k_height_sum2<<<1, 256, 0, ctx->stream>>>(ctx->d_scratch, ctx->d_scratch + SUM_BLOCKS);
   ctx->launches += 2;
   CK(cudaGetLastError());
@@ -1168,6 +1306,7 @@ int sm_frequency_update(sm_context* ctx) {
 // ---- single-cell operations -----------------------------------------------------------------------
 static int cell_op(sm_context* ctx, const CellOp& o, CellRes* out) {
   if (ctx->nsoils < 1) return fail(ctx, SM_ERR_INVALID, "soil table not set");
+  if (ctx->nranks > 1) return fail(ctx, SM_ERR_INVALID, "single-cell operations are not available on a sharded context");
   CK(cudaSetDevice(ctx->cfg.device));
   k_cell_op<<<1, 1, 0, ctx->stream>>>(ctx->d, o, ctx->d_cellres);
   ctx->launches++;
@@ -1219,6 +1358,9 @@ int sm_height_bilinear(sm_context* ctx, float x, float y, double* height) {
 static int launch_run(sm_context* ctx, int kind, int n, const float* d_spawn, int max_sweeps) {
   if (ctx->nsoils < 1) return fail(ctx, SM_ERR_INVALID, "soil table not set");
   if (n < 0 || n > ctx->max_particles) return fail(ctx, SM_ERR_INVALID, "batch larger than max_particles");
+  const bool multi = ctx->nranks > 1;
+  if (multi && !ctx->peers_attached) return fail(ctx, SM_ERR_INVALID, "sharded context: call sm_peer_attach first");
+  if (multi && n >= (1 << 28)) return fail(ctx, SM_ERR_INVALID, "sharded context: at most 2^28 particles");
   CK(cudaSetDevice(ctx->cfg.device));
   const int threads = SM_BLOCK;
   // lanes per particle (a power of two): only the first lane of each group carries a particle, which
@@ -1233,10 +1375,16 @@ static int launch_run(sm_context* ctx, int kind, int n, const float* d_spawn, in
     for (;; ls--) {
       smem = (size_t)(threads >> ls) * SM_WIN_BYTES;
       int occ = 0;
-      if (kind == KIND_WATER) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run<KIND_WATER>, threads, smem));
-      else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run<KIND_WIND>, threads, smem));
+      if (kind == KIND_WATER) {
+        if (multi) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run<KIND_WATER, true>, threads, smem));
+        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run<KIND_WATER, false>, threads, smem));
+      } else {
+        if (multi) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run<KIND_WIND, true>, threads, smem));
+        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run<KIND_WIND, false>, threads, smem));
+      }
       if (occ < 1) return fail(ctx, SM_ERR_CUDA, "sweep kernel does not fit an SM");
-      const long long maxblocks = (long long)ctx->num_sms * occ;
+      // contexts that share the device must all be resident at once (they meet in the cross-rank barrier)
+      const long long maxblocks = std::max<long long>(1, (long long)ctx->num_sms * occ / ctx->share);
       const long long need_threads = (long long)std::max(n, 1) << ls;
       lshift = ls;
       blocks = (int)std::min<long long>(maxblocks, (need_threads + threads - 1) / threads);
@@ -1246,7 +1394,7 @@ static int launch_run(sm_context* ctx, int kind, int n, const float* d_spawn, in
   }
   // wind: barrier-free super-steps when every particle can own a thread slot
   bool use_async = false;
-  if (kind == KIND_WIND) {
+  if (kind == KIND_WIND && !multi) {
     // measured on config 3: 780 ms vs 650 ms for the per-sweep-barrier kernel - the clusters that
     // bound a sweep are persistent (neighbouring particles alternate every sweep), so removing the
     // barrier does not shorten the critical path.  Kept as an opt-in (SM_ASYNC=1).
@@ -1265,12 +1413,16 @@ static int launch_run(sm_context* ctx, int kind, int n, const float* d_spawn, in
   void* args[] = {&d, &n, (void*)&d_spawn, &max_sweeps, &lshift};
   CK(cudaMemsetAsync(ctx->d.ctl, 0, 4 * sizeof(unsigned int), ctx->stream));  // barrier + alive_slot[3]
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  if (kind == KIND_WATER)
-    CK(cudaLaunchCooperativeKernel((void*)k_run<KIND_WATER>, dim3(blocks), dim3(threads), args, smem, ctx->stream));
+  if (multi && kind == KIND_WATER)
+    CK(cudaLaunchCooperativeKernel((void*)k_run<KIND_WATER, true>, dim3(blocks), dim3(threads), args, smem, ctx->stream));
+  else if (multi)
+    CK(cudaLaunchCooperativeKernel((void*)k_run<KIND_WIND, true>, dim3(blocks), dim3(threads), args, smem, ctx->stream));
+  else if (kind == KIND_WATER)
+    CK(cudaLaunchCooperativeKernel((void*)k_run<KIND_WATER, false>, dim3(blocks), dim3(threads), args, smem, ctx->stream));
   else if (use_async)
     CK(cudaLaunchCooperativeKernel((void*)k_run_async<KIND_WIND, SM_ASYNC_DELTA>, dim3(blocks), dim3(threads), args, smem, ctx->stream));
   else
-    CK(cudaLaunchCooperativeKernel((void*)k_run<KIND_WIND>, dim3(blocks), dim3(threads), args, smem, ctx->stream));
+    CK(cudaLaunchCooperativeKernel((void*)k_run<KIND_WIND, false>, dim3(blocks), dim3(threads), args, smem, ctx->stream));
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->launches++;
   ctx->timing_pending = true;
@@ -1302,6 +1454,8 @@ int sm_last_stats(sm_context* ctx, sm_stats* st) {
 
 static int run_host(sm_context* ctx, int kind, int n, const float* spawn_xy, int max_sweeps, sm_stats* st) {
   if (n > 0 && !spawn_xy) return fail(ctx, SM_ERR_INVALID, "null spawn list");
+  if (ctx->nranks > 1 && ctx->share > 1)
+    return fail(ctx, SM_ERR_INVALID, "contexts sharing a device must use sm_*_run_device on every rank, then sm_last_stats");
   if (n < 0 || n > ctx->max_particles) return fail(ctx, SM_ERR_INVALID, "batch larger than max_particles");
   CK(cudaSetDevice(ctx->cfg.device));
   if (n) CK(cudaMemcpyAsync(ctx->d_spawn, spawn_xy, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -1408,6 +1562,7 @@ int sm_set_soil_colors(sm_context* ctx, const float* rgba, int32_t n) {
 }
 int sm_mesh_update(sm_context* ctx, int32_t slice, float* host_vertices) {
   if (!ctx->d_colors) return fail(ctx, SM_ERR_INVALID, "sm_mesh_update: soil colours not set");
+  if (ctx->nranks > 1) return fail(ctx, SM_ERR_INVALID, "sm_mesh_update is not available on a sharded context");
   CK(cudaSetDevice(ctx->cfg.device));
   if (!ctx->d_verts) CK(cudaMalloc(&ctx->d_verts, ctx->cells * 11 * sizeof(float)));
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -1511,11 +1666,11 @@ int sm_initialize(sm_context* ctx, int32_t seed, const sm_layer* layers, int32_t
     L.bounding = fnl_fractal_bounding(L.octaves, L.gain);
     ls.zslice[l] = layer_zslice(seed, l, nlayers);
   }
-  const unsigned long long need = (unsigned long long)ctx->cells * (unsigned long long)(nlayers - 1);
+  const unsigned long long need = (unsigned long long)ctx->lcells * (unsigned long long)(nlayers - 1);
   if (ctx->cfg.pool_capacity > 0) {
     if (need > ctx->d.pool_cap) return fail(ctx, SM_ERR_POOL, "sm_initialize: pool_capacity too small");
   } else {
-    int rc = alloc_pool(ctx, need + (unsigned long long)ctx->cells + (4ull << 20));
+    int rc = alloc_pool(ctx, ctx->nranks > 1 ? need : need + (unsigned long long)ctx->cells + (4ull << 20));
     if (rc != SM_OK) return rc;
   }
   int rc = reset_pool_ctl(ctx, 0);

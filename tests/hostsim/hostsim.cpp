@@ -30,6 +30,7 @@ struct HostAccess {
   void dirty(int, int) {}
   void cascade_prefetch(int, int) {}
   void mark(int) {}
+  void focus(int, int) {}
   Sec32 pool_load(uint32_t i) { return M.pool[i]; }
   void pool_store(uint32_t i, const Sec32& r) { M.pool[i] = r; }
   uint32_t pool_alloc() {
