@@ -153,36 +153,34 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
 // rank's arrival.  Returns the number of live particles over all ranks.
 __device__ __forceinline__ unsigned int grid_barrier_multi(const DevCtx& c, unsigned int& epoch, unsigned int gbase,
                                                            unsigned int local_alive_slot) {
+  // Only the rank leader (block 0, thread 0) uses system scope: the other blocks synchronise with it at
+  // gpu scope (release: fence + arrival; acquire: the `release` word), and causality composes across the
+  // two scopes, so their peer writes are ordered before the leader's system-scope flag.
   RunCtl* ctl = c.ctl;
   __syncthreads();
   epoch++;
   const unsigned int ge = gbase + epoch;           // global epoch of this barrier
   if (threadIdx.x == 0) {
-    __threadfence_system();
+    __threadfence();
     atomicAdd(&ctl->barrier, 1u);
     if (blockIdx.x == 0) {
       const unsigned int target = epoch * gridDim.x;
-      while ((int)(ld_volatile_u32(&ctl->barrier) - target) < 0) { }
-      __threadfence_system();
+      while ((int)(ld_acquire_u32(&ctl->barrier) - target) < 0) { }
       const unsigned int mine = ld_volatile_u32(&ctl->alive_slot[local_alive_slot]);
-      for (int q = 0; q < c.nranks; q++) {
-        RunCtl* pc = c.peer[q].ctl;
-        st_volatile_u32(&pc->xalive[ge & 1u][c.rank], mine);
-      }
+      for (int q = 0; q < c.nranks; q++) st_volatile_u32(&c.peer[q].ctl->xalive[ge & 1u][c.rank], mine);
       __threadfence_system();
-      for (int q = 0; q < c.nranks; q++) st_release_sys_u32(&c.peer[q].ctl->xflag[c.rank], ge);
+      for (int q = 0; q < c.nranks; q++) st_volatile_u32(&c.peer[q].ctl->xflag[c.rank], ge);
       unsigned int total = 0;
       for (int q = 0; q < c.nranks; q++) {
-        while ((int)(ld_acquire_sys_u32(&ctl->xflag[q]) - ge) < 0) { }
-        total += ld_volatile_u32(&ctl->xalive[ge & 1u][q]);
+        while ((int)(ld_volatile_u32(&ctl->xflag[q]) - ge) < 0) { }
       }
-      st_volatile_u32(&ctl->alive_total[ge & 1u], total);
       __threadfence_system();
-      st_release_sys_u32(&ctl->release, ge);
+      for (int q = 0; q < c.nranks; q++) total += ld_volatile_u32(&ctl->xalive[ge & 1u][q]);
+      st_volatile_u32(&ctl->alive_total[ge & 1u], total);
+      st_release_u32(&ctl->release, ge);
     } else {
-      while ((int)(ld_acquire_sys_u32(&ctl->release) - ge) < 0) { }
+      while ((int)(ld_acquire_u32(&ctl->release) - ge) < 0) { }
     }
-    __threadfence_system();
   }
   __syncthreads();
   return ld_volatile_u32(&ctl->alive_total[ge & 1u]);

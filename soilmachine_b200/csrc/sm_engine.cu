@@ -151,7 +151,11 @@ __device__ __forceinline__ unsigned int poll_blockers(const DevCtx& c, unsigned 
   for (int k = 0; k < 9; k++) {
     if ((mask >> k) & 1u) {
       if (MULTI) {
-        if (ld_acquire_sys_u32(&c.peer[list[k] >> 28].done[list[k] & 0x0FFFFFFFu]) >= tag) mask &= ~(1u << k);
+        // a blocker on another rank is polled over NVLink at system scope, a local one at gpu scope
+        const int bq = (int)(list[k] >> 28);
+        const unsigned int* dp = &c.peer[bq].done[list[k] & 0x0FFFFFFFu];
+        const unsigned int v = (bq == c.rank) ? ld_acquire_u32(dp) : ld_acquire_sys_u32(dp);
+        if (v >= tag) mask &= ~(1u << k);
       } else {
 #ifdef SM_ACQREL
         if (ld_acquire_u32(&c.done[list[k]]) >= tag) mask &= ~(1u << k);
@@ -337,7 +341,12 @@ __global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run(DevCtx c, int n,
           // hand-off first: the map writes are all the successors of this step wait for
           a.flush();
           if (MULTI) {
-            st_release_sys_u32(&c.done[pid], r == SM_ALIVE ? tag : 0xFFFFFFFFu);
+            // only particles within two bins of a strip edge can have touched a peer's records or be
+            // polled from another rank: they release at system scope, the interior ones at gpu scope
+            const int xlo = c.rank * c.strip_w, xhi = xlo + c.strip_w;
+            const bool edge = (ix < xlo + 32 && c.rank > 0) || (ix >= xhi - 32 && c.rank < c.nranks - 1);
+            if (edge) st_release_sys_u32(&c.done[pid], r == SM_ALIVE ? tag : 0xFFFFFFFFu);
+            else st_release_u32(&c.done[pid], r == SM_ALIVE ? tag : 0xFFFFFFFFu);
           } else {
 #ifdef SM_ACQREL
             st_release_u32(&c.done[pid], r == SM_ALIVE ? tag : 0xFFFFFFFFu);
