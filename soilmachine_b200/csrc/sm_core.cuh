@@ -156,7 +156,9 @@ template <class A> SM_HD double col_remove(A& a, Sec32& r, double h) {
 // ------------------------------------------------------------------------------------------------
 // queries through the accessor
 // ------------------------------------------------------------------------------------------------
-template <class A> SM_HD double map_height(A& a, int x, int y) { return rec_height(*a.rec(x, y)); }
+// read-only queries go through the accessor so that it can serve them from its staged copy without
+// forming a generic pointer (shared-memory loads instead of generic ones on the device)
+template <class A> SM_HD double map_height(A& a, int x, int y) { return a.height(x, y); }
 
 // Layermap::height(vec2), layermap.h:427-439 (weights cross-wired exactly as upstream)
 template <class A> SM_HD double map_height_bilinear(A& a, float px, float py) {
@@ -251,9 +253,8 @@ template <int DEPTH, class A> struct Cascade {
       h[k] = -1.0e300;                                                   // out of bounds sorts last
       nty[k] = 0u;
       if (in) {
-        const Sec32* r = a.rec(nx, ny);
-        h[k] = rec_height(*r);
-        nty[k] = rec_surface(*r);
+        h[k] = a.height(nx, ny);
+        nty[k] = a.surface_of(nx, ny);
         inb |= 1u << k;
         num++;
       }
@@ -265,9 +266,8 @@ template <int DEPTH, class A> struct Cascade {
     // transfer every neighbour is evaluated exactly as the reference does.
     unsigned int active = 0;
     {
-      const Sec32* cr = a.rec(cx, cy);
-      const double hc = rec_height(*cr);
-      const uint32_t cty = rec_surface(*cr);
+      const double hc = a.height(cx, cy);
+      const uint32_t cty = a.surface_of(cx, cy);
       const float cmax = a.soil(cty).maxdiff;
 #pragma unroll
       for (int k = 0; k < 8; k++) {

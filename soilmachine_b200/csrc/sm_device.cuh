@@ -167,6 +167,7 @@ __device__ __forceinline__ unsigned int grid_barrier_multi(const DevCtx& c, unsi
       const unsigned int target = epoch * gridDim.x;
       while ((int)(ld_acquire_u32(&ctl->barrier) - target) < 0) { }
       const unsigned int mine = ld_volatile_u32(&ctl->alive_slot[local_alive_slot]);
+#ifdef SM_XBAR_FENCES
       for (int q = 0; q < c.nranks; q++) st_volatile_u32(&c.peer[q].ctl->xalive[ge & 1u][c.rank], mine);
       __threadfence_system();
       for (int q = 0; q < c.nranks; q++) st_volatile_u32(&c.peer[q].ctl->xflag[c.rank], ge);
@@ -176,6 +177,17 @@ __device__ __forceinline__ unsigned int grid_barrier_multi(const DevCtx& c, unsi
       }
       __threadfence_system();
       for (int q = 0; q < c.nranks; q++) total += ld_volatile_u32(&ctl->xalive[ge & 1u][q]);
+#else
+      // one system-scope release store per peer (orders the live count and every peer write of this rank
+      // before the flag), one acquire poll per peer; no separate system fences
+      for (int q = 0; q < c.nranks; q++) st_volatile_u32(&c.peer[q].ctl->xalive[ge & 1u][c.rank], mine);
+      for (int q = 0; q < c.nranks; q++) st_release_sys_u32(&c.peer[q].ctl->xflag[c.rank], ge);
+      unsigned int total = 0;
+      for (int q = 0; q < c.nranks; q++) {
+        while ((int)(ld_acquire_sys_u32(&ctl->xflag[q]) - ge) < 0) { }
+        total += ld_volatile_u32(&ctl->xalive[ge & 1u][q]);
+      }
+#endif
       st_volatile_u32(&ctl->alive_total[ge & 1u], total);
       st_release_u32(&ctl->release, ge);
     } else {
@@ -198,6 +210,8 @@ struct DevAccess {
   __device__ __forceinline__ int scale() const { return c.scale; }
   __device__ __forceinline__ SoilDev soil(uint32_t t) const { return s_soils[t]; }
   __device__ __forceinline__ Sec32* rec(int x, int y) { return &c.top[(size_t)x * c.dimy + y]; }
+  __device__ __forceinline__ double height(int x, int y) { return rec_height(*rec(x, y)); }
+  __device__ __forceinline__ uint32_t surface_of(int x, int y) { return rec_surface(*rec(x, y)); }
   __device__ __forceinline__ void begin(int, int) {}
   __device__ __forceinline__ void target(int, int) {}
   __device__ __forceinline__ void dirty(int, int) {}
@@ -350,6 +364,25 @@ struct WinAccess {
   __device__ __forceinline__ void dirty(int x, int y) {
     const int s = slot_of(x, y);
     if (s >= 0) dirtym |= 1u << s;
+  }
+  // read-only queries served from the window with shared-memory loads (no generic pointer is formed)
+  __device__ __forceinline__ double height(int x, int y) {
+    const int s = slot_of(x, y);
+    if (s >= 0) {
+      if (!((valid >> s) & 1u)) { win[s] = *cell_ptr<MULTI>(c, x, y); valid |= 1u << s; }
+      const double sz = win[s].size, fl = win[s].floor;
+      return win[s].type == SM_EMPTY ? 0.0 : (fl + sz);
+    }
+    return rec_height(*cell_ptr<MULTI>(c, x, y));
+  }
+  __device__ __forceinline__ uint32_t surface_of(int x, int y) {
+    const int s = slot_of(x, y);
+    if (s >= 0) {
+      if (!((valid >> s) & 1u)) { win[s] = *cell_ptr<MULTI>(c, x, y); valid |= 1u << s; }
+      const uint32_t t = win[s].type;
+      return t == SM_EMPTY ? 0u : t;
+    }
+    return rec_surface(*cell_ptr<MULTI>(c, x, y));
   }
   // write the modified records back (end of step)
   __device__ __forceinline__ void flush() {

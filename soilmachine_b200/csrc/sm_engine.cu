@@ -780,6 +780,7 @@ struct MeshAccess {   // adapts MeshMap to the accessor interface map_normal() e
   __device__ __forceinline__ int dimy() const { return c.dimy; }
   __device__ __forceinline__ int scale() const { return c.scale; }
   __device__ __forceinline__ const Sec32* rec(int x, int y) { tmp = ldg_rec(&c.top[(size_t)x * c.dimy + y]); return &tmp; }
+  __device__ __forceinline__ double height(int x, int y) { return rec_height(*rec(x, y)); }
 };
 #define MESH_BLOCK 256
 __global__ void __launch_bounds__(MESH_BLOCK) k_mesh(DevCtx c, int slice, const float4* __restrict__ colors,

@@ -25,6 +25,8 @@ struct HostAccess {
   int scale() const { return M.scale; }
   const SoilDev& soil(uint32_t t) const { return M.soils[t]; }
   Sec32* rec(int x, int y) { return &M.top[(size_t)x * M.dimy + y]; }
+  double height(int x, int y) { return rec_height(*rec(x, y)); }
+  uint32_t surface_of(int x, int y) { return rec_surface(*rec(x, y)); }
   void begin(int, int) {}
   void target(int, int) {}
   void dirty(int, int) {}
