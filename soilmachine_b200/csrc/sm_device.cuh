@@ -366,7 +366,9 @@ struct WinAccess {
     if (s >= 0) dirtym |= 1u << s;
   }
   // read-only queries served from the window with shared-memory loads (no generic pointer is formed)
+  // (measured: -5 % on the water kernel, +11 % on the wind kernel, so wind keeps the pointer path)
   __device__ __forceinline__ double height(int x, int y) {
+    if (KIND_ == 1) return rec_height(*rec(x, y));
     const int s = slot_of(x, y);
     if (s >= 0) {
       if (!((valid >> s) & 1u)) { win[s] = *cell_ptr<MULTI>(c, x, y); valid |= 1u << s; }
@@ -376,6 +378,7 @@ struct WinAccess {
     return rec_height(*cell_ptr<MULTI>(c, x, y));
   }
   __device__ __forceinline__ uint32_t surface_of(int x, int y) {
+    if (KIND_ == 1) return rec_surface(*rec(x, y));
     const int s = slot_of(x, y);
     if (s >= 0) {
       if (!((valid >> s) & 1u)) { win[s] = *cell_ptr<MULTI>(c, x, y); valid |= 1u << s; }
