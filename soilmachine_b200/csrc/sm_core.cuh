@@ -253,8 +253,7 @@ template <int DEPTH, class A> struct Cascade {
       h[k] = -1.0e300;                                                   // out of bounds sorts last
       nty[k] = 0u;
       if (in) {
-        h[k] = a.height(nx, ny);
-        nty[k] = a.surface_of(nx, ny);
+        a.query(nx, ny, h[k], nty[k]);
         inb |= 1u << k;
         num++;
       }
@@ -266,8 +265,9 @@ template <int DEPTH, class A> struct Cascade {
     // transfer every neighbour is evaluated exactly as the reference does.
     unsigned int active = 0;
     {
-      const double hc = a.height(cx, cy);
-      const uint32_t cty = a.surface_of(cx, cy);
+      double hc;
+      uint32_t cty;
+      a.query(cx, cy, hc, cty);
       const float cmax = a.soil(cty).maxdiff;
 #pragma unroll
       for (int k = 0; k < 8; k++) {

@@ -212,6 +212,7 @@ struct DevAccess {
   __device__ __forceinline__ Sec32* rec(int x, int y) { return &c.top[(size_t)x * c.dimy + y]; }
   __device__ __forceinline__ double height(int x, int y) { return rec_height(*rec(x, y)); }
   __device__ __forceinline__ uint32_t surface_of(int x, int y) { return rec_surface(*rec(x, y)); }
+  __device__ __forceinline__ void query(int x, int y, double& h, uint32_t& t) { const Sec32* r = rec(x, y); h = rec_height(*r); t = rec_surface(*r); }
   __device__ __forceinline__ void begin(int, int) {}
   __device__ __forceinline__ void target(int, int) {}
   __device__ __forceinline__ void dirty(int, int) {}
@@ -376,6 +377,21 @@ struct WinAccess {
       return win[s].type == SM_EMPTY ? 0.0 : (fl + sz);
     }
     return rec_height(*cell_ptr<MULTI>(c, x, y));
+  }
+  // height and surface type of one cell with a single slot lookup
+  __device__ __forceinline__ void query(int x, int y, double& h, uint32_t& t) {
+    if (KIND_ == 1) { const Sec32* r = rec(x, y); h = rec_height(*r); t = rec_surface(*r); return; }
+    const int s = slot_of(x, y);
+    if (s >= 0) {
+      if (!((valid >> s) & 1u)) { win[s] = *cell_ptr<MULTI>(c, x, y); valid |= 1u << s; }
+      const double sz = win[s].size, fl = win[s].floor;
+      const uint32_t ty = win[s].type;
+      h = (ty == SM_EMPTY) ? 0.0 : (fl + sz);
+      t = (ty == SM_EMPTY) ? 0u : ty;
+      return;
+    }
+    const Sec32 r = *cell_ptr<MULTI>(c, x, y);
+    h = rec_height(r); t = rec_surface(r);
   }
   __device__ __forceinline__ uint32_t surface_of(int x, int y) {
     if (KIND_ == 1) return rec_surface(*rec(x, y));

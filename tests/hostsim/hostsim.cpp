@@ -27,6 +27,7 @@ struct HostAccess {
   Sec32* rec(int x, int y) { return &M.top[(size_t)x * M.dimy + y]; }
   double height(int x, int y) { return rec_height(*rec(x, y)); }
   uint32_t surface_of(int x, int y) { return rec_surface(*rec(x, y)); }
+  void query(int x, int y, double& h, uint32_t& t) { const Sec32* r = rec(x, y); h = rec_height(*r); t = rec_surface(*r); }
   void begin(int, int) {}
   void target(int, int) {}
   void dirty(int, int) {}
