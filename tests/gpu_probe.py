@@ -26,7 +26,7 @@ def run(soil, dim, nw, nd, lanes=None, iters=1, label=""):
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
-    if which in ("profile", "one", "mesh") or which.startswith("cfg3:"): which = "none"
+    if which in ("profile", "one", "mesh", "big") or which.startswith("cfg3:"): which = "none"
     if which in ("all", "single"):
         # single particles: sweep time = step latency (+ trivial barrier)
         run("rocksand", 1024, 1, 0, label="single")
@@ -104,3 +104,26 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "mesh":
         print("k_mesh 4096^2: %.3f ms, %.1f GB/s algorithmic (32 B in + 44 B out per cell)" % (st.device_ms, cells * 76 / st.device_ms / 1e6), flush=True)
     sim.ctx.timer_start(); sim.ctx.frequency_update(); ms = sim.ctx.timer_stop()
     print("k_frequency_update 4096^2: %.3f ms, %.1f GB/s (16 B/cell)" % (ms, cells * 16 / ms / 1e6))
+
+
+def bigcfg(soil, dim, nw, nd, frames=2):
+    from soilmachine_b200 import host
+    t0 = time.time()
+    sim = host.Simulation(soil, seed=42, dimx=dim, dimy=dim, max_particles=max(nw, nd, 1))
+    print("%s %d^2: terrain init + context %.2f s, %d sections" % (soil, dim, time.time() - t0, sim.ctx.section_count() if dim <= 4096 else -1), flush=True)
+    for f in range(frames):
+        xw = host.spawn_list(nw, dim, dim)
+        g = sim.ctx.water_run(xw)
+        print("  frame %d water n=%d: steps=%d sweeps=%d ms=%.1f -> %.3e steps/s drops=%d" % (f, nw, g.steps, g.sweeps, g.device_ms, g.steps / g.device_ms * 1e3, g.pool_drops), flush=True)
+        if nd:
+            xd = host.spawn_list(nd, dim, dim)
+            g = sim.ctx.wind_run(xd)
+            print("  frame %d wind  n=%d: steps=%d sweeps=%d ms=%.1f exits=%d" % (f, nd, g.steps, g.sweeps, g.device_ms, g.exit_oob), flush=True)
+        sim.ctx.frequency_update()
+    print("  height sum %.9f" % sim.ctx.height_sum(), flush=True)
+    sim.close()
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "big":
+    bigcfg("bigbutte", 4096, 50000, 0)                       # BASELINE config 4 shape (single GPU)
+    bigcfg("rockgravelpebbles_big", 8192, 100000, 100000)    # BASELINE config 5 shape: 200k mixed, wind inert
