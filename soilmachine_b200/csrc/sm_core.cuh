@@ -351,10 +351,17 @@ template <class A> SM_HD uint32_t spawn_contains(A& a, float px, float py) {
 }
 
 // one move() && interact().  `a` must cover plus(ipos) and the 3x3 around the new position.
-template <class A> SM_HD int water_step(A& a, WaterP& p) {
+// What move() hands to interact() of the same step (the friction-modified `param` copy of water.h:48-54
+// is only read for solubility and equrate afterwards).
+struct WaterMid {
+  float freq, solubility, equrate;
+  double evaprate;
+  int ix, iy;
+};
+
+// WaterParticle::move, water.h:43-73.  `a` must cover plus(ipos).  Returns SM_ALIVE when interact() follows.
+template <class A> SM_HD int water_move(A& a, WaterP& p, WaterMid& m) {
   const int dimx = a.dimx(), dimy = a.dimy();
-  const int SCALE = a.scale();
-  // ---- move, water.h:43-73 ----
   const int ix = (int)roundf(p.px), iy = (int)roundf(p.py);        // :45
   a.begin(ix, iy);
   sm_f3 n = map_normal(a, ix, iy);                                  // :46
@@ -367,6 +374,8 @@ template <class A> SM_HD int water_step(A& a, WaterP& p) {
   const float freq = a.water_frequency(ind);
   param.friction = param.friction * (1.0f - freq);                  // :53
   evaprate = evaprate * (1.0f - 0.2f * freq);                       // :54
+  m.freq = freq; m.solubility = param.solubility; m.equrate = param.equrate; m.evaprate = evaprate;
+  m.ix = ix; m.iy = iy;
   {
     float vx = n.x * param.friction, vz = n.z * param.friction;     // :56
     float len = sqrtf(vx * vx + vz * vz);
@@ -387,10 +396,20 @@ template <class A> SM_HD int water_step(A& a, WaterP& p) {
     p.volume = 0.0;
     return SM_EXIT_OOB;
   }
-  // ---- interact, water.h:75-121 ----
+  return SM_ALIVE;
+}
+
+// WaterParticle::interact, water.h:75-121.  `a` must still hold the record of ipos; the 3x3 block around
+// the new position is staged here.
+template <class A> SM_HD int water_interact(A& a, WaterP& p, const WaterMid& m) {
+  const int SCALE = a.scale();
+  const int ix = m.ix, iy = m.iy;
+  const float freq = m.freq;
+  const double evaprate = m.evaprate;
+  Sec32* ir = a.rec(ix, iy);
   const int nx = (int)roundf(p.px), ny = (int)roundf(p.py);
   a.target(nx, ny);
-  double c_eq = param.solubility * (rec_height(*ir) - map_height_bilinear(a, p.px, p.py)) *
+  double c_eq = m.solubility * (rec_height(*ir) - map_height_bilinear(a, p.px, p.py)) *
                 (double)SCALE / 80.0;                               // :78
   if (c_eq < 0.0) c_eq = 0.0;
   if (c_eq > 1.0) c_eq = 1.0;
@@ -399,10 +418,10 @@ template <class A> SM_HD int water_step(A& a, WaterP& p) {
     p.contains = a.soil(p.contains).erodes;
   double cdiff = c_eq - p.sediment;                                 // :87
   if (cdiff > 0) {                                                  // :91-101
-    p.sediment += param.equrate * cdiff;
+    p.sediment += m.equrate * cdiff;
     p.contains = a.soil(rec_surface(*ir)).transports;
     a.focus(ix, iy);
-    double diff = col_remove(a, *ir, param.equrate * cdiff * p.volume);
+    double diff = col_remove(a, *ir, m.equrate * cdiff * p.volume);
     SM_UNROLL1
     while (fabs(diff) > 1E-8) diff = col_remove(a, *ir, diff);
     a.dirty(ix, iy);
@@ -420,6 +439,14 @@ template <class A> SM_HD int water_step(A& a, WaterP& p) {
   if (p.sediment > 1.0) p.sediment = 1.0;
   p.volume *= (1.0 - evaprate);
   return (p.volume > 0.01) ? SM_ALIVE : SM_EXIT_EVAP;
+}
+
+// one move() && interact().  `a` must cover plus(ipos) and the 3x3 around the new position.
+template <class A> SM_HD int water_step(A& a, WaterP& p) {
+  WaterMid m;
+  const int r = water_move(a, p, m);
+  if (r != SM_ALIVE) return r;
+  return water_interact(a, p, m);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -420,6 +420,284 @@ __global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run(DevCtx c, int n,
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_run_exact: water batches with EXACT footprints (single rank).
+//
+// k_run orders two steps whenever their conservative boxes (ipos +- 3) overlap.  The cells a water step
+// really touches are F = plus(ipos) U 3x3(npos) - about 14 of the 49 - but npos is only known after
+// move().  Here the step is split: a particle publishes mv = npos right after move(), its map writes
+// with fin, and a lower-index particle B only holds A back
+//   before A.move()     if B's writes W_B = {ipos_B} U 3x3(npos_B) can meet plus(ipos_A)
+//                       (while B has not moved yet: if B's box can meet plus(ipos_A)),
+//   before A.interact() if F_B can meet F_A (while B has not moved yet: if B's box can meet F_A).
+// The oracle emulation of this rule halves the longest chain per sweep (32.7 -> 16.1 at config-3
+// density).  Particles with more than KX in-range lower-index neighbours fall back to the per-bin
+// predecessor rule of k_run; to keep that rule sound every particle publishes `done` only after its
+// own-bin predecessor's `done` (so "X done => every lower index in X's bin done" still holds), while
+// exact waiters look at `fin`.
+#define SM_KX 32
+__device__ __forceinline__ bool plus_hits_3x3(int dx, int dy) {   // plus(c) meets 3x3(c + d)
+  dx = dx < 0 ? -dx : dx; dy = dy < 0 ? -dy : dy;
+  return (dx <= 1 && dy <= 2) || (dx <= 2 && dy <= 1);
+}
+__device__ __forceinline__ bool plus_hits_box3(int dx, int dy) {  // plus(c) meets the box (c + d) +- 3
+  dx = dx < 0 ? -dx : dx; dy = dy < 0 ? -dy : dy;
+  return (dx <= 4 && dy <= 3) || (dx <= 3 && dy <= 4);
+}
+__device__ __forceinline__ int iabs_(int v) { return v < 0 ? -v : v; }
+
+__global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run_exact(DevCtx c, int n, const float* __restrict__ spawn,
+                                                                      int max_sweeps, int lshift) {
+  const int KIND = KIND_WATER;
+  typedef WaterP P;
+  __shared__ SoilDev s_soils[SM_MAX_SOILS];
+  __shared__ unsigned int s_alive;
+  extern __shared__ __align__(32) unsigned char s_win[];   // per slot: window, then KX ids, then KX packed ipos
+  for (int i = threadIdx.x; i < c.nsoils; i += blockDim.x) s_soils[i] = c.soils[i];
+  if (threadIdx.x == 0) s_alive = 0;
+  __syncthreads();
+  const size_t slot_bytes = SM_WIN_BYTES + 2 * SM_KX * sizeof(uint32_t);
+  unsigned char* my_smem = s_win + (size_t)(threadIdx.x >> lshift) * slot_bytes;
+  Sec32* my_win = (Sec32*)my_smem;
+  uint32_t* blk = (uint32_t*)(my_smem + SM_WIN_BYTES);
+  uint32_t* bxy = blk + SM_KX;
+
+  RunCtl* ctl = c.ctl;
+  unsigned int epoch = 0;
+  const unsigned int tag0 = ctl->tag_base;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool leader = (gtid & ((1 << lshift) - 1)) == 0;
+  const int slot = gtid >> lshift;
+  const int nslots = (gridDim.x * blockDim.x) >> lshift;
+  const int trips = (n + nslots - 1) / nslots;
+  const int G = Reach<KIND>::G;
+  const int nbx = (c.dimx + G - 1) / G, nby = (c.dimy + G - 1) / G;
+
+  unsigned long long n_steps = 0, n_oob = 0, n_evap = 0, n_stall = 0;
+
+  // ---- prologue ----
+  {
+    unsigned int my_alive = 0;
+    if (leader) {
+      for (int pid = slot; pid < n; pid += nslots) {
+        bool alive;
+        if (spawn != nullptr) {
+          const float x = spawn[2 * pid], y = spawn[2 * pid + 1];
+          const uint32_t contains = s_soils[rec_surface(c.top[(size_t)(int)roundf(x) * c.dimy + (int)roundf(y)])].transports;
+          WaterP w{x, y, 0.0f, 0.0f, 1.0, 0.0, contains};
+          store_particle(c, pid, w);
+          alive = true;
+          c.alive[pid] = 1;
+          c.done[pid] = tag0 - 1u;
+          c.fin[pid] = tag0 - 1u;
+        } else {
+          alive = c.alive[pid] != 0;
+        }
+        if (alive) {
+          P q;
+          load_particle(c, pid, q);
+          bin_insert<KIND, false>(c, tag0, pid, (int)roundf(q.px), (int)roundf(q.py), 3);
+          my_alive++;
+        }
+      }
+    }
+    if (my_alive) atomicAdd(&s_alive, my_alive);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (s_alive) atomicAdd(&ctl->alive_slot[0], s_alive);
+      s_alive = 0;
+    }
+    grid_barrier(&ctl->barrier, epoch);
+  }
+
+  int s = 0;
+  unsigned int total_alive = 0;
+  for (;; s++) {
+    const unsigned int tag = tag0 + (unsigned int)s;
+    const unsigned int par = tag & 1u;
+    total_alive = ld_volatile_u32(&ctl->alive_slot[s % 3]);
+    if (total_alive == 0 || (max_sweeps >= 0 && s >= max_sweeps)) break;
+    if (gtid == 0) st_volatile_u32(&ctl->alive_slot[(s + 2) % 3], 0u);
+
+    unsigned int my_alive = 0;
+    for (int trip = 0; trip < trips; trip++) {
+      const int pid = slot + trip * nslots;
+      const bool has = leader && pid < n && c.alive[pid] != 0;
+      P p;
+      WaterMid mid;
+      WinAccess<KIND_WATER, false> a(c, s_soils, tag, my_win);
+      int ix = 0, iy = 0, nx = 0, ny = 0, nl = 0;
+      uint32_t ownpred = SM_NIL;          // largest lower index in my own bin
+      uint32_t pred[9];                   // crowded fallback: per-bin predecessors
+      unsigned int un0 = 0, un1 = 0;      // exact mode: unresolved list entries for move / interact
+      unsigned int pm = 0;                // crowded mode: per-bin predecessors not yet `done`
+      bool crowded = false;
+      int stage = 3;                      // 0 wait-to-move, 1 wait-to-interact, 2 wait-to-publish-done, 3 complete
+      int result = SM_ALIVE;
+      if (has) {
+        load_particle(c, pid, p);
+        ix = (int)roundf(p.px); iy = (int)roundf(p.py);
+        stage = 0;
+        // ---- scan: in-range lower indices (exact list) and per-bin predecessors (fallback) ----
+        const int bx = ix / G, by = iy / G;
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+          pred[k] = SM_NIL;
+          const int cx = bx + k / 3 - 1, cy = by + k % 3 - 1;
+          if (cx < 0 || cx >= nbx || cy < 0 || cy >= nby) continue;
+          const unsigned long long h = *((volatile unsigned long long*)&c.head[par][cx * nby + cy]);
+          if ((unsigned int)(h >> 32) != tag) continue;
+          uint32_t j = (uint32_t)h, best = SM_NIL;
+          while (j != SM_NIL) {
+            const uint2 nd = c.node[par][j];
+            if (j < (uint32_t)pid) {
+              if (best == SM_NIL || j > best) best = j;
+              const int jx = (int)(nd.y >> 18), jy = (int)((nd.y >> 4) & 0x3FFFu);
+              if (iabs_(jx - ix) <= 6 && iabs_(jy - iy) <= 6) {
+                if (nl < SM_KX) { blk[nl] = j; bxy[nl] = ((uint32_t)jx << 16) | (uint32_t)jy; nl++; }
+                else crowded = true;
+              }
+            }
+            j = nd.x;
+          }
+          pred[k] = best;
+        }
+        ownpred = pred[4];
+        if (crowded) {
+#pragma unroll
+          for (int k = 0; k < 9; k++) if (pred[k] != SM_NIL) pm |= 1u << k;
+        } else {
+          // static pruning: a neighbour whose box cannot meet plus(ipos) never delays the move
+          for (int q = 0; q < nl; q++) {
+            un1 |= 1u << q;
+            const int jx = (int)(bxy[q] >> 16), jy = (int)(bxy[q] & 0xFFFFu);
+            if (plus_hits_box3(jx - ix, jy - iy)) un0 |= 1u << q;
+          }
+        }
+      }
+
+      for (;;) {
+        // ---- readiness of this lane's next stage ----
+        bool ready = false;
+        if (stage == 0) {
+          if (crowded) {
+#pragma unroll
+            for (int k = 0; k < 9; k++)
+              if (((pm >> k) & 1u) && ld_acquire_u32(&c.done[pred[k]]) >= tag) pm &= ~(1u << k);
+            ready = (pm == 0);
+          } else {
+            unsigned int m = un0;
+            while (m) {
+              const int q = __ffs(m) - 1; m &= m - 1;
+              const uint32_t j = blk[q];
+              if (ld_acquire_u32(&c.fin[j]) >= tag) { un0 &= ~(1u << q); un1 &= ~(1u << q); continue; }
+              const unsigned long long v = *((volatile unsigned long long*)&c.mv[j]);
+              if ((unsigned int)(v >> 32) == tag) {
+                const int jx = (int)(bxy[q] >> 16), jy = (int)(bxy[q] & 0xFFFFu);
+                const int mx = (int)((v >> 16) & 0xFFFFu), my = (int)(v & 0xFFFFu);
+                // W_B = {ipos_B} U 3x3(npos_B) against plus(ipos_A)
+                const bool hit = (iabs_(jx - ix) + iabs_(jy - iy) <= 1) || plus_hits_3x3(mx - ix, my - iy);
+                if (!hit) un0 &= ~(1u << q);
+              }
+            }
+            ready = (un0 == 0);
+          }
+        } else if (stage == 1) {
+          if (crowded) ready = true;
+          else {
+            unsigned int m = un1;
+            while (m) {
+              const int q = __ffs(m) - 1; m &= m - 1;
+              const uint32_t j = blk[q];
+              if (ld_acquire_u32(&c.fin[j]) >= tag) { un1 &= ~(1u << q); continue; }
+              const int jx = (int)(bxy[q] >> 16), jy = (int)(bxy[q] & 0xFFFFu);
+              const unsigned long long v = *((volatile unsigned long long*)&c.mv[j]);
+              if ((unsigned int)(v >> 32) == tag) {
+                const int mx = (int)((v >> 16) & 0xFFFFu), my = (int)(v & 0xFFFFu);
+                const bool hit = (iabs_(jx - ix) + iabs_(jy - iy) <= 2)        // plus(A) x plus(B)
+                                 || plus_hits_3x3(mx - ix, my - iy)            // plus(A) x 3x3(npos_B)
+                                 || plus_hits_3x3(nx - jx, ny - jy)            // 3x3(npos_A) x plus(B)
+                                 || (iabs_(mx - nx) <= 2 && iabs_(my - ny) <= 2);   // 3x3 x 3x3
+                if (!hit) un1 &= ~(1u << q);
+              } else {
+                // B has not moved yet: its footprint lies in ipos_B +- 3
+                const bool hit = plus_hits_box3(jx - ix, jy - iy) || (iabs_(jx - nx) <= 4 && iabs_(jy - ny) <= 4);
+                if (!hit) un1 &= ~(1u << q);
+              }
+            }
+            ready = (un1 == 0);
+          }
+        } else if (stage == 2) {
+          ready = (ownpred == SM_NIL) || (ld_acquire_u32(&c.done[ownpred]) >= tag);
+        }
+        if (__ballot_sync(0xffffffffu, stage != 3) == 0u) break;
+        if (__ballot_sync(0xffffffffu, ready) == 0u) { __nanosleep(32); continue; }
+
+        // ---- move ----
+        if (stage == 0 && ready) {
+          result = water_move(a, p, mid);
+          if (result == SM_ALIVE) {
+            nx = (int)roundf(p.px); ny = (int)roundf(p.py);
+            *((volatile unsigned long long*)&c.mv[pid]) = ((unsigned long long)tag << 32) | ((unsigned long long)nx << 16) | (unsigned long long)ny;
+            if (iabs_(nx - ix) > 2 || iabs_(ny - iy) > 2) atomicOr(&ctl->err, 1u << 4);   // SM_ERR_REACH
+            stage = 1;
+          } else {
+            // stalled or left the map: only track[] was written
+            st_release_u32(&c.fin[pid], 0xFFFFFFFFu);
+            store_particle(c, pid, p);
+            c.alive[pid] = 0;
+            if (result == SM_EXIT_OOB) n_oob++; else n_stall++;
+            stage = 2;
+          }
+          ready = false;
+        }
+        __syncwarp();
+        // ---- interact ----
+        if (stage == 1 && ready) {
+          result = water_interact(a, p, mid);
+          a.flush();
+          st_release_u32(&c.fin[pid], result == SM_ALIVE ? tag : 0xFFFFFFFFu);
+          store_particle(c, pid, p);
+          n_steps++;
+          if (result == SM_ALIVE) {
+            bin_insert<KIND, false>(c, tag + 1u, pid, nx, ny, 3);
+            my_alive++;
+          } else {
+            c.alive[pid] = 0;
+            n_evap++;
+          }
+          stage = 2;
+          ready = false;
+        }
+        __syncwarp();
+        // ---- publish `done` in own-bin index order ----
+        if (stage == 2 && ready) {
+          st_release_u32(&c.done[pid], result == SM_ALIVE ? tag : 0xFFFFFFFFu);
+          stage = 3;
+        }
+        __syncwarp();
+      }
+    }
+    if (my_alive) atomicAdd(&s_alive, my_alive);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (s_alive) atomicAdd(&ctl->alive_slot[(s + 1) % 3], s_alive);
+      s_alive = 0;
+    }
+    grid_barrier(&ctl->barrier, epoch);
+  }
+
+  if (n_steps) atomicAdd(&ctl->steps, n_steps);
+  if (n_oob) atomicAdd(&ctl->exit_oob, n_oob);
+  if (n_evap) atomicAdd(&ctl->exit_evap, n_evap);
+  if (n_stall) atomicAdd(&ctl->exit_stall, n_stall);
+  if (gtid == 0) {
+    atomicMax(&ctl->sweeps, (unsigned long long)s);
+    ctl->alive = total_alive;
+    ctl->tag_base = tag0 + (unsigned int)s + 2u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // k_run_async: the sweep kernel without a grid barrier per sweep (used for wind batches).
 //
 // A wind batch is sparse (half the particles die at spawn, the rest drift for up to ~13 000 sweeps) and
@@ -931,7 +1209,7 @@ void sm_destroy(sm_context* ctx) {
   DevCtx& d = ctx->d;
   cudaFree(d.top); cudaFree(d.pool); cudaFree(d.ringbuf[0]); cudaFree(d.ringbuf[1]);
   cudaFree(d.wfreq); cudaFree(d.wtrack); cudaFree(d.windfreq); cudaFree(ctx->d_soils);
-  cudaFree(d.ctl); cudaFree(d.pa); cudaFree(d.pb); cudaFree(d.pc); cudaFree(d.alive); cudaFree(d.done); cudaFree(d.pstate);
+  cudaFree(d.ctl); cudaFree(d.pa); cudaFree(d.pb); cudaFree(d.pc); cudaFree(d.alive); cudaFree(d.done); cudaFree(d.pstate); cudaFree(d.fin); cudaFree(d.mv);
   for (int i = 0; i < 2; i++) { cudaFree(d.head[i]); cudaFree(d.node[i]); }
   cudaFree(ctx->d_verts); cudaFree(ctx->d_colors);
   cudaFree(ctx->d_spawn); cudaFree(ctx->d_scratch); cudaFree(ctx->d_iscratch); cudaFree(ctx->d_cellres);
@@ -1008,6 +1286,8 @@ static int create_impl(const sm_config* cfg, int nranks, int rank, int share, sm
     CK(cudaMemsetAsync(d.ctl, 0, sizeof(RunCtl), ctx->stream));
     CK(cudaMalloc(&d.pa, N * sizeof(float4))); CK(cudaMalloc(&d.pb, N * sizeof(double2)));
     CK(cudaMalloc(&d.pc, N * sizeof(uint2))); CK(cudaMalloc(&d.alive, N)); CK(cudaMalloc(&d.done, N * 4)); CK(cudaMalloc(&d.pstate, N * 8));
+    CK(cudaMalloc(&d.fin, N * 4)); CK(cudaMalloc(&d.mv, N * 8));
+    CK(cudaMemsetAsync(d.fin, 0, N * 4, ctx->stream)); CK(cudaMemsetAsync(d.mv, 0, N * 8, ctx->stream));
     d.nbx = (cfg->dimx + SM_MIN_BIN - 1) / SM_MIN_BIN; d.nby = (cfg->dimy + SM_MIN_BIN - 1) / SM_MIN_BIN;
     for (int i = 0; i < 2; i++) {
       CK(cudaMalloc(&d.head[i], (size_t)d.nbx * d.nby * 8));
@@ -1036,6 +1316,7 @@ static int create_impl(const sm_config* cfg, int nranks, int rank, int share, sm
     CK(cudaFuncSetAttribute(k_run<KIND_WATER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BLOCK * SM_WIN_BYTES));
     CK(cudaFuncSetAttribute(k_run<KIND_WIND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BLOCK * SM_WIN_BYTES));
     CK(cudaFuncSetAttribute(k_run<KIND_WATER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BLOCK * SM_WIN_BYTES));
+    CK(cudaFuncSetAttribute(k_run_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BLOCK * (SM_WIN_BYTES + 2 * SM_KX * 4)));
     CK(cudaFuncSetAttribute(k_run<KIND_WIND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BLOCK * SM_WIN_BYTES));
     CK(cudaFuncSetAttribute(k_run_async<KIND_WIND, SM_ASYNC_DELTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BLOCK * SM_WIN_BYTES));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1402,6 +1683,26 @@ static int launch_run(sm_context* ctx, int kind, int n, const float* d_spawn, in
     }
     if (blocks < 1) blocks = 1;
   }
+  // water, single rank: exact-footprint kernel (opt-in SM_EXACT=1 until it is the measured default)
+  bool use_exact = false;
+  if (kind == KIND_WATER && !multi) {
+    const char* e = getenv("SM_EXACT");
+    if (e && atoi(e) == 1) {
+      for (int ls = lshift;; ls--) {
+        const size_t sm2 = (size_t)(threads >> ls) * (SM_WIN_BYTES + 2 * SM_KX * 4);
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run_exact, threads, sm2));
+        const long long need_threads = (long long)std::max(n, 1) << ls;
+        const long long maxblocks = (long long)ctx->num_sms * occ;
+        if (occ >= 1 && (need_threads <= maxblocks * threads || ls == 0)) {
+          use_exact = true; lshift = ls; smem = sm2;
+          blocks = (int)std::max<long long>(1, std::min<long long>(maxblocks, (need_threads + threads - 1) / threads));
+          break;
+        }
+        if (ls == 0) break;
+      }
+    }
+  }
   // wind: barrier-free super-steps when every particle can own a thread slot
   bool use_async = false;
   if (kind == KIND_WIND && !multi) {
@@ -1427,6 +1728,8 @@ static int launch_run(sm_context* ctx, int kind, int n, const float* d_spawn, in
     CK(cudaLaunchCooperativeKernel((void*)k_run<KIND_WATER, true>, dim3(blocks), dim3(threads), args, smem, ctx->stream));
   else if (multi)
     CK(cudaLaunchCooperativeKernel((void*)k_run<KIND_WIND, true>, dim3(blocks), dim3(threads), args, smem, ctx->stream));
+  else if (use_exact)
+    CK(cudaLaunchCooperativeKernel((void*)k_run_exact, dim3(blocks), dim3(threads), args, smem, ctx->stream));
   else if (kind == KIND_WATER)
     CK(cudaLaunchCooperativeKernel((void*)k_run<KIND_WATER, false>, dim3(blocks), dim3(threads), args, smem, ctx->stream));
   else if (use_async)
