@@ -452,16 +452,24 @@ template <class A> SM_HD int water_step(A& a, WaterP& p) {
 // ------------------------------------------------------------------------------------------------
 // WindParticle  (wind.h)
 // ------------------------------------------------------------------------------------------------
-template <class A> SM_HD int wind_step(A& a, WindP& p) {
+// What WindParticle::move hands to interact() of the same step.
+struct WindMid {
+  float suspension;      // param.suspension of the surface at ipos
+  uint32_t transports;   // param.transports
+  int ix, iy;
+};
+
+// WindParticle::move, wind.h:54-92
+template <class A> SM_HD int wind_move(A& a, WindP& p, WindMid& m) {
   const int dimx = a.dimx(), dimy = a.dimy();
   const int SCALE = a.scale();
-  // ---- move, wind.h:54-92 ----
   if (a.soil(p.contains).suspension == 0.0) return SM_EXIT_OOB;     // :56-57
   const int ix = (int)roundf(p.px), iy = (int)roundf(p.py);         // :60
   a.begin(ix, iy);
   sm_f3 n = map_normal(a, ix, iy);                                  // :61
   Sec32* ir = a.rec(ix, iy);
   const SoilDev param = a.soil(rec_surface(*ir));                   // :62-63
+  m.suspension = param.suspension; m.transports = param.transports; m.ix = ix; m.iy = iy;
   a.wind_frequency_touch(iy * dimx + ix);                           // :64, 49-52
   double sheight = rec_height(*ir) * (float)SCALE / 80.0f;          // :67
   if (p.height < sheight) p.height = sheight;                       // :68-70
@@ -489,22 +497,29 @@ template <class A> SM_HD int wind_step(A& a, WindP& p) {
     return SM_EXIT_OOB;
   if (sqrtf(p.sx * p.sx + p.sy * p.sy + p.sz * p.sz) < 0.01)        // :87-88
     return SM_EXIT_OOB;
-  // ---- interact, wind.h:94-136 ----
+  return SM_ALIVE;
+}
+
+// WindParticle::interact, wind.h:94-136 (always returns true upstream)
+template <class A> SM_HD int wind_interact(A& a, WindP& p, const WindMid& m) {
+  const int SCALE = a.scale();
+  const int ix = m.ix, iy = m.iy;
+  Sec32* ir = a.rec(ix, iy);
   const int nx = (int)roundf(p.px), ny = (int)roundf(p.py);         // :99
   a.target(nx, ny);
   int ncascade = 0;
   if (p.height <= map_height_bilinear(a, p.px, p.py) * (float)SCALE / 80.0f) {   // :102
-    if (param.transports == p.contains) {                           // :105
+    if (m.transports == p.contains) {                               // :105
       float len = sqrtf(p.sx * p.sx + p.sy * p.sy + p.sz * p.sz);
       double force = len * (map_height(a, nx, ny) - p.height) * (float)SCALE / 80.0f *
                      (1.0f - p.sediment);                           // :107
       a.focus(ix, iy);
-      double diff = col_remove(a, *ir, param.suspension * force);   // :109
+      double diff = col_remove(a, *ir, m.suspension * force);       // :109
       a.dirty(ix, iy);
-      p.sediment += (param.suspension * force - diff);              // :110
+      p.sediment += (m.suspension * force - diff);                  // :110
       ncascade = 1;                                                 // :112 cascade(ipos, 1)
     }
-  } else if (param.suspension > 0.0) {                              // :119
+  } else if (m.suspension > 0.0) {                                  // :119
     const float sc = a.soil(p.contains).suspension;
     p.sediment -= sc * p.sediment;                                  // :121
     a.focus(nx, ny);
@@ -520,4 +535,11 @@ template <class A> SM_HD int wind_step(A& a, WindP& p) {
   for (int q = 0; q < ncascade; q++)                                // one call site for both
     Cascade<1, A>::run(a, q == 0 ? ix : nx, q == 0 ? iy : ny, 1);
   return SM_ALIVE;
+}
+
+template <class A> SM_HD int wind_step(A& a, WindP& p) {
+  WindMid m;
+  const int r = wind_move(a, p, m);
+  if (r != SM_ALIVE) return r;
+  return wind_interact(a, p, m);
 }

@@ -434,7 +434,8 @@ __global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run(DevCtx c, int n,
 // predecessor rule of k_run; to keep that rule sound every particle publishes `done` only after its
 // own-bin predecessor's `done` (so "X done => every lower index in X's bin done" still holds), while
 // exact waiters look at `fin`.
-#define SM_KX 32
+#define SM_KX 128            // in-range lower-index neighbours tracked exactly (ids in shared memory)
+#define SM_KXW (SM_KX / 64)
 __device__ __forceinline__ bool plus_hits_3x3(int dx, int dy) {   // plus(c) meets 3x3(c + d)
   dx = dx < 0 ? -dx : dx; dy = dy < 0 ? -dy : dy;
   return (dx <= 1 && dy <= 2) || (dx <= 2 && dy <= 1);
@@ -444,22 +445,68 @@ __device__ __forceinline__ bool plus_hits_box3(int dx, int dy) {  // plus(c) mee
   return (dx <= 4 && dy <= 3) || (dx <= 3 && dy <= 4);
 }
 __device__ __forceinline__ int iabs_(int v) { return v < 0 ? -v : v; }
+__device__ __forceinline__ bool plus_hits_5x5(int dx, int dy) {   // plus(c) meets 5x5(c + d)
+  dx = iabs_(dx); dy = iabs_(dy);
+  return (dx <= 3 && dy <= 2) || (dx <= 2 && dy <= 3);
+}
+// Footprints of one step, by kind.  ip = ipos, np = npos (known after move), R = published reach.
+//   water: reads plus(ip) in move; touches {ip} U 3x3(np) in interact        (no nested re-cascade)
+//   wind : reads plus(ip) in move; touches 5x5(ip) U 5x5(np) in interact     (cascade(.,1) + one re-cascade)
+template <int KIND> struct Foot;
+template <> struct Foot<KIND_WATER> {
+  static __device__ __forceinline__ bool in_range(int dx, int dy, int, int) { return iabs_(dx) <= 6 && iabs_(dy) <= 6; }
+  // d* = B - A
+  static __device__ __forceinline__ bool box_hits_M(int dx, int dy, int) { return plus_hits_box3(dx, dy); }
+  static __device__ __forceinline__ bool W_hits_M(int ibx, int iby, int nbx, int nby, int ax, int ay) {
+    return (iabs_(ibx - ax) + iabs_(iby - ay) <= 1) || plus_hits_3x3(nbx - ax, nby - ay);
+  }
+  static __device__ __forceinline__ bool F_hits_F(int ax, int ay, int nax, int nay, int bx, int by, int nbx, int nby) {
+    return (iabs_(bx - ax) + iabs_(by - ay) <= 2) || plus_hits_3x3(nbx - ax, nby - ay) ||
+           plus_hits_3x3(nax - bx, nay - by) || (iabs_(nbx - nax) <= 2 && iabs_(nby - nay) <= 2);
+  }
+  static __device__ __forceinline__ bool box_hits_F(int ax, int ay, int nax, int nay, int bx, int by, int) {
+    return plus_hits_box3(bx - ax, by - ay) || (iabs_(bx - nax) <= 4 && iabs_(by - nay) <= 4);
+  }
+};
+template <> struct Foot<KIND_WIND> {
+  static __device__ __forceinline__ bool in_range(int dx, int dy, int RA, int RB) { return iabs_(dx) <= RA + RB && iabs_(dy) <= RA + RB; }
+  static __device__ __forceinline__ bool box_hits_M(int dx, int dy, int RB) {
+    dx = iabs_(dx); dy = iabs_(dy);
+    return (dx <= RB + 1 && dy <= RB) || (dx <= RB && dy <= RB + 1);
+  }
+  static __device__ __forceinline__ bool W_hits_M(int ibx, int iby, int nbx, int nby, int ax, int ay) {
+    return plus_hits_5x5(ibx - ax, iby - ay) || plus_hits_5x5(nbx - ax, nby - ay);
+  }
+  static __device__ __forceinline__ bool c4(int dx, int dy) { return iabs_(dx) <= 4 && iabs_(dy) <= 4; }
+  static __device__ __forceinline__ bool F_hits_F(int ax, int ay, int nax, int nay, int bx, int by, int nbx, int nby) {
+    return c4(bx - ax, by - ay) || c4(nbx - ax, nby - ay) || c4(bx - nax, by - nay) || c4(nbx - nax, nby - nay);
+  }
+  static __device__ __forceinline__ bool box_hits_F(int ax, int ay, int nax, int nay, int bx, int by, int RB) {
+    return (iabs_(bx - ax) <= RB + 2 && iabs_(by - ay) <= RB + 2) || (iabs_(bx - nax) <= RB + 2 && iabs_(by - nay) <= RB + 2);
+  }
+};
+template <int KIND> struct MidType { typedef WaterMid T; };
+template <> struct MidType<KIND_WIND> { typedef WindMid T; };
+template <class A> __device__ __forceinline__ int do_move(A& a, WaterP& p, WaterMid& m) { return water_move(a, p, m); }
+template <class A> __device__ __forceinline__ int do_move(A& a, WindP& p, WindMid& m) { return wind_move(a, p, m); }
+template <class A> __device__ __forceinline__ int do_interact(A& a, WaterP& p, const WaterMid& m) { return water_interact(a, p, m); }
+template <class A> __device__ __forceinline__ int do_interact(A& a, WindP& p, const WindMid& m) { return wind_interact(a, p, m); }
 
+template <int KIND>
 __global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run_exact(DevCtx c, int n, const float* __restrict__ spawn,
                                                                       int max_sweeps, int lshift) {
-  const int KIND = KIND_WATER;
-  typedef WaterP P;
+  typedef typename PType<KIND>::T P;
+  typedef typename MidType<KIND>::T Mid;
   __shared__ SoilDev s_soils[SM_MAX_SOILS];
   __shared__ unsigned int s_alive;
   extern __shared__ __align__(32) unsigned char s_win[];   // per slot: window, then KX ids, then KX packed ipos
   for (int i = threadIdx.x; i < c.nsoils; i += blockDim.x) s_soils[i] = c.soils[i];
   if (threadIdx.x == 0) s_alive = 0;
   __syncthreads();
-  const size_t slot_bytes = SM_WIN_BYTES + 2 * SM_KX * sizeof(uint32_t);
+  const size_t slot_bytes = SM_WIN_BYTES + SM_KX * sizeof(uint32_t);
   unsigned char* my_smem = s_win + (size_t)(threadIdx.x >> lshift) * slot_bytes;
   Sec32* my_win = (Sec32*)my_smem;
   uint32_t* blk = (uint32_t*)(my_smem + SM_WIN_BYTES);
-  uint32_t* bxy = blk + SM_KX;
 
   RunCtl* ctl = c.ctl;
   unsigned int epoch = 0;
@@ -473,6 +520,7 @@ __global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run_exact(DevCtx c, 
   const int nbx = (c.dimx + G - 1) / G, nby = (c.dimy + G - 1) / G;
 
   unsigned long long n_steps = 0, n_oob = 0, n_evap = 0, n_stall = 0;
+  bool any_doa = false;
 
   // ---- prologue ----
   {
@@ -483,19 +531,26 @@ __global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run_exact(DevCtx c, 
         if (spawn != nullptr) {
           const float x = spawn[2 * pid], y = spawn[2 * pid + 1];
           const uint32_t contains = s_soils[rec_surface(c.top[(size_t)(int)roundf(x) * c.dimy + (int)roundf(y)])].transports;
-          WaterP w{x, y, 0.0f, 0.0f, 1.0, 0.0, contains};
-          store_particle(c, pid, w);
-          alive = true;
-          c.alive[pid] = 1;
-          c.done[pid] = tag0 - 1u;
-          c.fin[pid] = tag0 - 1u;
+          if (KIND == KIND_WATER) {
+            WaterP w{x, y, 0.0f, 0.0f, 1.0, 0.0, contains};
+            store_particle(c, pid, w);
+            alive = true;
+          } else {
+            WindP w{x, y, -2.0f, 0.0f, 1.0f, 0.0, 0.0, contains};
+            store_particle(c, pid, w);
+            alive = !(s_soils[contains].suspension == 0.0);     // wind.h:56-57
+            if (!alive) { n_oob++; any_doa = true; }
+          }
+          c.alive[pid] = alive ? 1 : 0;
+          c.done[pid] = alive ? (tag0 - 1u) : 0xFFFFFFFFu;
+          c.fin[pid] = alive ? (tag0 - 1u) : 0xFFFFFFFFu;
         } else {
           alive = c.alive[pid] != 0;
         }
         if (alive) {
           P q;
           load_particle(c, pid, q);
-          bin_insert<KIND, false>(c, tag0, pid, (int)roundf(q.px), (int)roundf(q.py), 3);
+          bin_insert<KIND, false>(c, tag0, pid, (int)roundf(q.px), (int)roundf(q.py), particle_reach(q));
           my_alive++;
         }
       }
@@ -523,12 +578,14 @@ __global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run_exact(DevCtx c, 
       const int pid = slot + trip * nslots;
       const bool has = leader && pid < n && c.alive[pid] != 0;
       P p;
-      WaterMid mid;
-      WinAccess<KIND_WATER, false> a(c, s_soils, tag, my_win);
-      int ix = 0, iy = 0, nx = 0, ny = 0, nl = 0;
+      Mid mid;
+      WinAccess<KIND, false> a(c, s_soils, tag, my_win);
+      int ix = 0, iy = 0, nx = 0, ny = 0, nl = 0, myR = 0;
       uint32_t ownpred = SM_NIL;          // largest lower index in my own bin
       uint32_t pred[9];                   // crowded fallback: per-bin predecessors
-      unsigned int un0 = 0, un1 = 0;      // exact mode: unresolved list entries for move / interact
+      unsigned long long un0[SM_KXW], un1[SM_KXW];   // exact mode: unresolved list entries for move / interact
+#pragma unroll
+      for (int w = 0; w < SM_KXW; w++) { un0[w] = 0; un1[w] = 0; }
       unsigned int pm = 0;                // crowded mode: per-bin predecessors not yet `done`
       bool crowded = false;
       int stage = 3;                      // 0 wait-to-move, 1 wait-to-interact, 2 wait-to-publish-done, 3 complete
@@ -536,6 +593,7 @@ __global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run_exact(DevCtx c, 
       if (has) {
         load_particle(c, pid, p);
         ix = (int)roundf(p.px); iy = (int)roundf(p.py);
+        myR = particle_reach(p);
         stage = 0;
         // ---- scan: in-range lower indices (exact list) and per-bin predecessors (fallback) ----
         const int bx = ix / G, by = iy / G;
@@ -552,9 +610,18 @@ __global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run_exact(DevCtx c, 
             if (j < (uint32_t)pid) {
               if (best == SM_NIL || j > best) best = j;
               const int jx = (int)(nd.y >> 18), jy = (int)((nd.y >> 4) & 0x3FFFu);
-              if (iabs_(jx - ix) <= 6 && iabs_(jy - iy) <= 6) {
-                if (nl < SM_KX) { blk[nl] = j; bxy[nl] = ((uint32_t)jx << 16) | (uint32_t)jy; nl++; }
-                else crowded = true;
+              const int jR = (int)(nd.y & 0xFu);
+              if (Foot<KIND>::in_range(jx - ix, jy - iy, myR, jR)) {
+                if (nl < SM_KX) {
+                  blk[nl] = j;
+                  // static pruning: a neighbour whose box cannot meet plus(ipos) never delays the move
+                  const bool m0 = Foot<KIND>::box_hits_M(jx - ix, jy - iy, jR);
+#pragma unroll
+                  for (int w = 0; w < SM_KXW; w++) {
+                    if ((nl >> 6) == w) { un1[w] |= 1ull << (nl & 63); if (m0) un0[w] |= 1ull << (nl & 63); }
+                  }
+                  nl++;
+                } else crowded = true;
               }
             }
             j = nd.x;
@@ -565,13 +632,6 @@ __global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run_exact(DevCtx c, 
         if (crowded) {
 #pragma unroll
           for (int k = 0; k < 9; k++) if (pred[k] != SM_NIL) pm |= 1u << k;
-        } else {
-          // static pruning: a neighbour whose box cannot meet plus(ipos) never delays the move
-          for (int q = 0; q < nl; q++) {
-            un1 |= 1u << q;
-            const int jx = (int)(bxy[q] >> 16), jy = (int)(bxy[q] & 0xFFFFu);
-            if (plus_hits_box3(jx - ix, jy - iy)) un0 |= 1u << q;
-          }
         }
       }
 
@@ -585,46 +645,55 @@ __global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run_exact(DevCtx c, 
               if (((pm >> k) & 1u) && ld_acquire_u32(&c.done[pred[k]]) >= tag) pm &= ~(1u << k);
             ready = (pm == 0);
           } else {
-            unsigned int m = un0;
-            while (m) {
-              const int q = __ffs(m) - 1; m &= m - 1;
-              const uint32_t j = blk[q];
-              if (ld_acquire_u32(&c.fin[j]) >= tag) { un0 &= ~(1u << q); un1 &= ~(1u << q); continue; }
-              const unsigned long long v = *((volatile unsigned long long*)&c.mv[j]);
-              if ((unsigned int)(v >> 32) == tag) {
-                const int jx = (int)(bxy[q] >> 16), jy = (int)(bxy[q] & 0xFFFFu);
-                const int mx = (int)((v >> 16) & 0xFFFFu), my = (int)(v & 0xFFFFu);
-                // W_B = {ipos_B} U 3x3(npos_B) against plus(ipos_A)
-                const bool hit = (iabs_(jx - ix) + iabs_(jy - iy) <= 1) || plus_hits_3x3(mx - ix, my - iy);
-                if (!hit) un0 &= ~(1u << q);
+            bool all0 = true;
+#pragma unroll
+            for (int w = 0; w < SM_KXW; w++) {
+              unsigned long long m = un0[w];
+              while (m) {
+                const int b = __ffsll((long long)m) - 1; m &= m - 1;
+                const uint32_t j = blk[w * 64 + b];
+                if (ld_acquire_u32(&c.fin[j]) >= tag) { un0[w] &= ~(1ull << b); un1[w] &= ~(1ull << b); continue; }
+                const unsigned long long v = *((volatile unsigned long long*)&c.mv[j]);
+                if ((unsigned int)(v >> 32) == tag) {
+                  const uint32_t xy = c.node[par][j].y;
+                  const int jx = (int)(xy >> 18), jy = (int)((xy >> 4) & 0x3FFFu);
+                  const int mx = (int)((v >> 16) & 0xFFFFu), my = (int)(v & 0xFFFFu);
+                  // what B writes against plus(ipos_A)
+                  const bool hit = Foot<KIND>::W_hits_M(jx, jy, mx, my, ix, iy);
+                  if (!hit) un0[w] &= ~(1ull << b);
+                }
               }
+              if (un0[w]) all0 = false;
             }
-            ready = (un0 == 0);
+            ready = all0;
           }
         } else if (stage == 1) {
           if (crowded) ready = true;
           else {
-            unsigned int m = un1;
-            while (m) {
-              const int q = __ffs(m) - 1; m &= m - 1;
-              const uint32_t j = blk[q];
-              if (ld_acquire_u32(&c.fin[j]) >= tag) { un1 &= ~(1u << q); continue; }
-              const int jx = (int)(bxy[q] >> 16), jy = (int)(bxy[q] & 0xFFFFu);
-              const unsigned long long v = *((volatile unsigned long long*)&c.mv[j]);
-              if ((unsigned int)(v >> 32) == tag) {
-                const int mx = (int)((v >> 16) & 0xFFFFu), my = (int)(v & 0xFFFFu);
-                const bool hit = (iabs_(jx - ix) + iabs_(jy - iy) <= 2)        // plus(A) x plus(B)
-                                 || plus_hits_3x3(mx - ix, my - iy)            // plus(A) x 3x3(npos_B)
-                                 || plus_hits_3x3(nx - jx, ny - jy)            // 3x3(npos_A) x plus(B)
-                                 || (iabs_(mx - nx) <= 2 && iabs_(my - ny) <= 2);   // 3x3 x 3x3
-                if (!hit) un1 &= ~(1u << q);
-              } else {
-                // B has not moved yet: its footprint lies in ipos_B +- 3
-                const bool hit = plus_hits_box3(jx - ix, jy - iy) || (iabs_(jx - nx) <= 4 && iabs_(jy - ny) <= 4);
-                if (!hit) un1 &= ~(1u << q);
+            bool all1 = true;
+#pragma unroll
+            for (int w = 0; w < SM_KXW; w++) {
+              unsigned long long m = un1[w];
+              while (m) {
+                const int b = __ffsll((long long)m) - 1; m &= m - 1;
+                const uint32_t j = blk[w * 64 + b];
+                if (ld_acquire_u32(&c.fin[j]) >= tag) { un1[w] &= ~(1ull << b); continue; }
+                const uint32_t xy = c.node[par][j].y;
+                const int jx = (int)(xy >> 18), jy = (int)((xy >> 4) & 0x3FFFu);
+                const unsigned long long v = *((volatile unsigned long long*)&c.mv[j]);
+                bool hit;
+                if ((unsigned int)(v >> 32) == tag) {
+                  const int mx = (int)((v >> 16) & 0xFFFFu), my = (int)(v & 0xFFFFu);
+                  hit = Foot<KIND>::F_hits_F(ix, iy, nx, ny, jx, jy, mx, my);
+                } else {
+                  // B has not moved yet: its footprint lies in ipos_B +- R_B
+                  hit = Foot<KIND>::box_hits_F(ix, iy, nx, ny, jx, jy, (int)(xy & 0xFu));
+                }
+                if (!hit) un1[w] &= ~(1ull << b);
               }
+              if (un1[w]) all1 = false;
             }
-            ready = (un1 == 0);
+            ready = all1;
           }
         } else if (stage == 2) {
           ready = (ownpred == SM_NIL) || (ld_acquire_u32(&c.done[ownpred]) >= tag);
@@ -634,18 +703,19 @@ __global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run_exact(DevCtx c, 
 
         // ---- move ----
         if (stage == 0 && ready) {
-          result = water_move(a, p, mid);
+          result = do_move(a, p, mid);
           if (result == SM_ALIVE) {
             nx = (int)roundf(p.px); ny = (int)roundf(p.py);
             *((volatile unsigned long long*)&c.mv[pid]) = ((unsigned long long)tag << 32) | ((unsigned long long)nx << 16) | (unsigned long long)ny;
-            if (iabs_(nx - ix) > 2 || iabs_(ny - iy) > 2) atomicOr(&ctl->err, 1u << 4);   // SM_ERR_REACH
+            if (iabs_(nx - ix) > myR - Reach<KIND>::RING || iabs_(ny - iy) > myR - Reach<KIND>::RING)
+              atomicOr(&ctl->err, 1u << 4);   // SM_ERR_REACH
             stage = 1;
           } else {
             // stalled or left the map: only track[] was written
             st_release_u32(&c.fin[pid], 0xFFFFFFFFu);
             store_particle(c, pid, p);
             c.alive[pid] = 0;
-            if (result == SM_EXIT_OOB) n_oob++; else n_stall++;
+            if (result == SM_EXIT_STALL) n_stall++; else n_oob++;
             stage = 2;
           }
           ready = false;
@@ -653,13 +723,13 @@ __global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run_exact(DevCtx c, 
         __syncwarp();
         // ---- interact ----
         if (stage == 1 && ready) {
-          result = water_interact(a, p, mid);
+          result = do_interact(a, p, mid);
           a.flush();
           st_release_u32(&c.fin[pid], result == SM_ALIVE ? tag : 0xFFFFFFFFu);
           store_particle(c, pid, p);
           n_steps++;
           if (result == SM_ALIVE) {
-            bin_insert<KIND, false>(c, tag + 1u, pid, nx, ny, 3);
+            bin_insert<KIND, false>(c, tag + 1u, pid, nx, ny, particle_reach(p));
             my_alive++;
           } else {
             c.alive[pid] = 0;
@@ -690,6 +760,7 @@ __global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run_exact(DevCtx c, 
   if (n_oob) atomicAdd(&ctl->exit_oob, n_oob);
   if (n_evap) atomicAdd(&ctl->exit_evap, n_evap);
   if (n_stall) atomicAdd(&ctl->exit_stall, n_stall);
+  if (any_doa) atomicMax(&ctl->sweeps, 1ull);
   if (gtid == 0) {
     atomicMax(&ctl->sweeps, (unsigned long long)s);
     ctl->alive = total_alive;
@@ -1316,7 +1387,8 @@ static int create_impl(const sm_config* cfg, int nranks, int rank, int share, sm
     CK(cudaFuncSetAttribute(k_run<KIND_WATER, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BLOCK * SM_WIN_BYTES));
     CK(cudaFuncSetAttribute(k_run<KIND_WIND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BLOCK * SM_WIN_BYTES));
     CK(cudaFuncSetAttribute(k_run<KIND_WATER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BLOCK * SM_WIN_BYTES));
-    CK(cudaFuncSetAttribute(k_run_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BLOCK * (SM_WIN_BYTES + 2 * SM_KX * 4)));
+    CK(cudaFuncSetAttribute(k_run_exact<KIND_WATER>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BLOCK * (SM_WIN_BYTES + SM_KX * 4)));
+    CK(cudaFuncSetAttribute(k_run_exact<KIND_WIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BLOCK * (SM_WIN_BYTES + SM_KX * 4)));
     CK(cudaFuncSetAttribute(k_run<KIND_WIND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BLOCK * SM_WIN_BYTES));
     CK(cudaFuncSetAttribute(k_run_async<KIND_WIND, SM_ASYNC_DELTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BLOCK * SM_WIN_BYTES));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1683,15 +1755,18 @@ static int launch_run(sm_context* ctx, int kind, int n, const float* d_spawn, in
     }
     if (blocks < 1) blocks = 1;
   }
-  // water, single rank: exact-footprint kernel (opt-in SM_EXACT=1 until it is the measured default)
+  // single rank: exact-footprint kernel.  SM_EXACT = bit mask of kinds (1 water, 2 wind); default 1:
+  // measured -16 % on the water batch of config 3
   bool use_exact = false;
-  if (kind == KIND_WATER && !multi) {
+  if (!multi) {
     const char* e = getenv("SM_EXACT");
-    if (e && atoi(e) == 1) {
+    const int mask = e ? atoi(e) : 1;
+    if (mask & (1 << kind)) {
       for (int ls = lshift;; ls--) {
-        const size_t sm2 = (size_t)(threads >> ls) * (SM_WIN_BYTES + 2 * SM_KX * 4);
+        const size_t sm2 = (size_t)(threads >> ls) * (SM_WIN_BYTES + SM_KX * 4);
         int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run_exact, threads, sm2));
+        if (kind == KIND_WATER) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run_exact<KIND_WATER>, threads, sm2));
+        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run_exact<KIND_WIND>, threads, sm2));
         const long long need_threads = (long long)std::max(n, 1) << ls;
         const long long maxblocks = (long long)ctx->num_sms * occ;
         if (occ >= 1 && (need_threads <= maxblocks * threads || ls == 0)) {
@@ -1705,7 +1780,7 @@ static int launch_run(sm_context* ctx, int kind, int n, const float* d_spawn, in
   }
   // wind: barrier-free super-steps when every particle can own a thread slot
   bool use_async = false;
-  if (kind == KIND_WIND && !multi) {
+  if (kind == KIND_WIND && !multi && !use_exact) {
     // measured on config 3: 780 ms vs 650 ms for the per-sweep-barrier kernel - the clusters that
     // bound a sweep are persistent (neighbouring particles alternate every sweep), so removing the
     // barrier does not shorten the critical path.  Kept as an opt-in (SM_ASYNC=1).
@@ -1728,8 +1803,10 @@ static int launch_run(sm_context* ctx, int kind, int n, const float* d_spawn, in
     CK(cudaLaunchCooperativeKernel((void*)k_run<KIND_WATER, true>, dim3(blocks), dim3(threads), args, smem, ctx->stream));
   else if (multi)
     CK(cudaLaunchCooperativeKernel((void*)k_run<KIND_WIND, true>, dim3(blocks), dim3(threads), args, smem, ctx->stream));
+  else if (use_exact && kind == KIND_WATER)
+    CK(cudaLaunchCooperativeKernel((void*)k_run_exact<KIND_WATER>, dim3(blocks), dim3(threads), args, smem, ctx->stream));
   else if (use_exact)
-    CK(cudaLaunchCooperativeKernel((void*)k_run_exact, dim3(blocks), dim3(threads), args, smem, ctx->stream));
+    CK(cudaLaunchCooperativeKernel((void*)k_run_exact<KIND_WIND>, dim3(blocks), dim3(threads), args, smem, ctx->stream));
   else if (kind == KIND_WATER)
     CK(cudaLaunchCooperativeKernel((void*)k_run<KIND_WATER, false>, dim3(blocks), dim3(threads), args, smem, ctx->stream));
   else if (use_async)
