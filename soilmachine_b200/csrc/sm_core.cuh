@@ -308,8 +308,18 @@ template <int DEPTH, class A> struct Cascade {
       if (!changed && !((active >> k) & 1u)) continue;
       const int kk = k + (k >= 4 ? 1 : 0);
       const int nx = cx + kk / 3 - 1, ny = cy + kk % 3 - 1;
-      // :66  full height difference, narrowed to float
-      float diff = (float)((map_height(a, cx, cy) - map_height(a, nx, ny)) * (float)SCALE / 80.0f);
+      // :66  full height difference, narrowed to float.  Same division-free proof as in the speculative
+      // pass, on the CURRENT heights: |dd| < 80*maxdiff*(1 - 2^-20) => diff == 0 or excess <= 0 => continue.
+      double hc2, hn2;
+      uint32_t tc2, tn2;
+      a.query(cx, cy, hc2, tc2);
+      a.query(nx, ny, hn2, tn2);
+      const double dd2 = (hc2 - hn2) * (float)SCALE;
+      {
+        const float md2 = a.soil(dd2 > 0 ? tc2 : tn2).maxdiff;
+        if (fabs(dd2) < 80.0 * (double)md2 * (1.0 - 9.5367431640625e-07)) continue;
+      }
+      float diff = (float)(dd2 / 80.0f);
       if (diff == 0) continue;
       int tx = (diff > 0) ? cx : nx, ty = (diff > 0) ? cy : ny;     // :71-72
       int bx = (diff > 0) ? nx : cx, by = (diff > 0) ? ny : cy;

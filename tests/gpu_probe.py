@@ -26,7 +26,7 @@ def run(soil, dim, nw, nd, lanes=None, iters=1, label=""):
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
-    if which in ("profile", "one", "mesh", "big") or which.startswith("cfg3:"): which = "none"
+    if which in ("profile", "one", "mesh", "big", "tail", "poolrate") or which.startswith("cfg3:"): which = "none"
     if which in ("all", "single"):
         # single particles: sweep time = step latency (+ trivial barrier)
         run("rocksand", 1024, 1, 0, label="single")
@@ -127,3 +127,34 @@ def bigcfg(soil, dim, nw, nd, frames=2):
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "big":
     bigcfg("bigbutte", 4096, 50000, 0)                       # BASELINE config 4 shape (single GPU)
     bigcfg("rockgravelpebbles_big", 8192, 100000, 100000)    # BASELINE config 5 shape: 200k mixed, wind inert
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "tail":
+    import ctypes as C
+    from soilmachine_b200 import host
+    sim = host.Simulation("rockgravelpebblessand", seed=42, dimx=4096, dimy=4096, max_particles=25000)
+    out = (C.c_uint64 * 16)()
+    for f in range(2):
+        xw = host.spawn_list(25000, 4096, 4096); xd = host.spawn_list(25000, 4096, 4096)
+        sim.ctx.water_run(xw)
+        sim.ctx.lib.sm_debug_profile(sim.ctx.h, out, 1)
+        g = sim.ctx.wind_run(xd)
+        sim.ctx.lib.sm_debug_profile(sim.ctx.h, out, 2)
+        print("wind frame %d: steps=%d sweeps=%d ms=%.1f | steps>20k cycles: %d (%.2f/sweep), >40k: %d (%.2f/sweep), max step %d cycles; avg step %.0f cycles"
+              % (f, g.steps, g.sweeps, g.device_ms, out[13], out[13] / g.sweeps, out[14], out[14] / g.sweeps, out[15], out[4] / max(g.steps, 1)), flush=True)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "poolrate":
+    import ctypes as C
+    from soilmachine_b200 import host
+    sim = host.Simulation("rockgravelpebblessand", seed=42, dimx=4096, dimy=4096, max_particles=25000)
+    out = (C.c_uint64 * 16)()
+    def snap():
+        sim.ctx.lib.sm_debug_profile(sim.ctx.h, out, 3)
+        return out[0] + out[1], out[2] + out[3], out[4]
+    for f in range(2):
+        xw = host.spawn_list(25000, 4096, 4096); xd = host.spawn_list(25000, 4096, 4096)
+        a0 = snap(); g = sim.ctx.water_run(xw); a1 = snap()
+        print("water: steps=%d frees=%d (%.3f/step) ring-allocs=%d bump-allocs=%d (allocs %.3f/step)" % (g.steps, a1[0]-a0[0], (a1[0]-a0[0])/g.steps, a1[1]-a0[1], a1[2]-a0[2], (a1[1]-a0[1]+a1[2]-a0[2])/g.steps), flush=True)
+        g = sim.ctx.wind_run(xd); a2 = snap()
+        print("wind : steps=%d frees=%d (%.3f/step) ring-allocs=%d bump-allocs=%d (allocs %.3f/step)" % (g.steps, a2[0]-a1[0], (a2[0]-a1[0])/g.steps, a2[1]-a1[1], a2[2]-a1[2], (a2[1]-a1[1]+a2[2]-a1[2])/g.steps), flush=True)
