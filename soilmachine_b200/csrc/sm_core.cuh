@@ -302,30 +302,26 @@ template <int DEPTH, class A> struct Cascade {
     for (int k = 0; k < 8; k++) order |= (unsigned int)k << (4 * rank[k]);
 
     bool changed = false;
+    Sec32* const pc = a.rec(cx, cy);                // the centre record: one lookup for the whole loop
     SM_UNROLL1
     for (int i = 0; i < num; i++) {
       const int k = (int)((order >> (4 * i)) & 7u);
       if (!changed && !((active >> k) & 1u)) continue;
       const int kk = k + (k >= 4 ? 1 : 0);
       const int nx = cx + kk / 3 - 1, ny = cy + kk % 3 - 1;
+      Sec32* const pn = a.rec(nx, ny);              // one lookup per neighbour and iteration
       // :66  full height difference, narrowed to float.  Same division-free proof as in the speculative
       // pass, on the CURRENT heights: |dd| < 80*maxdiff*(1 - 2^-20) => diff == 0 or excess <= 0 => continue.
-      double hc2, hn2;
-      uint32_t tc2, tn2;
-      a.query(cx, cy, hc2, tc2);
-      a.query(nx, ny, hn2, tn2);
-      const double dd2 = (hc2 - hn2) * (float)SCALE;
-      {
-        const float md2 = a.soil(dd2 > 0 ? tc2 : tn2).maxdiff;
-        if (fabs(dd2) < 80.0 * (double)md2 * (1.0 - 9.5367431640625e-07)) continue;
-      }
+      const double dd2 = (rec_height(*pc) - rec_height(*pn)) * (float)SCALE;
+      Sec32* const tr = (dd2 > 0) ? pc : pn;        // :71-72 the higher cell ...
+      Sec32* const br = (dd2 > 0) ? pn : pc;        //        ... and the lower one
+      const uint32_t type = rec_surface(*tr);       // :74-75
+      const SoilDev sp = a.soil(type);
+      if (fabs(dd2) < 80.0 * (double)sp.maxdiff * (1.0 - 9.5367431640625e-07)) continue;
       float diff = (float)(dd2 / 80.0f);
       if (diff == 0) continue;
-      int tx = (diff > 0) ? cx : nx, ty = (diff > 0) ? cy : ny;     // :71-72
-      int bx = (diff > 0) ? nx : cx, by = (diff > 0) ? ny : cy;
-      Sec32* tr = a.rec(tx, ty);
-      uint32_t type = rec_surface(*tr);                             // :74-75
-      const SoilDev sp = a.soil(type);
+      const int tx = (diff > 0) ? cx : nx, ty = (diff > 0) ? cy : ny;
+      const int bx = (diff > 0) ? nx : cx, by = (diff > 0) ? ny : cy;
       float excess = fabsf(diff) - sp.maxdiff;                      // :78
       if (excess <= 0) continue;
       float transfer = sp.settling * excess / 2.0f;                 // :83
@@ -335,10 +331,10 @@ template <int DEPTH, class A> struct Cascade {
       changed = true;
       a.focus(tx, ty);
       if (col_remove(a, *tr, (double)transfer) != 0) recascade = true;   // :90-91
-      a.dirty(tx, ty);
+      a.dirty_rec(tr, tx, ty);
       a.focus(bx, by);
-      col_add(a, *a.rec(bx, by), (double)transfer, sp.cascades);    // :92
-      a.dirty(bx, by);
+      col_add(a, *br, (double)transfer, sp.cascades);               // :92
+      a.dirty_rec(br, bx, by);
       if constexpr (DEPTH > 0) {
         if (recascade && transferloop > 0) {                        // :96-97
           --transferloop;

@@ -218,6 +218,7 @@ struct DevAccess {
   __device__ __forceinline__ void begin(int, int) {}
   __device__ __forceinline__ void target(int, int) {}
   __device__ __forceinline__ void dirty(int, int) {}
+  __device__ __forceinline__ void dirty_rec(Sec32*, int, int) {}
   __device__ __forceinline__ void cascade_prefetch(int, int) {}
   __device__ __forceinline__ void mark(int) {}
   __device__ __forceinline__ void focus(int, int) {}
@@ -324,7 +325,7 @@ struct WinAccess {
   }
   __device__ __forceinline__ void begin(int ix, int iy) {
     ax = ix; ay = iy; has_b = false; valid = 0; dirtym = 0;
-    issue_patch(ix, iy, 0, SM_PLUS_MASK);
+    issue_patch(ix, iy, 0, KIND_ == 1 ? 0x1FFu : SM_PLUS_MASK);   // wind cascades around ipos almost every step: fetch the whole patch at once
     const int ind = iy * c.dimx + ix;
     if (KIND_ == 0) { f_freq = c.wfreq[ind]; f_track = c.wtrack[ind]; }
     else { f_freq = c.windfreq[ind]; }
@@ -367,6 +368,11 @@ struct WinAccess {
   __device__ __forceinline__ void dirty(int x, int y) {
     const int s = slot_of(x, y);
     if (s >= 0) dirtym |= 1u << s;
+  }
+  // mark a record obtained from rec() dirty without looking its slot up again
+  __device__ __forceinline__ void dirty_rec(Sec32* r, int, int) {
+    const long off = r - win;
+    if (off >= 0 && off < SM_WIN_SLOTS) dirtym |= 1u << (int)off;
   }
   // read-only queries served from the window with shared-memory loads (no generic pointer is formed)
   // (measured: -5 % on the water kernel, +11 % on the wind kernel, so wind keeps the pointer path)

@@ -31,6 +31,7 @@ struct HostAccess {
   void begin(int, int) {}
   void target(int, int) {}
   void dirty(int, int) {}
+  void dirty_rec(Sec32*, int, int) {}
   void cascade_prefetch(int, int) {}
   void mark(int) {}
   void focus(int, int) {}
