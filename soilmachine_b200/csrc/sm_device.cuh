@@ -92,6 +92,7 @@ struct DevCtx {
   // sharding by x-strips: rank q owns the columns x in [q*strip_w, min((q+1)*strip_w, dimx)); its `top`
   // holds only that strip.  nranks == 1: one strip = the whole map.
   int nranks, rank, strip_w;
+  unsigned long long* dbg;       // -DSM_PROFILE: per-sweep (clock64, live particles) of the last launch
   PeerPtrs peer[SM_MAX_RANKS];
 };
 

@@ -292,6 +292,9 @@ __global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run(DevCtx c, int n,
     if (!MULTI) total_alive = ld_volatile_u32(&ctl->alive_slot[s % 3]);
     if (total_alive == 0 || (max_sweeps >= 0 && s >= max_sweeps)) break;
     if (gtid == 0) st_volatile_u32(&ctl->alive_slot[(s + 2) % 3], 0u);
+#ifdef SM_PROFILE
+    if (gtid == 0 && s < 16384 && c.dbg) { c.dbg[2 * s] = (unsigned long long)clock64(); c.dbg[2 * s + 1] = total_alive; }
+#endif
 
     unsigned int my_alive = 0;
     SM_PROF(0)   // barrier exit -> loop top
@@ -1288,7 +1291,7 @@ void sm_destroy(sm_context* ctx) {
   cudaFree(d.wfreq); cudaFree(d.wtrack); cudaFree(d.windfreq); cudaFree(ctx->d_soils);
   cudaFree(d.ctl); cudaFree(d.pa); cudaFree(d.pb); cudaFree(d.pc); cudaFree(d.alive); cudaFree(d.done); cudaFree(d.pstate); cudaFree(d.fin); cudaFree(d.mv);
   for (int i = 0; i < 2; i++) { cudaFree(d.head[i]); cudaFree(d.node[i]); }
-  cudaFree(ctx->d_verts); cudaFree(ctx->d_colors);
+  cudaFree(ctx->d_verts); cudaFree(ctx->d_colors); cudaFree(d.dbg);
   cudaFree(ctx->d_spawn); cudaFree(ctx->d_scratch); cudaFree(ctx->d_iscratch); cudaFree(ctx->d_cellres);
   if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -1375,6 +1378,8 @@ static int create_impl(const sm_config* cfg, int nranks, int rank, int share, sm
     CK(cudaMalloc(&ctx->d_scratch, std::max(C, (size_t)SUM_BLOCKS + 8) * 8));
     CK(cudaMalloc(&ctx->d_iscratch, C * 4));
     CK(cudaMalloc(&ctx->d_cellres, sizeof(CellRes)));
+    CK(cudaMalloc(&d.dbg, 2 * 16384 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(d.dbg, 0, 2 * 16384 * sizeof(unsigned long long), ctx->stream));
     CK(cudaMallocHost(&ctx->h_ctl, sizeof(RunCtl)));
     // tags start at 1 so that zero-initialised bin heads never match
     RunCtl init; memset(&init, 0, sizeof(init)); init.tag_base = 2;
@@ -2018,6 +2023,12 @@ int sm_timer_stop(sm_context* ctx, double* elapsed_ms) {
 }
 int sm_launch_count(sm_context* ctx, int64_t* n) { *n = ctx->launches; return SM_OK; }
 // debug (only meaningful in a -DSM_PROFILE build): clock64() totals per phase, summed over particles
+int sm_debug_sweeps(sm_context* ctx, uint64_t* out, int nsweeps) {   // -DSM_PROFILE builds: (clock64, alive) per sweep
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(out, ctx->d.dbg, (size_t)std::min(nsweeps, 16384) * 16, cudaMemcpyDeviceToHost));
+  return SM_OK;
+}
 int sm_debug_profile(sm_context* ctx, uint64_t* out16, int reset) {
   CK(cudaSetDevice(ctx->cfg.device));
   CK(cudaStreamSynchronize(ctx->stream));

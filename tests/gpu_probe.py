@@ -26,7 +26,7 @@ def run(soil, dim, nw, nd, lanes=None, iters=1, label=""):
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
-    if which in ("profile", "one", "mesh", "big", "tail", "poolrate") or which.startswith("cfg3:"): which = "none"
+    if which in ("profile", "one", "mesh", "big", "tail", "poolrate", "sweepcurve") or which.startswith("cfg3:"): which = "none"
     if which in ("all", "single"):
         # single particles: sweep time = step latency (+ trivial barrier)
         run("rocksand", 1024, 1, 0, label="single")
@@ -158,3 +158,21 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "poolrate":
         print("water: steps=%d frees=%d (%.3f/step) ring-allocs=%d bump-allocs=%d (allocs %.3f/step)" % (g.steps, a1[0]-a0[0], (a1[0]-a0[0])/g.steps, a1[1]-a0[1], a1[2]-a0[2], (a1[1]-a0[1]+a1[2]-a0[2])/g.steps), flush=True)
         g = sim.ctx.wind_run(xd); a2 = snap()
         print("wind : steps=%d frees=%d (%.3f/step) ring-allocs=%d bump-allocs=%d (allocs %.3f/step)" % (g.steps, a2[0]-a1[0], (a2[0]-a1[0])/g.steps, a2[1]-a1[1], a2[2]-a1[2], (a2[1]-a1[1]+a2[2]-a1[2])/g.steps), flush=True)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "sweepcurve":
+    import ctypes as C
+    from soilmachine_b200 import host
+    sim = host.Simulation("rockgravelpebblessand", seed=42, dimx=4096, dimy=4096, max_particles=25000)
+    xw = host.spawn_list(25000, 4096, 4096); xd = host.spawn_list(25000, 4096, 4096)
+    sim.ctx.water_run(xw)
+    g = sim.ctx.wind_run(xd)
+    n = min(int(g.sweeps), 16384)
+    buf = np.zeros((n, 2), np.uint64)
+    sim.ctx.lib.sm_debug_sweeps(sim.ctx.h, buf.ctypes.data_as(C.c_void_p), n)
+    t = buf[:, 0].astype(np.float64); alive = buf[:, 1].astype(np.int64)
+    dt = np.diff(t) / 1.965e3    # us at 1965 MHz
+    print("wind: sweeps=%d ms=%.1f" % (g.sweeps, g.device_ms))
+    for lo in range(0, n - 1, 1000):
+        hi = min(lo + 1000, n - 1)
+        print("  sweeps %5d-%5d: alive %6d..%6d  avg %.1f us/sweep  (sum %.1f ms)" % (lo, hi, alive[lo], alive[hi], dt[lo:hi].mean(), dt[lo:hi].sum() / 1e3), flush=True)
