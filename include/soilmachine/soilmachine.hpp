@@ -26,6 +26,7 @@
 #include <string>
 #include <vector>
 #include "../soilmachine_b200.h"
+#include "soilfile.hpp"
 
 namespace soilmachine {
 
@@ -77,6 +78,34 @@ inline std::vector<SurfLayer>& layers_table() { static std::vector<SurfLayer> l;
 #define soils (::soilmachine::soils_table())
 #define soilmap (::soilmachine::soilmap_table())
 #define layers (::soilmachine::layers_table())
+
+// loadsoil(), io.h:7-230: fills the soils / soilmap / layers tables from a `.soil` file (same quirks as
+// upstream, see soilfile.hpp) and returns the WORLD block; an application that keeps the reference's global
+// ints assigns them from the result (SIZEX = w.sizex; ...).
+inline WorldEntry loadsoil(const std::string& file = "soil/default.soil") {
+  SoilFile f;
+  parse_soil_file(file, f);
+  soils.clear(); soilmap.clear(); layers.clear();
+  for (const SoilEntry& e : f.soils) {
+    SurfParam p;
+    p.name = e.name; p.density = e.density; p.porosity = e.porosity;
+    p.color = vec4{e.color[0], e.color[1], e.color[2], e.color[3]};
+    p.phong = vec4{e.phong[0], e.phong[1], e.phong[2], e.phong[3]};
+    p.transports = (SurfType)e.transports; p.solubility = e.solubility; p.equrate = e.equrate; p.friction = e.friction;
+    p.erodes = (SurfType)e.erodes; p.erosionrate = e.erosionrate;
+    p.cascades = (SurfType)e.cascades; p.maxdiff = e.maxdiff; p.settling = e.settling;
+    p.abrades = (SurfType)e.abrades; p.suspension = e.suspension; p.abrasion = e.abrasion;
+    soils.push_back(p);
+  }
+  for (const auto& kv : f.soilmap) soilmap[kv.first] = kv.second;
+  for (const LayerEntry& l : f.layers) {
+    SurfLayer L((SurfType)l.type);
+    L.min = l.min; L.bias = l.bias; L.scale = l.scale; L.octaves = l.octaves; L.lacunarity = l.lacunarity;
+    L.gain = l.gain; L.frequency = l.frequency;
+    layers.push_back(L);
+  }
+  return f.world;
+}
 
 struct Error : std::runtime_error { int code; Error(int c, const std::string& m) : std::runtime_error(m), code(c) {} };
 

@@ -99,6 +99,13 @@ int sm_peer_attach(sm_context* ctx, const sm_peer_blob* blobs, int32_t nblobs, i
 /* ---- tables: soils[] / layers (surface.h:41-57,104; io.h:7-230 fills them) -------------------- */
 int sm_set_soils(sm_context* ctx, const sm_soil* soils, int32_t n);
 
+/* loadsoil() (source/io.h:7-230): parse a `.soil` text file into the tables (host only, no device work).
+ * Buffers: soils[max_soils], names[max_soils][32], colors[max_soils][4], layers[max_layers],
+ * world5 = {SIZEX, SIZEY, SCALE, NWATER, NWIND}.  ctx may be NULL.  Returns SM_ERR_INVALID on a missing
+ * file or a syntax error (message in sm_last_error(NULL)). */
+int sm_parse_soil_file(const char* path, sm_soil* soils, char* names, float* colors, int32_t max_soils,
+                       int32_t* nsoils, sm_layer* layers, int32_t max_layers, int32_t* nlayers, int32_t* world5);
+
 /* ---- terrain -------------------------------------------------------------------------------- */
 /* Layermap::initialize (layermap.h:163-216): for each layer, for each cell, add(noise section).
  * Bit-identical to the reference's FastNoiseLite OpenSimplex2/FBm path (FastNoiseLite.h:321-340,

@@ -12,6 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libsoilmachine_b200.so")
 
 SM_OK, SM_ERR_INVALID, SM_ERR_CUDA, SM_ERR_POOL, SM_ERR_REACH, SM_ERR_NOGPU = range(6)
+SM_MAX_SOILS = 64
 
 SOIL_DTYPE = np.dtype([
     ("transports", "<i4"), ("erodes", "<i4"), ("cascades", "<i4"), ("abrades", "<i4"),
@@ -35,7 +36,7 @@ SYMBOLS = [
     "sm_wind_sweeps", "sm_wind_state", "sm_launch_count", "sm_device_alloc", "sm_device_free",
     "sm_device_upload", "sm_timer_start", "sm_timer_stop", "sm_set_soil_colors", "sm_mesh_update",
     "sm_mesh_device_ptr", "sm_export_height", "sm_export_color", "sm_create_sharded", "sm_shard_range",
-    "sm_peer_export", "sm_peer_attach",
+    "sm_peer_export", "sm_peer_attach", "sm_parse_soil_file",
 ]
 
 
@@ -80,6 +81,24 @@ def load():
 
 def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+def parse_soil_file(path):
+    """loadsoil() of the reference (source/io.h:7-230) through the library's own parser."""
+    lib = load()
+    soils = np.zeros(SM_MAX_SOILS, SOIL_DTYPE); names = np.zeros((SM_MAX_SOILS, 32), np.uint8)
+    colors = np.zeros((SM_MAX_SOILS, 4), np.float32); layers = np.zeros(16, LAYER_DTYPE)
+    ns, nl = C.c_int32(), C.c_int32()
+    world = (C.c_int32 * 5)()
+    rc = lib.sm_parse_soil_file(str(path).encode(), soils.ctypes.data_as(C.c_void_p), names.ctypes.data_as(C.c_char_p),
+                                _p(colors, C.c_float), SM_MAX_SOILS, C.byref(ns), layers.ctypes.data_as(C.c_void_p), 16,
+                                C.byref(nl), world)
+    if rc != SM_OK:
+        raise SoilMachineError(rc, lib.sm_last_error(None).decode())
+    n = ns.value
+    return {"soils": soils[:n].copy(), "colors": colors[:n].copy(), "layers": layers[:nl.value].copy(),
+            "soil_names": [bytes(names[i]).split(b"\0")[0].decode() for i in range(n)],
+            "world": dict(zip(("sizex", "sizey", "scale", "nwater", "nwind"), list(world)))}
 
 
 def soils_from(table):

@@ -14,6 +14,7 @@
 #include <vector>
 #include <algorithm>
 #include "../../include/soilmachine_b200.h"
+#include "../../include/soilmachine/soilfile.hpp"
 #include "sm_device.cuh"
 #include "sm_noise.cuh"
 
@@ -2006,6 +2007,36 @@ int sm_export_height(sm_context* ctx, float* height) {
 int sm_export_color(sm_context* ctx, float* bgra) {
   if (!bgra) return fail(ctx, SM_ERR_INVALID, "null buffer");
   return export_maps(ctx, nullptr, bgra);
+}
+int sm_parse_soil_file(const char* path, sm_soil* soils, char* names, float* colors, int32_t max_soils,
+                       int32_t* nsoils, sm_layer* layers, int32_t max_layers, int32_t* nlayers, int32_t* world5) {
+  if (!path || !nsoils || !nlayers) { g_create_err = "sm_parse_soil_file: null argument"; return SM_ERR_INVALID; }
+  soilmachine::SoilFile f;
+  try {
+    soilmachine::parse_soil_file(path, f);
+  } catch (const std::exception& e) {
+    g_create_err = e.what();
+    return SM_ERR_INVALID;
+  }
+  if ((int)f.soils.size() > max_soils || (int)f.layers.size() > max_layers) {
+    g_create_err = "sm_parse_soil_file: output buffers too small";
+    return SM_ERR_INVALID;
+  }
+  *nsoils = (int32_t)f.soils.size();
+  *nlayers = (int32_t)f.layers.size();
+  for (size_t i = 0; i < f.soils.size(); i++) {
+    const soilmachine::SoilEntry& e = f.soils[i];
+    if (soils) soils[i] = sm_soil{e.transports, e.erodes, e.cascades, e.abrades, e.density, e.porosity, e.solubility,
+                                  e.equrate, e.friction, e.erosionrate, e.maxdiff, e.settling, e.suspension, e.abrasion};
+    if (names) { memset(names + 32 * i, 0, 32); strncpy(names + 32 * i, e.name.c_str(), 31); }
+    if (colors) for (int k = 0; k < 4; k++) colors[4 * i + k] = e.color[k];
+  }
+  for (size_t i = 0; i < f.layers.size(); i++) {
+    const soilmachine::LayerEntry& l = f.layers[i];
+    if (layers) layers[i] = sm_layer{l.type, l.min, l.bias, l.scale, l.octaves, l.lacunarity, l.gain, l.frequency};
+  }
+  if (world5) { world5[0] = f.world.sizex; world5[1] = f.world.sizey; world5[2] = f.world.scale; world5[3] = f.world.nwater; world5[4] = f.world.nwind; }
+  return SM_OK;
 }
 int sm_timer_start(sm_context* ctx) {
   CK(cudaSetDevice(ctx->cfg.device));

@@ -8,6 +8,7 @@ GCC evaluates the two arguments right to left, so y takes the first draw).
 """
 import ctypes as C
 import ctypes.util
+import os
 import numpy as np
 from . import capi, presets
 
@@ -43,7 +44,9 @@ class Simulation:
     """soil preset + GPU context + frame loop."""
 
     def __init__(self, soil, seed=42, dimx=0, dimy=0, device=0, max_particles=0, pool_capacity=0):
-        self.preset = presets.load(soil)
+        # a preset name (JSON tables dumped from the reference loader) or a path to a `.soil` file
+        self.preset = capi.parse_soil_file(soil) if str(soil).endswith(".soil") and os.path.exists(str(soil)) \
+            else presets.load(soil)
         w = self.preset["world"]
         self.dimx = int(dimx or w["sizex"])
         self.dimy = int(dimy or w["sizey"])

@@ -83,3 +83,28 @@ def test_cpp_facade_compiles_and_links():
         assert "legacy ops ok" in out.stdout
     else:
         assert out.returncode == 77 and "no CUDA device" in out.stdout
+
+
+def test_soil_file_parser_matches_reference_loader(ref):
+    """include/soilmachine/soilfile.hpp (restatement of loadsoil, io.h:7-230, quirks included) against the
+    reference loader itself on every preset file, and against the committed JSON presets."""
+    import glob
+    from oracle import refapi
+    from soilmachine_b200 import capi, presets
+    files = sorted(glob.glob(os.path.join(os.path.dirname(refapi.soil_path("default")), "*.soil")))
+    assert len(files) == 11
+    for path in files:
+        name = os.path.basename(path)[:-5]
+        got = capi.parse_soil_file(path)
+        ref.init(path, seed=0, dimx=8, dimy=8, poolsize=1000)
+        rs, rl = ref.soils(), ref.layers()
+        assert got["soil_names"] == [s.decode() for s in rs["name"]], name
+        for k in got["soils"].dtype.names:
+            assert np.array_equal(got["soils"][k], rs[k]), (name, k)
+        assert np.array_equal(got["colors"], rs["color"]), name
+        for k in got["layers"].dtype.names:
+            assert np.array_equal(got["layers"][k], rl[k]), (name, k)
+        pre = presets.load(name)
+        assert got["world"] == pre["world"], name
+    with pytest.raises(capi.SoilMachineError):
+        capi.parse_soil_file("/nonexistent/file.soil")
