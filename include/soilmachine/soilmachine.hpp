@@ -75,17 +75,13 @@ inline std::vector<SurfParam>& soils_table() {
 }
 inline std::map<std::string, int>& soilmap_table() { static std::map<std::string, int> m{{"Air", 0}}; return m; }
 inline std::vector<SurfLayer>& layers_table() { static std::vector<SurfLayer> l; return l; }
-#define soils (::soilmachine::soils_table())
-#define soilmap (::soilmachine::soilmap_table())
-#define layers (::soilmachine::layers_table())
-
 // loadsoil(), io.h:7-230: fills the soils / soilmap / layers tables from a `.soil` file (same quirks as
 // upstream, see soilfile.hpp) and returns the WORLD block; an application that keeps the reference's global
 // ints assigns them from the result (SIZEX = w.sizex; ...).
 inline WorldEntry loadsoil(const std::string& file = "soil/default.soil") {
   SoilFile f;
   parse_soil_file(file, f);
-  soils.clear(); soilmap.clear(); layers.clear();
+  soils_table().clear(); soilmap_table().clear(); layers_table().clear();
   for (const SoilEntry& e : f.soils) {
     SurfParam p;
     p.name = e.name; p.density = e.density; p.porosity = e.porosity;
@@ -95,17 +91,21 @@ inline WorldEntry loadsoil(const std::string& file = "soil/default.soil") {
     p.erodes = (SurfType)e.erodes; p.erosionrate = e.erosionrate;
     p.cascades = (SurfType)e.cascades; p.maxdiff = e.maxdiff; p.settling = e.settling;
     p.abrades = (SurfType)e.abrades; p.suspension = e.suspension; p.abrasion = e.abrasion;
-    soils.push_back(p);
+    soils_table().push_back(p);
   }
-  for (const auto& kv : f.soilmap) soilmap[kv.first] = kv.second;
+  for (const auto& kv : f.soilmap) soilmap_table()[kv.first] = kv.second;
   for (const LayerEntry& l : f.layers) {
     SurfLayer L((SurfType)l.type);
     L.min = l.min; L.bias = l.bias; L.scale = l.scale; L.octaves = l.octaves; L.lacunarity = l.lacunarity;
     L.gain = l.gain; L.frequency = l.frequency;
-    layers.push_back(L);
+    layers_table().push_back(L);
   }
   return f.world;
 }
+
+#define soils (::soilmachine::soils_table())
+#define soilmap (::soilmachine::soilmap_table())
+#define layers (::soilmachine::layers_table())
 
 struct Error : std::runtime_error { int code; Error(int c, const std::string& m) : std::runtime_error(m), code(c) {} };
 
