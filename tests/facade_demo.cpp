@@ -9,8 +9,14 @@ using namespace soilmachine;
 int SIZEX = 128, SIZEY = 128, SCALE = 80, NWATER = 300, NWIND = 150, SEED = 42;
 struct DummyVertexpool {} vertexpool;
 
-int main() {
+int main(int argc, char** argv) {
   srand(SEED);                                               // SoilMachine.cpp:41
+  if (argc > 1) {                                            // loadsoil(parse::option["soil"]), SoilMachine.cpp:43-45
+    try {
+      WorldEntry w = loadsoil(argv[1]);
+      SCALE = w.scale;                                       // SIZEX/SIZEY stay small for the demo
+    } catch (const SoilFileError& e) { printf("%s\n", e.what()); return 2; }
+  } else {
   // what loadsoil("soil/rocksand.soil") leaves in the tables (io.h:7-230), abbreviated
   SurfParam rock; rock.name = "Rock"; rock.transports = rock.erodes = rock.cascades = rock.abrades = 1;
   rock.density = 0.95f; rock.solubility = 1.0f; rock.equrate = 0.1f; rock.friction = 0.15f; rock.maxdiff = 0.01f; rock.settling = 0.1f;
@@ -20,6 +26,7 @@ int main() {
   SurfLayer l0(1); l0.bias = 0.5f; l0.scale = 0.8f; l0.octaves = 8; l0.lacunarity = 2; l0.gain = 0.5f; l0.frequency = 1;
   SurfLayer l1(2); l1.bias = 0.0f; l1.scale = 0.4f; l1.octaves = 6; l1.lacunarity = 2; l1.gain = 0.4f; l1.frequency = 2;
   layers.push_back(l0); layers.push_back(l1);
+  }
   WaterParticle::init(); WindParticle::init();               // :47-48
   try {
     Layermap map(SEED, ivec2(SIZEX, SIZEY), vertexpool, SCALE);   // :83

@@ -214,6 +214,11 @@ def test_cpp_facade_frame_loop_runs():
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "frame 1:" in out.stdout and "legacy ops ok" in out.stdout
+    # the same loop with the tables coming from loadsoil() on a preset file
+    from oracle import refapi
+    out2 = subprocess.run([exe, refapi.soil_path("rocksand")], capture_output=True, text=True, timeout=300)
+    assert out2.returncode == 0, out2.stdout + out2.stderr
+    assert "frame 1:" in out2.stdout
 
 
 def test_batch_larger_than_resident_threads(ref):
