@@ -329,6 +329,7 @@ template <int DEPTH, class A> struct Cascade {
       if (transfer > tsize) transfer = (float)tsize;                // :87-88 (f64 -> f32 narrowing)
       bool recascade = false;
       changed = true;
+      a.note_transfer();
       a.focus(tx, ty);
       if (col_remove(a, *tr, (double)transfer) != 0) recascade = true;   // :90-91
       a.dirty_rec(tr, tx, ty);

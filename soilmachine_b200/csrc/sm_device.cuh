@@ -222,6 +222,7 @@ struct DevAccess {
   __device__ __forceinline__ void dirty_rec(Sec32*, int, int) {}
   __device__ __forceinline__ void cascade_prefetch(int, int) {}
   __device__ __forceinline__ void mark(int) {}
+  __device__ __forceinline__ void note_transfer() {}
   __device__ __forceinline__ void focus(int, int) {}
   __device__ __forceinline__ Sec32 pool_load(uint32_t i) { return c.pool[i]; }
   __device__ __forceinline__ void pool_store(uint32_t i, const Sec32& r) { c.pool[i] = r; }
@@ -292,8 +293,11 @@ struct WinAccess {
 #ifdef SM_PROFILE
   long long t_last = 0; unsigned long long t_mark[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   __device__ __forceinline__ void mark(int i) { long long t = clock64(); t_mark[i] += (unsigned long long)(t - t_last); t_last = t; }
+  unsigned int n_transfers = 0;
+  __device__ __forceinline__ void note_transfer() { n_transfers++; }
 #else
   __device__ __forceinline__ void mark(int) {}
+  __device__ __forceinline__ void note_transfer() {}
 #endif
   __device__ __forceinline__ WinAccess(const DevCtx& ctx, const SoilDev* ss, unsigned int ph, Sec32* w)
       : c(ctx), s_soils(ss), win(w), phase(ph & 1u), ax(0), ay(0), bx(0), by(0), valid(0), dirtym(0),

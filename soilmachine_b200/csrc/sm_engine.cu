@@ -344,7 +344,9 @@ __global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run(DevCtx c, int n,
 #ifdef SM_PROFILE
           { const unsigned long long dt_ = (unsigned long long)(clock64() - pt_);   // step duration (pt_ = after acquire)
             if (dt_ > 20000ull) atomicAdd(&ctl->marks[0], 1ull);
-            if (dt_ > 40000ull) atomicAdd(&ctl->marks[7], 1ull);
+            if (dt_ > 40000ull) { atomicAdd(&ctl->marks[7], 1ull); atomicAdd(&ctl->prof[13], (unsigned long long)a.n_transfers);
+                                  atomicAdd(&ctl->prof[14], dt_); }
+            atomicAdd(&ctl->prof[12], (unsigned long long)a.n_transfers);
             atomicMax(&ctl->prof[15], dt_); }
 #endif
           SM_PROF(4)   // step
@@ -2068,7 +2070,7 @@ int sm_debug_profile(sm_context* ctx, uint64_t* out16, int reset) {
   for (int i = 0; i < 16; i++) out16[i] = h.prof[i];
   for (int i = 1; i < 4; i++) out16[12 + i] = h.marks[i] + (i == 3 ? h.marks[4] + h.marks[5] + h.marks[6] : 0);
   out16[13] = h.marks[1]; out16[14] = h.marks[2]; out16[15] = h.marks[3] + h.marks[4] + h.marks[5] + h.marks[6];
-  if (reset == 2) { out16[13] = h.marks[0]; out16[14] = h.marks[7]; out16[15] = h.prof[15]; }
+  if (reset == 2) { out16[13] = h.marks[0]; out16[14] = h.marks[7]; out16[15] = h.prof[15]; out16[10] = h.prof[12]; out16[11] = h.prof[13]; out16[12] = h.prof[14]; }
   if (reset == 3) { out16[0] = h.ring[0].tail; out16[1] = h.ring[1].tail; out16[2] = h.ring[0].head; out16[3] = h.ring[1].head; out16[4] = h.bump; return SM_OK; }
   if (reset) { CK(cudaMemset(&ctx->d.ctl->prof[0], 0, sizeof(h.prof))); CK(cudaMemset(&ctx->d.ctl->marks[0], 0, sizeof(h.marks))); }
   return SM_OK;

@@ -142,6 +142,8 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "tail":
         sim.ctx.lib.sm_debug_profile(sim.ctx.h, out, 2)
         print("wind frame %d: steps=%d sweeps=%d ms=%.1f | steps>20k cycles: %d (%.2f/sweep), >40k: %d (%.2f/sweep), max step %d cycles; avg step %.0f cycles"
               % (f, g.steps, g.sweeps, g.device_ms, out[13], out[13] / g.sweeps, out[14], out[14] / g.sweeps, out[15], out[4] / max(g.steps, 1)), flush=True)
+        print("   transfers per step: %.3f overall; in the >40k-cycle steps: %.2f transfers, %.0f cycles on average"
+              % (out[10] / max(g.steps, 1), out[11] / max(out[14], 1), out[12] / max(out[14], 1)), flush=True)
 
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "poolrate":

@@ -34,6 +34,7 @@ struct HostAccess {
   void dirty_rec(Sec32*, int, int) {}
   void cascade_prefetch(int, int) {}
   void mark(int) {}
+  void note_transfer() {}
   void focus(int, int) {}
   Sec32 pool_load(uint32_t i) { return M.pool[i]; }
   void pool_store(uint32_t i, const Sec32& r) { M.pool[i] = r; }
