@@ -264,7 +264,7 @@ def main():
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     h2d = (W["nwater"] + W["nwind"]) * 8
-    d2h = 2 * 312                                  # two RunCtl read-backs per step
+    d2h = 2 * 424                                  # two RunCtl read-backs per step (sizeof(RunCtl) = 424)
 
     # max over ranks / sums over ranks
     ev_ms, e2e_ms, tot_steps, tot_e = aggregate(ev_ms, e2e_ms, steps_w + steps_d, e_steps, device="cuda")
