@@ -76,3 +76,29 @@ def test_port_matches_reference_live(port, ref, soil, dim, n):
     a, b = ref.wind_seq(0, xd), port.wind_seq(xd)
     assert a.steps == b.steps
     _golden.same_cols(ref.columns(), port.columns(), "columns (sequential)")
+
+
+def test_port_vs_reference_random_column_ops(port, ref):
+    """5000 random add / remove / cascade calls (incl. Air sections, zero and negative sizes, re-cascade
+    budgets 0..3, border cells) on a small map: the restatement must track the reference section by section."""
+    ref.init("rockgravelpebblessand", seed=2, dimx=12, dimy=10)
+    port.init(ref.dimx, ref.dimy, ref.scale, ref.soils())
+    port.set_columns(ref.columns())
+    rng = np.random.RandomState(11)
+    for i in range(5000):
+        x, y = int(rng.randint(0, 12)), int(rng.randint(0, 10))
+        k = rng.randint(0, 3)
+        if k == 0:
+            size = float(rng.choice([0.02, 0.0, -0.01, 0.3, 1e-9]) * rng.rand())
+            typ = int(rng.randint(0, 5))
+            ref.add(x, y, size, typ); port.add(x, y, size, typ)
+        elif k == 1:
+            h = float(rng.choice([0.02, 0.0, -0.5, 0.6, 1e-10]) * rng.rand())
+            a, b = ref.remove(x, y, h), port.remove(x, y, h)
+            assert np.float64(a).tobytes() == np.float64(b).tobytes(), i
+        else:
+            fx, fy, loop = float(rng.rand() * 11), float(rng.rand() * 9), int(rng.randint(0, 4))
+            ref.cascade(fx, fy, loop); port.cascade(fx, fy, loop)
+        if i % 500 == 499:
+            _golden.same_cols(ref.columns(), port.columns(), "columns after %d ops" % (i + 1))
+    _golden.same(ref.heights(), port.heights(), "heights")
