@@ -26,6 +26,11 @@
 #define SM_UNROLL1
 #endif
 
+#if defined(__CUDA_ARCH__)
+#define SM_FFS(x) __ffs((int)(x))
+#else
+#define SM_FFS(x) __builtin_ffs((int)(x))
+#endif
 #define SM_NIL 0xFFFFFFFFu
 #define SM_EMPTY 0xFFFFFFFFu   // Sec32::type of an empty column (dat[] == NULL, layermap.h:176)
 #define SM_AIR 0u              // soilmap["Air"] (surface.h:53-57)
@@ -301,12 +306,24 @@ template <int DEPTH, class A> struct Cascade {
 #pragma unroll
     for (int k = 0; k < 8; k++) order |= (unsigned int)k << (4 * rank[k]);
 
-    bool changed = false;
+    // Ranks still to be looked at, as a bit mask over the sorted order.  Until the first transfer only the
+    // neighbours the speculative pass found active matter; after a transfer every later rank is evaluated,
+    // exactly as the reference loop does.  Iterating over the set bits (instead of over all ranks with
+    // `continue`) keeps the trip count of a warp at the LARGEST per-lane count rather than at the union of
+    // the ranks any lane needs - the lanes of a warp carry different particles.
+    unsigned int todo = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int k = (int)((order >> (4 * i)) & 7u);
+      if (i < num && ((active >> k) & 1u)) todo |= 1u << i;
+    }
+    const unsigned int allranks = (num >= 8) ? 0xFFu : ((1u << num) - 1u);
     Sec32* const pc = a.rec(cx, cy);                // the centre record: one lookup for the whole loop
     SM_UNROLL1
-    for (int i = 0; i < num; i++) {
+    while (todo) {
+      const int i = SM_FFS(todo) - 1;
+      todo &= todo - 1u;
       const int k = (int)((order >> (4 * i)) & 7u);
-      if (!changed && !((active >> k) & 1u)) continue;
       const int kk = k + (k >= 4 ? 1 : 0);
       const int nx = cx + kk / 3 - 1, ny = cy + kk % 3 - 1;
       Sec32* const pn = a.rec(nx, ny);              // one lookup per neighbour and iteration
@@ -328,7 +345,7 @@ template <int DEPTH, class A> struct Cascade {
       double tsize = (tr->type == SM_EMPTY) ? 0.0 : tr->size;
       if (transfer > tsize) transfer = (float)tsize;                // :87-88 (f64 -> f32 narrowing)
       bool recascade = false;
-      changed = true;
+      todo |= allranks & ~((2u << i) - 1u);          // from now on every later rank is evaluated
       a.note_transfer();
       a.focus(tx, ty);
       if (col_remove(a, *tr, (double)transfer) != 0) recascade = true;   // :90-91
