@@ -24,6 +24,14 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class Hydro(C.Structure):
+    _fields_ = [("floods", C.c_int64), ("nested", C.c_int64), ("nested_steps", C.c_int64),
+                ("transfers", C.c_int64), ("cells", C.c_int64)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 def build():
     src = [os.path.join(HERE, "sm_oracle.cpp"), os.path.join(HERE, "sm_oracle.h")]
     if (not os.path.exists(LIB_PATH)) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(s) for s in src):
@@ -137,6 +145,22 @@ class Port:
 
     def water_seq(self, xy):
         return self._run(self.lib.smo_water_seq, xy)
+
+    def water_seq_full(self, xy, flood=True, seep=True):
+        xy = np.ascontiguousarray(xy, np.float32)
+        st, hy = Stats(), Hydro()
+        self.lib.smo_water_seq_full(len(xy), _p(xy, C.c_float), int(flood) | (int(seep) << 1), C.byref(st), C.byref(hy))
+        return st, hy
+
+    def water_flood(self):
+        hy = Hydro()
+        self.lib.smo_water_flood(C.byref(hy))
+        return hy
+
+    def seep(self):
+        hy = Hydro()
+        self.lib.smo_seep(C.byref(hy))
+        return hy
 
     def wind_seq(self, xy):
         return self._run(self.lib.smo_wind_seq, xy)

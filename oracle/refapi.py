@@ -212,6 +212,15 @@ class Ref:
         self.lib.smref_water_run(len(xy), _p(xy, C.c_float), int(max_sweeps), C.byref(st))
         return st
 
+    def water_flood(self):
+        """flood() for every finished particle of the last water batch, ascending index; returns the count."""
+        self.lib.smref_water_flood.restype = C.c_int64
+        return int(self.lib.smref_water_flood())
+
+    def seep(self):
+        """WaterParticle::seep(map, vertexpool): the per-frame full-grid pass."""
+        self.lib.smref_seep()
+
     def wind_begin(self, xy):
         xy = np.ascontiguousarray(xy, np.float32)
         self._nd = len(xy)

@@ -355,6 +355,26 @@ void smref_water_run(int n, const float* xy, int max_sweeps, Stats* st) {
   st->seconds = now() - t0;
 }
 
+// ---- pooling hydrology after a lockstep batch ----------------------------
+// Every particle of the finished water batch that is no longer live gets its flood() call
+// (water.h:123-145), in ascending particle index.  A flood is atomic: the nested particles
+// WaterParticle::cascade (water.h:151-283) spawns run to completion inside it, as upstream.  flood()
+// itself decides who floods (volume >= minvol and spill left).  Returns how many did.
+int64_t smref_water_flood(void) {
+  vector<char> live(g.water.size(), 0);
+  for (int i : g.water_live) live[i] = 1;
+  int64_t floods = 0;
+  for (size_t i = 0; i < g.water.size(); i++) {
+    if (live[i]) continue;
+    WaterParticle& p = *g.water[i];
+    if (!(p.volume < p.minvol) && p.spill > 0) floods++;
+    p.flood(*g.lmap, *g.vp);
+  }
+  return floods;
+}
+// the per-frame full-grid pass WaterParticle::seep(map, vertexpool), water.h:335-343 / SoilMachine.cpp:300-301
+void smref_seep(void) { WaterParticle::seep(*g.lmap, *g.vp); }
+
 // ---- LOCKSTEP wind ----------------------------------------------------------------------------------
 void smref_wind_begin(int n, const float* xy) {
   g.wind.clear(); g.wind_live.clear();

@@ -167,6 +167,7 @@ struct Water {
   int ix = 0, iy = 0;
   smo_soil param;
   int surf = 0, contains = 0;
+  int spill = 3;                                             // water.h:33
 };
 void water_spawn(Water& p, float x, float y) {               // ctor, water.h:11-19
   p.pos = {x, y};
@@ -223,6 +224,112 @@ bool water_interact(Water& p) {                              // water.h:75-121
   if (p.sediment > 1.0) p.sediment = 1.0;
   p.volume *= (1.0 - p.evaprate);
   return p.volume > 0.01;
+}
+
+// ---- pooling hydrology, water.h:123-343 ---------------------------------
+const double volumeFactor = 0.015;                           // water.h:368
+smo_hydro H;                                                 // counters of the current hydrology call
+void water_cascade(int ix, int iy, int spill);
+
+void water_seep(int x, int y) {                              // WaterParticle::seep(vec2,...), water.h:285-333
+  Column& c = at(x, y);
+  if (c.empty()) return;
+  // `top` walks down the column; sections are named by their index from the bottom, which a pop of the
+  // column's top (map.remove acts on dat[], not on `top`) leaves valid for everything underneath.
+  for (int t = (int)c.size() - 1; t >= 1; t--) {
+    const smo_soil param = W.soils[c[t].type], nparam = W.soils[c[t - 1].type];
+    const double vol = c[t].size * c[t].saturation * param.porosity;
+    const double nevol = c[t - 1].size * (1.0 - c[t - 1].saturation) * nparam.porosity;
+    double seepage = 1.0;
+    const double transfer = (vol < nevol) ? vol : nevol;
+    if (transfer < 1E-6) seepage = 1.0;
+    if (transfer > 0) {
+      if (c[t].type == AIR) remove(x, y, seepage * transfer);
+      else c[t].saturation -= (seepage * transfer) / (c[t].size * param.porosity);
+      c[t - 1].saturation += (seepage * transfer) / (c[t - 1].size * nparam.porosity);
+    }
+  }
+}
+
+bool water_flood(Water& p) {                                 // WaterParticle::flood, water.h:123-145
+  if (p.volume < 0.01 || p.spill-- <= 0) return false;
+  H.floods++;
+  p.ix = (int)p.pos.x; p.iy = (int)p.pos.y;                  // ipos = pos truncates (:128)
+  add(p.ix, p.iy, p.sediment * W.soils[p.contains].equrate, p.contains);
+  cascade(p.pos, 0);
+  add(p.ix, p.iy, p.volume * volumeFactor, AIR);
+  water_seep(p.ix, p.iy);
+  water_cascade(p.ix, p.iy, p.spill);
+  return false;
+}
+
+void water_to_completion(Water& p, int64_t* steps) {         // SoilMachine.cpp:292-296 / water.h:252-256
+  for (;;) {
+    while (water_move(p)) {
+      ++*steps;
+      if (!water_interact(p)) break;
+    }
+    if (!water_flood(p)) break;
+  }
+}
+
+void water_cascade(int ix, int iy, int spill) {              // WaterParticle::cascade, water.h:151-283
+  static const int nx8[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
+  static const int ny8[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
+  struct Point { int x, y; double h; } sn[8];
+  int num = 0;
+  for (int k = 0; k < 8; k++) {
+    const int nx = ix + nx8[k], ny = iy + ny8[k];
+    if (nx >= W.dimx || ny >= W.dimy || nx < 0 || ny < 0) continue;
+    sn[num++] = {nx, ny, height(nx, ny)};
+  }
+  for (int i = 1; i < num; i++) {                            // std::sort on <= 8 elements, highest first
+    Point v = sn[i];
+    int j = i;
+    while (j > 0 && v.h > sn[j - 1].h) { sn[j] = sn[j - 1]; j--; }
+    sn[j] = v;
+  }
+  for (int i = 0; i < num; i++) {
+    const int nx = sn[i].x, ny = sn[i].y;
+    const Column& A = at(ix, iy);
+    const Column& B = at(nx, ny);
+    double whA = 0, whB = 0, fA = 0.0, fB = 0.0;             // water table = top of the column (:183-203)
+    if (!A.empty()) { whA = A.back().size; fA = A.back().floor; }
+    if (!B.empty()) { whB = B.back().size; fB = B.back().floor; }
+    const double diff = (fA + whA - fB - whB) * (double)W.SCALE / 80.0;
+    if (diff == 0) continue;
+    const int tx = (diff > 0) ? ix : nx, ty = (diff > 0) ? iy : ny;
+    const int bx = (diff > 0) ? nx : ix, by = (diff > 0) ? ny : iy;
+    const Column& top = at(tx, ty);
+    if (top.empty() || top.back().type != AIR) continue;     // only water moves (:218-219)
+    double transfer = std::fabs(diff) / 2.0;
+    const double wh = top.back().size;
+    transfer = (wh < transfer) ? wh : transfer;
+    if (transfer <= 0) continue;
+    bool recascade = false;
+    if (transfer == wh) {                                    // the whole water section leaves as a particle
+      remove(tx, ty, transfer);
+      Water q;
+      // the ctor draws a random position only to read `contains` there (water.h:13-17); that value is
+      // overwritten by the first erosion before it can reach the map (deposits need sediment > 0)
+      water_spawn(q, (float)tx, (float)ty);
+      const V2 d = {(float)bx - (float)tx, (float)by - (float)ty};
+      const float inv = 1.0f / std::sqrt(d.x * d.x + d.y * d.y);
+      const float r2 = std::sqrt(2.0f);
+      q.speed = {r2 * (d.x * inv), r2 * (d.y * inv)};
+      q.spill = spill;
+      q.volume = transfer / volumeFactor;
+      H.nested++;
+      water_to_completion(q, &H.nested_steps);
+    } else {
+      if (remove(tx, ty, transfer) != 0) recascade = true;
+      if (transfer > 0) recascade = true;
+      add(bx, by, transfer, AIR);
+      at(bx, by).back().saturation = 1.0f;
+      H.transfers++;
+    }
+    if (recascade && spill > 0) water_cascade(nx, ny, --spill);
+  }
 }
 
 // ---- WindParticle, wind.h ----------------------------------------------------------------------------------
@@ -371,6 +478,24 @@ void smo_water_run(int n, const float* xy, int max_sweeps, smo_stats* st) {
   while (!Wlive.empty() && (max_sweeps <= 0 || st->sweeps < max_sweeps)) smo_water_sweep(st);
   st->seconds = now() - t0;
 }
+// floods of the finished lockstep batch, ascending particle index (see oracle/refharness: smref_water_flood)
+void smo_water_flood(smo_hydro* out) {
+  H = smo_hydro();
+  std::vector<char> live(WP.size(), 0);
+  for (int i : Wlive) live[i] = 1;
+  for (size_t i = 0; i < WP.size(); i++) if (!live[i]) water_flood(WP[i]);
+  if (out) *out = H;
+}
+// WaterParticle::seep(map, vertexpool), water.h:335-343 / SoilMachine.cpp:300-301
+void smo_seep(smo_hydro* out) {
+  H = smo_hydro();
+  for (int x = 0; x < W.dimx; x++) for (int y = 0; y < W.dimy; y++) {
+    water_seep(x, y);
+    water_cascade(x, y, 3);
+    H.cells++;
+  }
+  if (out) *out = H;
+}
 void smo_wind_begin(int n, const float* xy) {
   DP.assign(n, Wind()); Dlive.clear();
   for (int i = 0; i < n; i++) { wind_spawn(DP[i], xy[2 * i], xy[2 * i + 1]); Dlive.push_back(i); }
@@ -415,6 +540,28 @@ void smo_water_seq(int n, const float* xy, smo_stats* st) {  // SoilMachine.cpp:
     }
   }
   st->seconds = now() - t0;
+}
+// the full water part of the reference frame: flags bit0 = flood (SoilMachine.cpp:292-296), bit1 = seep pass (:300-301)
+void smo_water_seq_full(int n, const float* xy, int flags, smo_stats* st, smo_hydro* out) {
+  memset(st, 0, sizeof(*st));
+  H = smo_hydro();
+  const double t0 = now();
+  for (int i = 0; i < n; i++) {
+    Water p;
+    water_spawn(p, xy[2 * i], xy[2 * i + 1]);
+    for (;;) {
+      for (;;) {
+        if (!water_move(p)) { if (p.volume == 0.0) st->exit_oob++; else st->exit_stall++; break; }
+        st->steps++;
+        if (!water_interact(p)) { st->exit_evap++; break; }
+      }
+      if (!(flags & 1)) break;
+      if (!water_flood(p)) break;
+    }
+  }
+  st->seconds = now() - t0;
+  if (flags & 2) for (int x = 0; x < W.dimx; x++) for (int y = 0; y < W.dimy; y++) { water_seep(x, y); water_cascade(x, y, 3); H.cells++; }
+  if (out) *out = H;
 }
 void smo_wind_seq(int n, const float* xy, smo_stats* st) {   // SoilMachine.cpp:304-307
   memset(st, 0, sizeof(*st));

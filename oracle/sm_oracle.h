@@ -27,6 +27,14 @@ typedef struct smo_stats {
   double seconds;
 } smo_stats;
 
+typedef struct smo_hydro {   /* counters of one hydrology call (flood phase or seep pass) */
+  int64_t floods;        /* flood() calls that passed the volume/spill guard, nested particles included */
+  int64_t nested;        /* particles spawned by the water-table cascade (water.h:243-256) */
+  int64_t nested_steps;  /* their particle-steps */
+  int64_t transfers;     /* partial water-table transfers (water.h:260-272) */
+  int64_t cells;         /* seep pass: cells visited */
+} smo_hydro;
+
 void smo_init(int dimx, int dimy, int scale, int nsoils, const smo_soil* soils);
 void smo_set_columns(const int64_t* offsets, const int32_t* type, const double* size, const double* saturation);
 int64_t smo_nsections(void);
@@ -49,12 +57,18 @@ void smo_water_begin(int n, const float* xy);
 int smo_water_sweep(smo_stats* st);
 void smo_water_state(float* pos2, float* speed2, double* volume, double* sediment, int32_t* contains, int32_t* alive);
 void smo_water_run(int n, const float* xy, int max_sweeps, smo_stats* st);
+/* pooling hydrology: flood() of every finished particle of the last lockstep
+ * water batch in ascending index, each flood atomic (water.h:123-145); the per-frame full-grid seep pass
+ * (water.h:335-343) */
+void smo_water_flood(smo_hydro* out);
+void smo_seep(smo_hydro* out);
 void smo_wind_begin(int n, const float* xy);
 int smo_wind_sweep(smo_stats* st);
 void smo_wind_state(float* pos2, float* speed3, double* height, double* sediment, int32_t* contains, int32_t* alive);
 void smo_wind_run(int n, const float* xy, int max_sweeps, smo_stats* st);
 /* sequential: each particle runs to completion before the next is spawned (SoilMachine.cpp:288-307) */
 void smo_water_seq(int n, const float* xy, smo_stats* st);
+void smo_water_seq_full(int n, const float* xy, int flags, smo_stats* st, smo_hydro* out);
 void smo_wind_seq(int n, const float* xy, smo_stats* st);
 
 #ifdef __cplusplus

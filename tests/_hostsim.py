@@ -10,6 +10,7 @@ SRC = os.path.join(HERE, "hostsim", "hostsim.cpp")
 LIB = os.path.join(HERE, "hostsim", "libhostsim.so")
 CORE = os.path.join(HERE, "..", "soilmachine_b200", "csrc", "sm_core.cuh")
 NOISE = os.path.join(HERE, "..", "soilmachine_b200", "csrc", "sm_noise.cuh")
+HYDRO = os.path.join(HERE, "..", "soilmachine_b200", "csrc", "sm_hydro.cuh")
 
 SOILDEV = np.dtype([("friction", "<f4"), ("solubility", "<f4"), ("equrate", "<f4"), ("erosionrate", "<f4"),
                     ("maxdiff", "<f4"), ("settling", "<f4"), ("suspension", "<f4"), ("porosity", "<f4"),
@@ -21,8 +22,16 @@ class Stats(C.Structure):
                 ("exit_evap", C.c_int64), ("exit_stall", C.c_int64), ("seconds", C.c_double)]
 
 
+class HydroCount(C.Structure):
+    _fields_ = [("floods", C.c_uint64), ("nested", C.c_uint64), ("nested_steps", C.c_uint64),
+                ("transfers", C.c_uint64), ("cells", C.c_uint64), ("overflow", C.c_uint64)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 def build():
-    if (not os.path.exists(LIB)) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(CORE), os.path.getmtime(NOISE)):
+    if (not os.path.exists(LIB)) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(CORE), os.path.getmtime(NOISE), os.path.getmtime(HYDRO)):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", SRC, "-o", LIB])
     return LIB
 
@@ -109,6 +118,30 @@ class HostSim:
         self.lib.hs_water_state(_p(pos, C.c_float), _p(speed, C.c_float), _p(vol, C.c_double),
                                 _p(sed, C.c_double), _p(cont, C.c_int32), _p(alive, C.c_int32))
         return {"pos": pos, "speed": speed, "volume": vol, "sediment": sed, "contains": cont, "alive": alive}
+
+    def water_run(self, xy):
+        self.water_begin(xy)
+        st = Stats()
+        while self.water_sweep(st) > 0:
+            pass
+        return st
+
+    def water_flood(self):
+        hc = HydroCount()
+        self.lib.hs_water_flood(C.byref(hc))
+        return hc
+
+    def seep(self, mode=1):
+        hc = HydroCount()
+        self.lib.hs_seep(int(mode), C.byref(hc))
+        return hc
+
+    def frequency_update(self):
+        f = self.frequency()
+        lrate, K = np.float32(0.01), np.float32(50.0)
+        t = f["water_track"]
+        wf = (np.float32(1.0) - lrate) * f["water_frequency"] + lrate * K * t / (np.float32(1.0) + K * t)
+        self.set_frequency(water_frequency=wf.astype(np.float32), water_track=np.zeros_like(t))
 
     def wind_begin(self, xy):
         xy = np.ascontiguousarray(xy, np.float32); self._n = len(xy)

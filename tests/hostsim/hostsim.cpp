@@ -8,6 +8,7 @@
 #include <cstdio>
 #include "../../soilmachine_b200/csrc/sm_core.cuh"
 #include "../../soilmachine_b200/csrc/sm_noise.cuh"
+#include "../../soilmachine_b200/csrc/sm_hydro.cuh"
 
 namespace {
 struct HostMap {
@@ -18,6 +19,7 @@ struct HostMap {
   std::vector<float> wfreq, wtrack, windfreq;
   int64_t drops = 0;
 } M;
+ActiveMap* G_act = nullptr;   // seep pass with the active-cell index: cells the executor makes wet are flagged
 
 struct HostAccess {
   int dimx() const { return M.dimx; }
@@ -30,8 +32,9 @@ struct HostAccess {
   void query(int x, int y, double& h, uint32_t& t) { const Sec32* r = rec(x, y); h = rec_height(*r); t = rec_surface(*r); }
   void begin(int, int) {}
   void target(int, int) {}
-  void dirty(int, int) {}
-  void dirty_rec(Sec32*, int, int) {}
+  void dirty(int x, int y) { dirty_rec(rec(x, y), x, y); }
+  void dirty_rec(Sec32* r, int x, int y) { if (G_act && r->type == SM_AIR) active_mark_block(*G_act, x, y, M.dimx, M.dimy); }
+  void wet_mark(int x, int y) { if (G_act) active_set(*G_act, (unsigned long long)x * M.dimy + y); }
   void cascade_prefetch(int, int) {}
   void mark(int) {}
   void note_transfer() {}
@@ -173,5 +176,41 @@ void hs_wind_state(float* pos, float* speed3, double* h, double* sed, int32_t* c
     h[i] = D[i].height; sed[i] = D[i].sediment; cont[i] = (int32_t)D[i].contains; alive[i] = 0;
   }
   for (int i : Dlive) alive[i] = 1;
+}
+
+// ---- pooling hydrology (sm_hydro.cuh) ------------------------------------------------------------
+void hs_water_flood(HydroCount* out) {
+  HostAccess a; HydroCount hc{};
+  std::vector<char> live(W.size(), 0);
+  for (int i : Wlive) live[i] = 1;
+  for (size_t i = 0; i < W.size(); i++) if (!live[i]) hydro_flood_particle(a, W[i], hc);
+  if (out) *out = hc;
+}
+// mode 0: visit every cell in x-major order, as upstream; mode 1: classify + visit the flagged cells only,
+// the way the device pass does
+void hs_seep(int mode, HydroCount* out) {
+  HostAccess a; HydroCount hc{};
+  if (mode == 0) {
+    for (int x = 0; x < M.dimx; x++) for (int y = 0; y < M.dimy; y++) hydro_seep_visit(a, x, y, hc);
+  } else {
+    ActiveMap am{};
+    const unsigned long long cells = (unsigned long long)M.dimx * M.dimy;
+    unsigned long long total = active_layout(cells, am.nwords, &am.nlevels);
+    std::vector<unsigned long long> store(total, 0ull);
+    unsigned long long off = 0;
+    for (int l = 0; l < am.nlevels; l++) { am.lvl[l] = store.data() + off; off += am.nwords[l]; }
+    am.ncells = cells;
+    for (int x = 0; x < M.dimx; x++) for (int y = 0; y < M.dimy; y++) {
+      bool airtop, holds;
+      hydro_classify(a, x, y, airtop, holds);
+      if (airtop) active_mark_block(am, x, y, M.dimx, M.dimy);
+      if (holds) active_set(am, (unsigned long long)x * M.dimy + y);
+    }
+    G_act = &am;
+    for (unsigned long long c = active_next(am, 0); c < cells; c = active_next(am, c + 1))
+      hydro_seep_visit(a, (int)(c / M.dimy), (int)(c % M.dimy), hc);
+    G_act = nullptr;
+  }
+  if (out) *out = hc;
 }
 }
