@@ -157,7 +157,7 @@ int sm_height_bilinear(sm_context* ctx, float x, float y, double* height); /* la
 /* ---- the hot path --------------------------------------------------------------------------- */
 /* One batch of n particles run to completion in lockstep sweeps: in every sweep each live particle,
  * in ascending index order, executes move() && interact().  Replaces the loop
- * SoilMachine.cpp:288-298 (water, flood excluded) / 304-307 (wind).  spawn_xy = n (x,y) pairs,
+ * SoilMachine.cpp:288-298 (water; the flood tail is sm_water_flood) / 304-307 (wind).  spawn_xy = n (x,y) pairs,
  * the positions the ctor draws (water.h:13, wind.h:15).  max_sweeps <= 0: until all are dead. */
 int sm_water_run(sm_context* ctx, int32_t n, const float* spawn_xy, int32_t max_sweeps, sm_stats* stats);
 int sm_wind_run(sm_context* ctx, int32_t n, const float* spawn_xy, int32_t max_sweeps, sm_stats* stats);
@@ -177,6 +177,23 @@ int sm_wind_begin(sm_context* ctx, int32_t n, const float* spawn_xy);
 int sm_wind_sweeps(sm_context* ctx, int32_t k, sm_stats* stats);
 int sm_wind_state(sm_context* ctx, float* pos2, float* speed3, double* height, double* sediment,
                   int32_t* contains, int32_t* alive);
+
+/* ---- pooling hydrology (the rest of the water part of the frame, SoilMachine.cpp:292-301) --------- */
+typedef struct sm_hydro_stats {
+  int64_t floods;        /* flood() calls that passed the volume/spill guard (water.h:125), nested ones included */
+  int64_t nested;        /* particles spawned by the water-table cascade (water.h:243-256) */
+  int64_t nested_steps;  /* their particle-steps */
+  int64_t transfers;     /* partial water-table transfers (water.h:260-272) */
+  int64_t cells;         /* sm_seep: cells visited (the cells where a visit can change anything) */
+  double device_ms;      /* CUDA-event time of the call's kernels */
+} sm_hydro_stats;
+/* WaterParticle::flood (water.h:123-145) for every finished particle of the last water batch, in
+ * ascending particle index; each flood is atomic, i.e. the water-table cascade (water.h:151-283) and the
+ * particles it spawns run to completion inside it exactly as upstream.  Call after sm_water_run. */
+int sm_water_flood(sm_context* ctx, sm_hydro_stats* stats);
+/* WaterParticle::seep(map, vertexpool) (water.h:335-343): the per-frame pass over all cells in x-major
+ * order, seep(cell) then the water-table cascade with spill 3. */
+int sm_seep(sm_context* ctx, sm_hydro_stats* stats);
 
 /* CUDA-event stopwatch on the context's stream (the stream every kernel of this context is
  * launched on): start records an event, stop records another, synchronises and returns the elapsed

@@ -36,7 +36,7 @@ SYMBOLS = [
     "sm_wind_sweeps", "sm_wind_state", "sm_launch_count", "sm_device_alloc", "sm_device_free",
     "sm_device_upload", "sm_timer_start", "sm_timer_stop", "sm_set_soil_colors", "sm_mesh_update",
     "sm_mesh_device_ptr", "sm_export_height", "sm_export_color", "sm_create_sharded", "sm_shard_range",
-    "sm_peer_export", "sm_peer_attach", "sm_parse_soil_file",
+    "sm_peer_export", "sm_peer_attach", "sm_parse_soil_file", "sm_water_flood", "sm_seep",
 ]
 
 
@@ -49,6 +49,14 @@ class Stats(C.Structure):
     _fields_ = [("steps", C.c_int64), ("sweeps", C.c_int64), ("exit_oob", C.c_int64),
                 ("exit_evap", C.c_int64), ("exit_stall", C.c_int64), ("pool_drops", C.c_int64),
                 ("alive", C.c_int64), ("device_ms", C.c_double)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class HydroStats(C.Structure):
+    _fields_ = [("floods", C.c_int64), ("nested", C.c_int64), ("nested_steps", C.c_int64),
+                ("transfers", C.c_int64), ("cells", C.c_int64), ("device_ms", C.c_double)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -283,6 +291,18 @@ class Context:
     def wind_run(self, xy, max_sweeps=0):
         self._n["wind"] = len(xy)
         return self._run(self.lib.sm_wind_run, xy, max_sweeps)
+
+    def water_flood(self):
+        """flood() of every finished particle of the last water batch (water.h:123-145), ascending index."""
+        st = HydroStats()
+        self._ck(self.lib.sm_water_flood(self.h, C.byref(st)))
+        return st
+
+    def seep(self):
+        """The per-frame full-grid pass WaterParticle::seep(map, vertexpool) (water.h:335-343)."""
+        st = HydroStats()
+        self._ck(self.lib.sm_seep(self.h, C.byref(st)))
+        return st
 
     def water_begin(self, xy):
         xy = np.ascontiguousarray(xy, np.float32)

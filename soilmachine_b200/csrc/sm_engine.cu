@@ -17,6 +17,7 @@
 #include "../../include/soilmachine/soilfile.hpp"
 #include "sm_device.cuh"
 #include "sm_noise.cuh"
+#include "sm_hydro.cuh"
 
 #define KIND_WATER 0
 #define KIND_WIND 1
@@ -1225,6 +1226,159 @@ __global__ void k_cell_op(DevCtx c, CellOp o, CellRes* res) {
   *res = r;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// pooling hydrology (sm_hydro.cuh): flood phase and the per-frame seep pass
+// ---------------------------------------------------------------------------------------------
+// Both are sequential by definition: the flood of particle i sees the map the floods of all
+// lower-indexed particles left behind, nested particles included (water.h:123-145,252-256), and the seep
+// pass visits the cells in x-major order with the same nesting (water.h:335-343).  One thread executes them;
+// what the device adds is (a) a full-grid classification that reduces the 16.8 M-cell scan of the seep pass
+// to the few cells where water is, and (b) a software-managed record cache in shared memory, because the
+// executor works on a handful of neighbouring cells over and over and a shared-memory hit costs a tenth of
+// an L2 round trip.
+//
+// The cache is direct-mapped on (x mod 64, y mod 64): all cells of any 64 x 64 window have distinct lines,
+// and the core never holds record pointers that are further apart than one particle step (a few cells), so
+// a pointer handed out by rec() cannot be evicted while it is in use.  Lines are written back when they are
+// replaced and when the kernel ends.  Buried sections (pool) and the frequency maps are accessed in place.
+#define SM_HC_EDGE 64
+#define SM_HC_LINES (SM_HC_EDGE * SM_HC_EDGE)
+#define SM_HC_BYTES (SM_HC_LINES * (int)sizeof(Sec32) + SM_HC_LINES * 4)
+
+struct HydroAccess : DevAccess {
+  Sec32* s_rec;          // SM_HC_LINES records
+  uint32_t* s_tag;       // cell index held by each line, SM_NIL = none
+  ActiveMap act;
+  bool marking;
+  __device__ __forceinline__ HydroAccess(const DevCtx& ctx, const SoilDev* ss, Sec32* sr, uint32_t* st, const ActiveMap& am, bool mk)
+      : DevAccess(ctx, ss, 0u), s_rec(sr), s_tag(st), act(am), marking(mk) {}
+  __device__ __forceinline__ Sec32* rec(int x, int y) {
+    const uint32_t cell = (uint32_t)x * (uint32_t)c.dimy + (uint32_t)y;
+    const int line = (x & (SM_HC_EDGE - 1)) * SM_HC_EDGE + (y & (SM_HC_EDGE - 1));
+    const uint32_t held = s_tag[line];
+    if (held != cell) {
+      if (held != SM_NIL) c.top[held] = s_rec[line];
+      s_rec[line] = c.top[cell];
+      s_tag[line] = cell;
+    }
+    return &s_rec[line];
+  }
+  __device__ __forceinline__ double height(int x, int y) { return rec_height(*rec(x, y)); }
+  __device__ __forceinline__ uint32_t surface_of(int x, int y) { return rec_surface(*rec(x, y)); }
+  __device__ __forceinline__ void query(int x, int y, double& h, uint32_t& t) { const Sec32* r = rec(x, y); h = rec_height(*r); t = rec_surface(*r); }
+  __device__ __forceinline__ void dirty_rec(Sec32* r, int x, int y) {
+    if (marking && r->type == SM_AIR) active_mark_block(act, x, y, c.dimx, c.dimy);
+  }
+  __device__ __forceinline__ void dirty(int x, int y) { dirty_rec(rec(x, y), x, y); }
+  __device__ __forceinline__ void wet_mark(int x, int y) {
+    if (marking) active_set(act, (unsigned long long)x * c.dimy + y);
+  }
+  __device__ void flush() {
+    for (int line = 0; line < SM_HC_LINES; line++) {
+      const uint32_t held = s_tag[line];
+      if (held != SM_NIL) c.top[held] = s_rec[line];
+    }
+  }
+};
+
+__device__ __forceinline__ void hydro_smem_init(unsigned char* smem, Sec32*& s_rec, uint32_t*& s_tag, SoilDev* s_soils, const DevCtx& c) {
+  s_rec = reinterpret_cast<Sec32*>(smem);
+  s_tag = reinterpret_cast<uint32_t*>(smem + SM_HC_LINES * sizeof(Sec32));
+  for (int i = threadIdx.x; i < SM_HC_LINES; i += blockDim.x) s_tag[i] = SM_NIL;
+  for (int i = threadIdx.x; i < c.nsoils; i += blockDim.x) s_soils[i] = c.soils[i];
+  __syncthreads();
+}
+__device__ __forceinline__ void hydro_count_out(HydroCount* out, const HydroCount& hc) {
+  out->floods = hc.floods; out->nested = hc.nested; out->nested_steps = hc.nested_steps;
+  out->transfers = hc.transfers; out->cells = hc.cells; out->overflow = hc.overflow;
+}
+
+// flood() of every finished particle of the last water batch, ascending index (SoilMachine.cpp:292-296).
+// The warp scans the batch 32 particles at a time; lane 0 executes the floods the ballot found.
+__global__ void __launch_bounds__(32) k_hydro_flood(DevCtx c, int n, HydroCount* out) {
+  extern __shared__ __align__(32) unsigned char hy_smem[];
+  __shared__ SoilDev s_soils[SM_MAX_SOILS];
+  Sec32* s_rec; uint32_t* s_tag;
+  hydro_smem_init(hy_smem, s_rec, s_tag, s_soils, c);
+  ActiveMap none{};
+  HydroAccess a(c, s_soils, s_rec, s_tag, none, false);
+  HydroCount hc{};
+  const int lane = threadIdx.x;
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    bool cand = false;
+    if (i < n) cand = (c.alive[i] == 0) && !(c.pb[i].x < SM_MINVOL);
+    unsigned int m = __ballot_sync(0xFFFFFFFFu, cand);
+    if (lane == 0) {
+      while (m) {
+        const int j = base + __ffs((int)m) - 1;
+        m &= m - 1u;
+        const float4 pa = c.pa[j];
+        const double2 pb = c.pb[j];
+        WaterP p;
+        p.px = pa.x; p.py = pa.y; p.sx = pa.z; p.sy = pa.w;
+        p.volume = pb.x; p.sediment = pb.y; p.contains = c.pc[j].x;
+        hydro_flood_particle(a, p, hc);
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) { a.flush(); hydro_count_out(out, hc); }
+}
+
+// full-grid classification for the seep pass: flag the cells whose visit can change anything
+__device__ __forceinline__ void active_set_atomic(const ActiveMap& m, unsigned long long idx) {
+  for (int l = 0; l < m.nlevels; l++) {
+    const unsigned long long w = idx >> 6, b = 1ull << (idx & 63);
+    const unsigned long long old = atomicOr(&m.lvl[l][w], b);
+    if (old) return;                 // bit already set, or the word already announced one level up
+    idx = w;
+  }
+}
+__global__ void __launch_bounds__(256) k_hydro_classify(DevCtx c, ActiveMap am) {
+  const unsigned long long cells = am.ncells;
+  for (unsigned long long cell = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; cell < cells;
+       cell += (unsigned long long)gridDim.x * blockDim.x) {
+    const Sec32 r = c.top[cell];
+    if (r.type == SM_EMPTY) continue;
+    const int x = (int)(cell / (unsigned long long)c.dimy), y = (int)(cell % (unsigned long long)c.dimy);
+    if (r.type == SM_AIR) {
+      for (int dx = -1; dx <= 1; dx++) {
+        const int xx = x + dx;
+        if (xx < 0 || xx >= c.dimx) continue;
+        for (int dy = -1; dy <= 1; dy++) {
+          const int yy = y + dy;
+          if (yy < 0 || yy >= c.dimy) continue;
+          active_set_atomic(am, (unsigned long long)xx * c.dimy + yy);
+        }
+      }
+    }
+    bool holds = (r.saturation != 0.0);
+    for (uint32_t b = r.below; !holds && b != SM_NIL;) {
+      const Sec32 s = c.pool[b];
+      holds = (s.saturation != 0.0);
+      b = s.below;
+    }
+    if (holds) active_set_atomic(am, cell);
+  }
+}
+// WaterParticle::seep(map, vertexpool), water.h:335-343, over the flagged cells in x-major order
+__global__ void __launch_bounds__(32) k_hydro_seep(DevCtx c, ActiveMap am, HydroCount* out) {
+  extern __shared__ __align__(32) unsigned char hy_smem[];
+  __shared__ SoilDev s_soils[SM_MAX_SOILS];
+  Sec32* s_rec; uint32_t* s_tag;
+  hydro_smem_init(hy_smem, s_rec, s_tag, s_soils, c);
+  if (threadIdx.x != 0) return;
+  HydroAccess a(c, s_soils, s_rec, s_tag, am, true);
+  HydroCount hc{};
+  const unsigned long long cells = am.ncells;
+  for (unsigned long long cell = active_next(am, 0); cell < cells; cell = active_next(am, cell + 1))
+    hydro_seep_visit(a, (int)(cell / (unsigned long long)c.dimy), (int)(cell % (unsigned long long)c.dimy), hc);
+  a.flush();
+  hydro_count_out(out, hc);
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -1249,6 +1403,9 @@ struct sm_context {
   float* d_verts = nullptr;       // 11 floats per cell, allocated on first sm_mesh_update
   float4* d_colors = nullptr;
   bool mesh_valid = false;
+  unsigned long long* d_act = nullptr;   // active-cell index of the seep pass (allocated on first use)
+  unsigned long long act_words = 0;
+  HydroCount* d_hydro = nullptr;
   RunCtl* h_ctl = nullptr;        // pinned
   int64_t launches = 0;
   int cur_kind = -1, cur_n = 0;
@@ -1295,6 +1452,7 @@ void sm_destroy(sm_context* ctx) {
   cudaFree(d.ctl); cudaFree(d.pa); cudaFree(d.pb); cudaFree(d.pc); cudaFree(d.alive); cudaFree(d.done); cudaFree(d.pstate); cudaFree(d.fin); cudaFree(d.mv);
   for (int i = 0; i < 2; i++) { cudaFree(d.head[i]); cudaFree(d.node[i]); }
   cudaFree(ctx->d_verts); cudaFree(ctx->d_colors); cudaFree(d.dbg);
+  cudaFree(ctx->d_act); cudaFree(ctx->d_hydro);
   cudaFree(ctx->d_spawn); cudaFree(ctx->d_scratch); cudaFree(ctx->d_iscratch); cudaFree(ctx->d_cellres);
   if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -1888,6 +2046,69 @@ int sm_wind_run_device(sm_context* ctx, int32_t n, const float* d_xy, int32_t ma
   if (rc != SM_OK) return rc;
   ctx->cur_kind = KIND_WIND; ctx->cur_n = n;
   return launch_run(ctx, KIND_WIND, n, d_xy, max_sweeps);
+}
+
+// ---- pooling hydrology ----------------------------------------------------------------------------
+static int hydro_ready(sm_context* ctx) {
+  if (ctx->nsoils < 1) return fail(ctx, SM_ERR_INVALID, "soil table not set");
+  if (ctx->nranks > 1) return fail(ctx, SM_ERR_INVALID, "pooling hydrology is not available on a sharded context");
+  CK(cudaSetDevice(ctx->cfg.device));
+  if (!ctx->d_hydro) {
+    CK(cudaMalloc(&ctx->d_hydro, sizeof(HydroCount)));
+    CK(cudaFuncSetAttribute(k_hydro_flood, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_HC_BYTES));
+    CK(cudaFuncSetAttribute(k_hydro_seep, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_HC_BYTES));
+  }
+  return SM_OK;
+}
+static int hydro_finish(sm_context* ctx, sm_hydro_stats* st) {
+  HydroCount hc;
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(cudaMemcpyAsync(&hc, ctx->d_hydro, sizeof(hc), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  ctx->timing_pending = false;
+  ctx->mesh_valid = false;
+  if (st) {
+    st->floods = (int64_t)hc.floods; st->nested = (int64_t)hc.nested; st->nested_steps = (int64_t)hc.nested_steps;
+    st->transfers = (int64_t)hc.transfers; st->cells = (int64_t)hc.cells; st->device_ms = ms;
+  }
+  if (hc.overflow) return fail(ctx, SM_ERR_REACH, "water cascade nesting exceeded its bound");
+  unsigned int err = 0;
+  CK(cudaMemcpy(&err, &ctx->d.ctl->err, sizeof(err), cudaMemcpyDeviceToHost));
+  if (err & (1u << 3)) return fail(ctx, SM_ERR_POOL, "section pool exhausted (sections were dropped)");
+  return SM_OK;
+}
+int sm_water_flood(sm_context* ctx, sm_hydro_stats* st) {
+  int rc = hydro_ready(ctx);
+  if (rc != SM_OK) return rc;
+  if (ctx->cur_kind != KIND_WATER) return fail(ctx, SM_ERR_INVALID, "sm_water_flood: the last batch was not a water batch");
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  k_hydro_flood<<<1, 32, SM_HC_BYTES, ctx->stream>>>(ctx->d, ctx->cur_n, ctx->d_hydro);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return hydro_finish(ctx, st);
+}
+int sm_seep(sm_context* ctx, sm_hydro_stats* st) {
+  int rc = hydro_ready(ctx);
+  if (rc != SM_OK) return rc;
+  ActiveMap am{};
+  am.ncells = ctx->cells;
+  const unsigned long long total = active_layout(ctx->cells, am.nwords, &am.nlevels);
+  if (!ctx->d_act || ctx->act_words < total) {
+    cudaFree(ctx->d_act); ctx->d_act = nullptr;
+    CK(cudaMalloc(&ctx->d_act, total * sizeof(unsigned long long)));
+    ctx->act_words = total;
+  }
+  unsigned long long off = 0;
+  for (int l = 0; l < am.nlevels; l++) { am.lvl[l] = ctx->d_act + off; off += am.nwords[l]; }
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_act, 0, total * sizeof(unsigned long long), ctx->stream));
+  k_hydro_classify<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(ctx->d, am);
+  k_hydro_seep<<<1, 32, SM_HC_BYTES, ctx->stream>>>(ctx->d, am, ctx->d_hydro);
+  ctx->launches += 2;
+  CK(cudaGetLastError());
+  return hydro_finish(ctx, st);
 }
 
 // stepping interface: *_begin runs the prologue only (spawn + bins), *_sweeps(k) resumes the batch

@@ -178,3 +178,26 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "sweepcurve":
     for lo in range(0, n - 1, 1000):
         hi = min(lo + 1000, n - 1)
         print("  sweeps %5d-%5d: alive %6d..%6d  avg %.1f us/sweep  (sum %.1f ms)" % (lo, hi, alive[lo], alive[hi], dt[lo:hi].mean(), dt[lo:hi].sum() / 1e3), flush=True)
+
+
+def hydro(soil="rockgravelpebblessand", dim=4096, n=25000, frames=4):
+    """full water part of the frame at bench scale: batch, floods, seep pass (device timings)."""
+    from soilmachine_b200 import host
+    sim = host.Simulation(soil, seed=42, dimx=dim, dimy=dim, max_particles=n)
+    for f in range(frames):
+        xw = host.spawn_list(n, dim, dim)
+        g = sim.ctx.water_run(xw)
+        h = sim.ctx.water_flood()
+        s = sim.ctx.seep()
+        sim.ctx.frequency_update()
+        print("hydro %s %d^2 frame %d: batch %.1f ms (%d steps, %d stalled) | flood %.2f ms %s | seep %.2f ms %s" % (
+            soil, dim, f, g.device_ms, g.steps, g.exit_stall, h.device_ms,
+            {k: v for k, v in h.asdict().items() if k != "device_ms"}, s.device_ms,
+            {k: v for k, v in s.asdict().items() if k != "device_ms"}), flush=True)
+    print("  height sum %.9f" % sim.ctx.height_sum(), flush=True)
+    sim.close()
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "hydro":
+    hydro()
+    hydro("default", 1024, 10000, 4)

@@ -366,3 +366,71 @@ def test_sharded_map_is_bit_identical(ref, nranks, soil, dimx, dimy, nw, nd):
     for k in f1:
         _same(f1[k], f2[k], k)
     sh.close()
+
+@pytest.mark.parametrize("soil,dim,n,frames", [
+    ("default", 128, 600, 3), ("rockgravelpebblessand", 160, 1500, 3), ("bigbutte", 128, 800, 3),
+    ("rocksand", 192, 1200, 2)])
+def test_hydrology_frames(ref, soil, dim, n, frames):
+    """The full water part of the frame (SoilMachine.cpp:288-301): lockstep batch, flood() of the finished
+    particles in ascending index (water.h:123-145), the full-grid seep pass (water.h:335-343), frequency
+    update - against the reference's own flood/cascade/seep functions.  Bit-exact after every phase."""
+    ctx, _ = _setup(ref, soil, dim)
+    total = {"floods": 0, "transfers": 0}
+    for frame in range(frames):
+        xy = ref.spawn_list(n, seed=42 + frame)
+        ref.water_run(xy); ctx.water_run(xy)
+        _compare_maps(ref, ctx)
+        nf = ref.water_flood()
+        h = ctx.water_flood()
+        _compare_maps(ref, ctx)
+        assert h.floods >= nf                      # nested particles flood too; the batch's own floods are nf
+        ref.seep()
+        h2 = ctx.seep()
+        _compare_maps(ref, ctx)
+        ref.frequency_update(); ctx.frequency_update()
+        _compare_maps(ref, ctx)
+        total["floods"] += h.floods; total["transfers"] += h.transfers + h2.transfers
+    assert total["floods"] > 0 and total["transfers"] > 0     # the case exercises the path
+
+
+def test_hydrology_counters_match_port(ref):
+    """Counters the verbatim reference cannot report (nested particles, their steps, transfers) against the
+    oracle port, which is itself pinned to the reference bit for bit (tests/test_oracle_port.py)."""
+    from oracle import portapi
+    ctx, cols = _setup(ref, "default", 128)
+    po = portapi.Port().init(ref.dimx, ref.dimy, ref.scale, ref.soils())
+    po.set_columns(cols)
+    for frame in range(2):
+        xy = ref.spawn_list(600, seed=11 + frame)
+        po.water_run(xy); ctx.water_run(xy)
+        a, b = po.water_flood(), ctx.water_flood()
+        assert (a.floods, a.nested, a.nested_steps, a.transfers) == (b.floods, b.nested, b.nested_steps, b.transfers)
+        a, b = po.seep(), ctx.seep()
+        assert (a.floods, a.nested, a.nested_steps, a.transfers) == (b.floods, b.nested, b.nested_steps, b.transfers)
+        assert b.cells < a.cells                   # the device pass visits only the cells where water is
+        po.frequency_update(); ctx.frequency_update()
+    c1, c2 = po.columns(), ctx.download_columns()
+    for k in ("offsets", "type", "size", "floor", "saturation"):
+        _same(c1[k], c2[k], "columns." + k)
+
+
+def test_hydrology_with_wind_and_uploaded_water(ref):
+    """Water already on the map when the columns are uploaded (saturated sections below, Air on top), wind
+    batches in between: the seep pass must find every wet cell by itself."""
+    ctx, _ = _setup(ref, "rocksand", 128)
+    xy = ref.spawn_list(900, seed=5)
+    for frame in range(2):                          # make the reference map wet, then upload it afresh
+        ref.water_run(xy); ref.water_flood(); ref.seep(); ref.frequency_update()
+    cols = ref.columns()
+    assert (cols["saturation"] > 0).sum() > 0
+    ctx.upload_columns(cols["offsets"], cols["type"], cols["size"], cols["saturation"])
+    f = ref.frequency()
+    ctx.set_frequency(f["water_frequency"], f["water_track"], f["wind_frequency"])
+    xd = ref.spawn_list(400, seed=6)
+    ref.wind_run(xd); ctx.wind_run(xd)
+    ref.seep(); ctx.seep()
+    _compare_maps(ref, ctx)
+    ref.water_run(xy); ctx.water_run(xy)
+    ref.water_flood(); ctx.water_flood()
+    ref.seep(); ctx.seep()
+    _compare_maps(ref, ctx)
