@@ -211,6 +211,19 @@ struct WaterParticle : Particle {
     map.ck(sm_water_run(map.ctx, NWATER, xy.data(), 0, &st));
     return st;
   }
+  // The flood tail of the per-particle loop (SoilMachine.cpp:292-296, water.h:123-145) for the whole batch:
+  // every finished particle of the last run() floods, in ascending particle index.
+  template <class VP> static sm_hydro_stats flood(Layermap& map, VP&) {
+    sm_hydro_stats st{};
+    map.ck(sm_water_flood(map.ctx, &st));
+    return st;
+  }
+  // WaterParticle::seep(map, vertexpool), water.h:335-343 / SoilMachine.cpp:300-301
+  template <class VP> static sm_hydro_stats seep(Layermap& map, VP&) {
+    sm_hydro_stats st{};
+    map.ck(sm_seep(map.ctx, &st));
+    return st;
+  }
   static void mapfrequency(Layermap& map) { map.ck(sm_frequency_update(map.ctx)); }   // water.h:358-365 (+ reset, fused)
   static void resetfrequency(Layermap&) {}                                            // water.h:353-356
   static std::vector<float> frequency(Layermap& map) {                                // water.h:345

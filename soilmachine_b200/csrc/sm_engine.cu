@@ -1244,15 +1244,28 @@ __global__ void k_cell_op(DevCtx c, CellOp o, CellRes* res) {
 // replaced and when the kernel ends.  Buried sections (pool) and the frequency maps are accessed in place.
 #define SM_HC_EDGE 64
 #define SM_HC_LINES (SM_HC_EDGE * SM_HC_EDGE)
-#define SM_HC_BYTES (SM_HC_LINES * (int)sizeof(Sec32) + SM_HC_LINES * 4)
+#define SM_HC_FREE 256    // private free list of pool slots (the executor is the only thread touching the pool)
+#define SM_HC_BYTES (SM_HC_LINES * (int)sizeof(Sec32) + SM_HC_LINES * 8 + SM_HC_FREE * 4)
 
 struct HydroAccess : DevAccess {
   Sec32* s_rec;          // SM_HC_LINES records
   uint32_t* s_tag;       // cell index held by each line, SM_NIL = none
+  uint32_t* s_mark;      // cell whose 3x3 block this line last flagged in the active index (marks are never cleared)
+  uint32_t* s_free;      // pool slots freed by this kernel, reused before the shared rings are touched
+  int nfree;
   ActiveMap act;
   bool marking;
   __device__ __forceinline__ HydroAccess(const DevCtx& ctx, const SoilDev* ss, Sec32* sr, uint32_t* st, const ActiveMap& am, bool mk)
-      : DevAccess(ctx, ss, 0u), s_rec(sr), s_tag(st), act(am), marking(mk) {}
+      : DevAccess(ctx, ss, 0u), s_rec(sr), s_tag(st), s_mark(st + SM_HC_LINES), s_free(st + 2 * SM_HC_LINES), nfree(0),
+        act(am), marking(mk) {}
+  __device__ __forceinline__ uint32_t pool_alloc() {
+    if (nfree > 0) return s_free[--nfree];
+    return DevAccess::pool_alloc();
+  }
+  __device__ __forceinline__ void pool_free(uint32_t i) {
+    if (nfree < SM_HC_FREE) s_free[nfree++] = i;
+    else DevAccess::pool_free(i);
+  }
   __device__ __forceinline__ Sec32* rec(int x, int y) {
     const uint32_t cell = (uint32_t)x * (uint32_t)c.dimy + (uint32_t)y;
     const int line = (x & (SM_HC_EDGE - 1)) * SM_HC_EDGE + (y & (SM_HC_EDGE - 1));
@@ -1268,7 +1281,14 @@ struct HydroAccess : DevAccess {
   __device__ __forceinline__ uint32_t surface_of(int x, int y) { return rec_surface(*rec(x, y)); }
   __device__ __forceinline__ void query(int x, int y, double& h, uint32_t& t) { const Sec32* r = rec(x, y); h = rec_height(*r); t = rec_surface(*r); }
   __device__ __forceinline__ void dirty_rec(Sec32* r, int x, int y) {
-    if (marking && r->type == SM_AIR) active_mark_block(act, x, y, c.dimx, c.dimy);
+    if (marking && r->type == SM_AIR) {
+      const int line = (int)(r - s_rec);             // r always comes from rec()
+      const uint32_t cell = s_tag[line];
+      if (s_mark[line] != cell) {
+        active_mark_block(act, x, y, c.dimx, c.dimy);
+        s_mark[line] = cell;
+      }
+    }
   }
   __device__ __forceinline__ void dirty(int x, int y) { dirty_rec(rec(x, y), x, y); }
   __device__ __forceinline__ void wet_mark(int x, int y) {
@@ -1279,13 +1299,14 @@ struct HydroAccess : DevAccess {
       const uint32_t held = s_tag[line];
       if (held != SM_NIL) c.top[held] = s_rec[line];
     }
+    while (nfree > 0) DevAccess::pool_free(s_free[--nfree]);
   }
 };
 
 __device__ __forceinline__ void hydro_smem_init(unsigned char* smem, Sec32*& s_rec, uint32_t*& s_tag, SoilDev* s_soils, const DevCtx& c) {
   s_rec = reinterpret_cast<Sec32*>(smem);
   s_tag = reinterpret_cast<uint32_t*>(smem + SM_HC_LINES * sizeof(Sec32));
-  for (int i = threadIdx.x; i < SM_HC_LINES; i += blockDim.x) s_tag[i] = SM_NIL;
+  for (int i = threadIdx.x; i < 2 * SM_HC_LINES; i += blockDim.x) s_tag[i] = SM_NIL;   // tags and marks
   for (int i = threadIdx.x; i < c.nsoils; i += blockDim.x) s_soils[i] = c.soils[i];
   __syncthreads();
 }

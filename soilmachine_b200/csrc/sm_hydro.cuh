@@ -141,6 +141,10 @@ template <class A> SM_HD_NOINLINE void hydro_flood(A& a, const WaterP& p, int sp
   hydro_push(a, st, sp, ix, iy, spill, hc);                         // :140
 }
 
+// the nested particle's move() && interact() (water.h:252-253), out of line: it is the rare branch of the
+// frame loop and would otherwise triple the loop's code size
+template <class A> SM_HD_NOINLINE int hydro_nested_step(A& a, WaterP& q) { return water_step(a, q); }
+
 // run every open frame to its end
 template <class A> SM_HD_NOINLINE void hydro_drain(A& a, WFrame* st, int& sp, HydroCount& hc) {
   const int SCALE = a.scale();
@@ -158,13 +162,17 @@ template <class A> SM_HD_NOINLINE void hydro_drain(A& a, WFrame* st, int& sp, Hy
     double whA = 0, whB = 0, fA = 0.0, fB = 0.0;                    // :189-208
     if (pa->type != SM_EMPTY) { whA = pa->size; fA = pa->floor; }
     if (pb->type != SM_EMPTY) { whB = pb->size; fB = pb->floor; }
-    const double diff = (fA + whA - fB - whB) * (double)SCALE / 80.0;   // :211
-    if (diff == 0) continue;
-    Sec32* const top = (diff > 0) ? pa : pb;                        // :216-220
-    Sec32* const bot = (diff > 0) ? pb : pa;
-    const int tx = (diff > 0) ? cx : nx, ty = (diff > 0) ? cy : ny;
-    const int bx = (diff > 0) ? nx : cx, by = (diff > 0) ? ny : cy;
+    // diff = num / 80.0 (:211) has num's sign and is zero only when num is zero or the quotient underflows;
+    // both early exits below are side-effect free, so the IEEE division is only paid where water can move
+    const double num = (fA + whA - fB - whB) * (double)SCALE;
+    if (num == 0) continue;
+    Sec32* const top = (num > 0) ? pa : pb;                         // :216-220
+    Sec32* const bot = (num > 0) ? pb : pa;
+    const int tx = (num > 0) ? cx : nx, ty = (num > 0) ? cy : ny;
+    const int bx = (num > 0) ? nx : cx, by = (num > 0) ? ny : cy;
     if (top->type != SM_AIR) continue;                              // :223-224 only water moves
+    const double diff = num / 80.0;
+    if (diff == 0) continue;                                        // :212-213
     double transfer = fabs(diff) / 2.0;                             // :227
     const double wh = top->size;                                    // :230
     transfer = (wh < transfer) ? wh : transfer;
@@ -190,7 +198,7 @@ template <class A> SM_HD_NOINLINE void hydro_drain(A& a, WFrame* st, int& sp, Hy
       hc.nested++;
       SM_UNROLL1
       for (;;) {                                                    // :252-253
-        const int rc = water_step(a, q);
+        const int rc = hydro_nested_step(a, q);
         if (rc == SM_ALIVE || rc == SM_EXIT_EVAP) hc.nested_steps++;
         if (rc != SM_ALIVE) break;
       }

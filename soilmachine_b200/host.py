@@ -1,8 +1,9 @@
 """Host-side mirror of the GL-free part of the reference's main() (SoilMachine.cpp:34-48,82-83,
 283-320) on top of the C ABI: load a preset, build the terrain on the GPU, run frames.
 
-A frame = one water batch run to completion, one wind batch run to completion, the frequency
-update (flood/seep are outside the hot path).  Spawn positions are drawn with
+A frame = one water batch run to completion, optionally the pooling hydrology (the batch's floods and
+the full-grid seep pass, SoilMachine.cpp:296,300-301), one wind batch run to completion, the frequency
+update.  Spawn positions are drawn with
 the C library's rand() in the order the particle constructors draw them (water.h:13, wind.h:15:
 GCC evaluates the two arguments right to left, so y takes the first draw).
 """
@@ -59,12 +60,17 @@ class Simulation:
         self.ctx.set_soil_colors(self.preset["colors"])
         self.ctx.initialize(self.seed, self.preset["layers"])   # Layermap(SEED, dim), SoilMachine.cpp:83
 
-    def frame(self, nwater, nwind, water_xy=None, wind_xy=None):
-        """SoilMachine.cpp:287-320 (hot path only).  Returns (water_stats, wind_stats)."""
+    def frame(self, nwater, nwind, water_xy=None, wind_xy=None, hydrology=False):
+        """SoilMachine.cpp:287-320.  hydrology=False: the hot path only (flood disabled, no seep pass);
+        True: the water batch is followed by its floods and by the seep pass (self.last_hydrology holds the
+        two counter sets).  Returns (water_stats, wind_stats)."""
         ws = ds = None
+        self.last_hydrology = None
         if nwater:
             xy = water_xy if water_xy is not None else spawn_list(nwater, self.dimx, self.dimy)
             ws = self.ctx.water_run(xy)
+            if hydrology:
+                self.last_hydrology = (self.ctx.water_flood(), self.ctx.seep())
         if nwind:
             xy = wind_xy if wind_xy is not None else spawn_list(nwind, self.dimx, self.dimy)
             ds = self.ctx.wind_run(xy)

@@ -5,6 +5,7 @@ import numpy as np
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 FRAME_CASES = ["frame_default_48", "frame_rocksand_56", "frame_rgps_64", "frame_bigbutte_40"]
+HYDRO_CASES = ["hydro_default_48", "hydro_bigbutte_40"]
 
 
 def load(name):
@@ -51,6 +52,25 @@ def replay_frame(g, backend, stats_of):
     for k in f:
         same(f[k], g["freq_" + k], "frequency " + k)
     same(backend.heights(), g["heights"], "heights")
+
+
+def replay_hydro(g, backend):
+    """backend initialised with g's init columns; needs water_run / water_flood / seep / frequency_update.
+    Returns the per-frame counters of the backend's flood phase."""
+    counters = []
+    for f in range(int(g["frames"])):
+        backend.water_run(g["water_xy_%d" % f])
+        counters.append(backend.water_flood())
+        if ("after_flood_%d_offsets" % f) in g.files:
+            same_cols(backend_columns(backend), cols(g, "after_flood_%d" % f), "frame %d columns after the floods" % f)
+        backend.seep()
+        same_cols(backend_columns(backend), cols(g, "after_seep_%d" % f), "frame %d columns after the seep pass" % f)
+        backend.frequency_update()
+    fr = backend.frequency()
+    for k in fr:
+        same(fr[k], g["freq_" + k], "frequency " + k)
+    same(backend.heights(), g["heights"], "heights")
+    return counters
 
 
 def backend_columns(b):

@@ -32,11 +32,14 @@ int main(int argc, char** argv) {
     Layermap map(SEED, ivec2(SIZEX, SIZEY), vertexpool, SCALE);   // :83
     for (int frame = 0; frame < 2; frame++) {                // the body of Tiny::loop, :287-320
       sm_stats w = WaterParticle::run(map, vertexpool, NWATER);
+      sm_hydro_stats fl = WaterParticle::flood(map, vertexpool);   // :296, for the whole batch
+      sm_hydro_stats se = WaterParticle::seep(map, vertexpool);    // :300-301
       sm_stats d = WindParticle::run(map, vertexpool, NWIND);
       WaterParticle::mapfrequency(map);
       WaterParticle::resetfrequency(map);
-      printf("frame %d: water %lld steps in %lld sweeps, wind %lld steps; h(5,5)=%.17g surface=%zu\n", frame,
-             (long long)w.steps, (long long)w.sweeps, (long long)d.steps, map.height(ivec2(5, 5)), map.surface(ivec2(5, 5)));
+      printf("frame %d: water %lld steps in %lld sweeps, %lld floods, seep pass over %lld cells, wind %lld steps; h(5,5)=%.17g surface=%zu\n", frame,
+             (long long)w.steps, (long long)w.sweeps, (long long)fl.floods, (long long)se.cells, (long long)d.steps,
+             map.height(ivec2(5, 5)), map.surface(ivec2(5, 5)));
     }
     map.add(ivec2(3, 3), map.pool.get(0.01, soilmap["Red Sand"]));   // legacy per-cell idiom
     double left = map.remove(ivec2(3, 3), 0.005);

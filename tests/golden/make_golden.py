@@ -83,9 +83,42 @@ def column_ops_case():
     print("column_ops", r.nsections(), "sections")
 
 
+def hydro_case(soil, dim, seed, n, frames, name):
+    """Full water part of the frame in the batch order (SoilMachine.cpp:288-301): lockstep batch, flood() of the
+    finished particles in ascending index, the seep pass, the frequency update; columns after every phase."""
+    r = refapi.get().init(soil, seed=seed, dimx=dim, dimy=dim + 8)
+    out = {"dimx": r.dimx, "dimy": r.dimy, "scale": r.scale, "seed": seed, "soils": r.soils(), "frames": frames}
+    pack_cols("init", r.columns(), out)
+    r.lib.smref_srand(seed)
+    floods = []
+    for f in range(frames):
+        xy = r.spawn_list(n)
+        out["water_xy_%d" % f] = xy
+        r.water_run(xy)
+        floods.append(r.water_flood())
+        if f == frames - 1:                       # one snapshot between the two phases keeps the fixture small
+            pack_cols("after_flood_%d" % f, r.columns(), out)
+        r.seep()
+        pack_cols("after_seep_%d" % f, r.columns(), out)
+        r.frequency_update()
+    out["floods"] = np.array(floods, np.int64)
+    for k, v in r.frequency().items():
+        out["freq_" + k] = v
+    out["heights"] = r.heights()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    c = r.columns()
+    print(name, "floods", floods, "air sections", int((c["type"] == 0).sum()), "saturated", int((c["saturation"] > 0).sum()))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "hydro":
+        hydro_case("default", 48, 42, 400, 3, "hydro_default_48")
+        hydro_case("bigbutte", 40, 3, 500, 3, "hydro_bigbutte_40")
+        sys.exit(0)
     column_ops_case()
     frame_case("default", 48, 42, 150, 0, "frame_default_48")
     frame_case("rocksand", 56, 7, 200, 120, "frame_rocksand_56")
     frame_case("rockgravelpebblessand", 64, 42, 250, 150, "frame_rgps_64")
     frame_case("bigbutte", 40, 3, 120, 0, "frame_bigbutte_40")
+    hydro_case("default", 48, 42, 400, 3, "hydro_default_48")
+    hydro_case("bigbutte", 40, 3, 500, 3, "hydro_bigbutte_40")

@@ -213,4 +213,17 @@ void hs_seep(int mode, HydroCount* out) {
   }
   if (out) *out = hc;
 }
+// enumerate a bitmap built from `idx` (n distinct cell numbers) with active_next; returns the count written
+int hs_active_selftest(unsigned long long cells, const unsigned long long* idx, int n, unsigned long long* out) {
+  ActiveMap am{};
+  unsigned long long total = active_layout(cells, am.nwords, &am.nlevels);
+  std::vector<unsigned long long> store(total, 0ull);
+  unsigned long long off = 0;
+  for (int l = 0; l < am.nlevels; l++) { am.lvl[l] = store.data() + off; off += am.nwords[l]; }
+  am.ncells = cells;
+  for (int i = n - 1; i >= 0; i--) { active_set(am, idx[i]); active_set(am, idx[i]); }
+  int k = 0;
+  for (unsigned long long c = active_next(am, 0); c < cells; c = active_next(am, c + 1)) { if (k <= n) out[k] = c; k++; }
+  return k;
+}
 }

@@ -434,3 +434,18 @@ def test_hydrology_with_wind_and_uploaded_water(ref):
     ref.water_flood(); ctx.water_flood()
     ref.seep(); ctx.seep()
     _compare_maps(ref, ctx)
+
+
+@pytest.mark.parametrize("case", ["hydro_default_48", "hydro_bigbutte_40"])
+def test_gpu_replays_golden_hydrology(case):
+    """Committed vectors of the full water part of the frame (batch, floods, seep pass; generated from the
+    reference by tests/golden/make_golden.py) through the C ABI - independent of oracle/_ref."""
+    import _golden
+    import soilmachine_b200 as smb
+    g = _golden.load(case)
+    ctx = smb.Context(int(g["dimx"]), int(g["dimy"]), int(g["scale"]), max_particles=4096)
+    ctx.set_soils(g["soils"])
+    c = _golden.cols(g, "init")
+    ctx.upload_columns(c["offsets"], c["type"], c["size"], c["saturation"])
+    counters = _golden.replay_hydro(g, ctx)
+    assert all(h.floods >= f for h, f in zip(counters, g["floods"]))

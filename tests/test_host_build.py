@@ -91,3 +91,68 @@ def test_product_column_ops_truth_table():
     for x, y, loop in g["cascades"]:
         hs.lib.hs_cascade(float(x), float(y), int(loop))
     _golden.same_cols(hs.columns(), _golden.cols(g, "after_cascade"), "columns after cascades")
+
+
+# ---- pooling hydrology: the product's frame machine and active-cell index (sm_hydro.cuh) ----------------
+class HydroBackend(Backend):
+    def __init__(self, g, seep_mode):
+        super().__init__(g)
+        self.seep_mode = seep_mode
+
+    def water_flood(self):
+        return self.hs.water_flood()
+
+    def seep(self):
+        return self.hs.seep(self.seep_mode)
+
+
+@pytest.mark.parametrize("case", _golden.HYDRO_CASES)
+@pytest.mark.parametrize("seep_mode", [0, 1], ids=["every_cell", "active_index"])
+def test_product_hydrology_replays_golden(case, seep_mode):
+    """flood / water-table cascade / seep as the device executes them - explicit frame stack instead of
+    recursion, and (seep_mode 1) the classification + active-cell index instead of the full scan - against
+    vectors generated from the reference's recursive code."""
+    g = _golden.load(case)
+    b = HydroBackend(g, seep_mode)
+    b.hs.set_columns(_golden.cols(g, "init"))
+    counters = _golden.replay_hydro(g, b)
+    assert all(c.overflow == 0 for c in counters)
+    assert all(c.floods >= f for c, f in zip(counters, g["floods"]))
+
+
+def test_product_hydrology_counters_match_port():
+    """nested particles, their steps and the transfers are invisible to the verbatim reference; the oracle
+    port (recursive, pinned to the reference) and the product's frame machine must agree on them."""
+    from oracle import portapi
+    g = _golden.load("hydro_bigbutte_40")
+    b = HydroBackend(g, 1)
+    b.hs.set_columns(_golden.cols(g, "init"))
+    po = portapi.Port().init(int(g["dimx"]), int(g["dimy"]), int(g["scale"]), g["soils"])
+    po.set_columns(_golden.cols(g, "init"))
+    cells = int(g["dimx"]) * int(g["dimy"])
+    for f in range(int(g["frames"])):
+        xy = g["water_xy_%d" % f]
+        po.water_run(xy); b.water_run(xy)
+        x, y = po.water_flood(), b.water_flood()
+        assert (x.floods, x.nested, x.nested_steps, x.transfers) == (y.floods, y.nested, y.nested_steps, y.transfers)
+        x, y = po.seep(), b.seep()
+        assert (x.floods, x.nested, x.nested_steps, x.transfers) == (y.floods, y.nested, y.nested_steps, y.transfers)
+        assert x.cells == cells and y.cells < cells
+        po.frequency_update(); b.frequency_update()
+
+
+def test_active_index_next_and_set():
+    """the hierarchical bitmap of the seep pass (active_set / active_next) against a sorted list"""
+    import ctypes as C
+    hs = _hostsim.HostSim()
+    rng = np.random.RandomState(3)
+    for cells in (1, 63, 64, 65, 4096, 4097, 300000):
+        k = min(cells, 200)
+        idx = np.unique(rng.randint(0, cells, k)).astype(np.uint64)
+        if cells > 64:
+            idx = np.unique(np.concatenate([idx, np.array([0, cells - 1, 63, 64], np.uint64)]))
+        out = np.zeros(len(idx) + 1, np.uint64)
+        n = hs.lib.hs_active_selftest(C.c_uint64(cells), idx.ctypes.data_as(C.c_void_p), len(idx),
+                                      out.ctypes.data_as(C.c_void_p))
+        assert n == len(idx)
+        assert np.array_equal(out[:n], idx)

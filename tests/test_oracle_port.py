@@ -102,3 +102,64 @@ def test_port_vs_reference_random_column_ops(port, ref):
         if i % 500 == 499:
             _golden.same_cols(ref.columns(), port.columns(), "columns after %d ops" % (i + 1))
     _golden.same(ref.heights(), port.heights(), "heights")
+
+
+# ---- pooling hydrology (flood, water-table cascade, seep) ------------------
+@pytest.mark.parametrize("case", _golden.HYDRO_CASES)
+def test_port_replays_golden_hydrology(port, case):
+    g = _golden.load(case)
+    port.init(int(g["dimx"]), int(g["dimy"]), int(g["scale"]), g["soils"])
+    port.set_columns(_golden.cols(g, "init"))
+    counters = _golden.replay_hydro(g, port)
+    # the batch's own floods are what the reference can count; nested particles flood on top of that
+    assert all(c.floods >= f for c, f in zip(counters, g["floods"]))
+    assert sum(c.floods for c in counters) > 0 and sum(c.transfers for c in counters) > 0
+
+
+@pytest.mark.parametrize("soil,dim,n,frames", [("default", 96, 500, 3), ("rockgravelpebblessand", 112, 900, 3),
+                                               ("bigbutte", 64, 500, 3)])
+def test_port_hydrology_matches_reference_live(port, ref, soil, dim, n, frames):
+    """batch order: lockstep batch, floods in ascending index, seep pass - after every phase."""
+    ref.init(soil, seed=42, dimx=dim, dimy=dim + 8)
+    port.init(ref.dimx, ref.dimy, ref.scale, ref.soils())
+    port.set_columns(ref.columns())
+    for f in range(frames):
+        xy = ref.spawn_list(n, seed=42 + f)
+        ref.water_run(xy); port.water_run(xy)
+        nf = ref.water_flood(); h = port.water_flood()
+        assert h.floods >= nf
+        _golden.same_cols(ref.columns(), port.columns(), "frame %d after floods" % f)
+        ref.seep(); port.seep()
+        _golden.same_cols(ref.columns(), port.columns(), "frame %d after seep" % f)
+        ref.frequency_update(); port.frequency_update()
+        fa, fb = ref.frequency(), port.frequency()
+        for k in fa:
+            _golden.same(fa[k], fb[k], k)
+
+
+def test_port_hydrology_sequential_order(port, ref):
+    """The reference's own order - each particle floods right after its loop, then the seep pass
+    (SoilMachine.cpp:288-301) - with an explicit spawn list on both sides."""
+    ref.init("default", seed=42, dimx=96, dimy=96)
+    port.init(ref.dimx, ref.dimy, ref.scale, ref.soils())
+    port.set_columns(ref.columns())
+    for f in range(2):
+        xy = ref.spawn_list(400, seed=3 + f)
+        a = ref.water_seq(0, xy, flood=True, seep=True)
+        b, h = port.water_seq_full(xy, flood=True, seep=True)
+        assert stats5(a)[0] == stats5(b)[0] and (a.exit_oob, a.exit_evap, a.exit_stall) == (b.exit_oob, b.exit_evap, b.exit_stall)
+        _golden.same_cols(ref.columns(), port.columns(), "frame %d" % f)
+        ref.frequency_update(); port.frequency_update()
+    assert h.cells == ref.dimx * ref.dimy
+
+
+def test_reference_build_reproduces_survey_hydrology_kat(ref):
+    """default.soil, 256^2, SEED 42, srand(42), one frame of 1000 water particles through
+    the reference loop INCLUDING flood and the seep pass (rand() spawns, sequential order)."""
+    ref.init("default", seed=42, dimx=256, dimy=256)
+    ref.lib.smref_srand(42)
+    st = ref.water_seq(1000, None, flood=True, seep=True)
+    c = ref.columns()
+    assert st.steps == 313844 and (st.exit_oob, st.exit_evap, st.exit_stall) == (170, 636, 194)
+    assert len(c["type"]) == 65638 and int((c["type"] == 0).sum()) == 309
+    assert abs(ref.heights().sum() - 29250.672765019299) < 1e-9
