@@ -266,6 +266,23 @@ def main():
     h2d = (W["nwater"] + W["nwind"]) * 8
     d2h = 2 * 424                                  # two RunCtl read-backs per step (sizeof(RunCtl) = 424)
 
+    # ---- reported beside the metric, outside both timed regions: the rest of the water part of the frame
+    # (the batch's floods and the seep pass, SoilMachine.cpp:296,300-301) on the map the frames above left.
+    # BASELINE.json's metric excludes flood, so none of this enters `value` or `e2e`.
+    hydrology = None
+    if world == 1:
+        try:
+            sw = ctx.water_run(lists[-1][0])
+            hf = ctx.water_flood()
+            hs = ctx.seep()
+            hydrology = {"water_batch_ms": sw.device_ms, "stalled": sw.exit_stall,
+                         "flood_ms": hf.device_ms, "floods": hf.floods, "nested_particles": hf.nested,
+                         "flood_transfers": hf.transfers,
+                         "seep_ms": hs.device_ms, "seep_cells_visited": hs.cells, "seep_transfers": hs.transfers,
+                         "cells": W["dim"] * W["dim"]}
+        except Exception as e:                     # never let the extra report break the bench line
+            hydrology = {"error": str(e)[:200]}
+
     # max over ranks / sums over ranks
     ev_ms, e2e_ms, tot_steps, tot_e = aggregate(ev_ms, e2e_ms, steps_w + steps_d, e_steps, device="cuda")
     value = tot_steps / (ev_ms * 1e-3)
@@ -300,6 +317,8 @@ def main():
             "e2e": {"value": e2e_val, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K},
             "gpu_launches": launches, "roofline": roofline, "wall_ms_per_step": wall_ms / K}
+    if hydrology is not None:
+        line["hydrology"] = hydrology
 
     if rank == 0 and world == 1 and not args.no_cpu:
         sample = dict(CPU_SAMPLE)
