@@ -198,6 +198,7 @@ def hydro(soil="rockgravelpebblessand", dim=4096, n=25000, frames=4):
     sim.close()
 
 
-if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "hydro":
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1].startswith("hydro"):
     hydro()
-    hydro("default", 1024, 10000, 4)
+    if sys.argv[1] == "hydro":
+        hydro("default", 1024, 10000, 4)
