@@ -163,3 +163,55 @@ def test_reference_build_reproduces_survey_hydrology_kat(ref):
     assert st.steps == 313844 and (st.exit_oob, st.exit_evap, st.exit_stall) == (170, 636, 194)
     assert len(c["type"]) == 65638 and int((c["type"] == 0).sum()) == 309
     assert abs(ref.heights().sum() - 29250.672765019299) < 1e-9
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_hydrology_random_differential(port, ref, seed):
+    """Random wet maps (0-4 soil sections per column with random saturations, Air on top of a quarter of
+    them, empty columns, tiny sections), then 40 random operations - seep pass, small water batch + its
+    floods, puddles added by hand, frequency update - on the reference, the oracle port and the product core
+    (tests/hostsim, alternating between the every-cell and the active-index seep pass): all three must stay
+    identical section by section, saturation included."""
+    import _hostsim
+    ref.init("rockgravelpebblessand", seed=3, dimx=14, dimy=11)
+    soils = ref.soils()
+    rng = np.random.RandomState(seed)
+    off, typ, size, sat = [0], [], [], []
+    for c in range(ref.dimx * ref.dimy):
+        k = int(rng.randint(0, 5))
+        for j in range(k):
+            typ.append(int(rng.randint(1, len(soils))))
+            size.append(float(rng.choice([0.05, 0.2, 1e-7, 0.01]) * rng.rand() + 0.001))
+            sat.append(float(rng.choice([0, 0, 0.3, 1.0, 0.999])))
+        if rng.rand() < 0.25:
+            typ.append(0); size.append(float(0.05 * rng.rand() + 1e-4)); sat.append(float(rng.choice([0, 1.0])))
+            k += 1
+        off.append(off[-1] + k)
+    ref.set_columns(np.array(off, np.int64), np.array(typ, np.int32), np.array(size), np.array(sat))
+    cols = ref.columns()
+    port.init(ref.dimx, ref.dimy, ref.scale, soils); port.set_columns(cols)
+    hs = _hostsim.HostSim(); hs.init(ref.dimx, ref.dimy, ref.scale, soils); hs.set_columns(cols)
+
+    def check(tag):
+        a = ref.columns()
+        _golden.same_cols(a, port.columns(), tag + " (port)")
+        _golden.same_cols(a, hs.columns(), tag + " (product core)")
+
+    check("initial")
+    for it in range(40):
+        op = int(rng.randint(0, 4))
+        if op == 0:
+            ref.seep(); port.seep(); hs.seep(int(rng.randint(0, 2)))
+        elif op == 1:
+            n = int(rng.randint(1, 30))
+            xy = np.stack([rng.randint(0, ref.dimx, n), rng.randint(0, ref.dimy, n)], 1).astype(np.float32)
+            ref.water_run(xy); port.water_run(xy); hs.water_run(xy)
+            check("op %d batch" % it)
+            ref.water_flood(); port.water_flood(); hs.water_flood()
+        elif op == 2:
+            for _ in range(5):
+                x, y, s = int(rng.randint(0, ref.dimx)), int(rng.randint(0, ref.dimy)), float(0.2 * rng.rand())
+                ref.add(x, y, s, 0); port.add(x, y, s, 0); hs.lib.hs_add(x, y, s, 0)
+        else:
+            ref.frequency_update(); port.frequency_update(); hs.frequency_update()
+        check("op %d kind %d" % (it, op))
