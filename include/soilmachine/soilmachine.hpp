@@ -204,8 +204,21 @@ inline std::vector<float> spawn(const Layermap& map, int n) {
 
 // water.h:9-373 -- the batch entry point replaces the loop SoilMachine.cpp:288-298
 struct WaterParticle : Particle {
-  static void init() {}                                       // frequency/track live on the device
+  // Host mirrors of the device maps, indexed [y*dim.x + x] as upstream (water.h:345-346).  They exist only
+  // after init(dimx, dimy) (upstream: init() allocates them, water.h:21-24) and are refreshed by
+  // mapfrequency() / resetfrequency(), i.e. exactly where the reference frame loop reads them
+  // (SoilMachine.cpp:314-319).  A headless loop that never calls init(...) pays no download.
+  inline static float* frequency = nullptr;
+  inline static float* track = nullptr;
+  inline static double volumeFactor = 0.015;                  // water.h:368 (fixed on the device; see flood())
+  static void init() {}                                       // maps live on the device; no host mirror
+  static void init(int dimx, int dimy) {
+    delete[] frequency; delete[] track;
+    frequency = new float[(size_t)dimx * dimy]();
+    track = new float[(size_t)dimx * dimy]();
+  }
   template <class VP> static sm_stats run(Layermap& map, VP&, int NWATER) {
+    map.push_tables();                                        // upstream reads soils[] live (GUI sliders, :165-200)
     std::vector<float> xy = detail::spawn(map, NWATER);
     sm_stats st{};
     map.ck(sm_water_run(map.ctx, NWATER, xy.data(), 0, &st));
@@ -214,19 +227,25 @@ struct WaterParticle : Particle {
   // The flood tail of the per-particle loop (SoilMachine.cpp:292-296, water.h:123-145) for the whole batch:
   // every finished particle of the last run() floods, in ascending particle index.
   template <class VP> static sm_hydro_stats flood(Layermap& map, VP&) {
+    if (volumeFactor != 0.015) throw Error(SM_ERR_INVALID, "WaterParticle::volumeFactor is fixed at 0.015 on the device");
     sm_hydro_stats st{};
     map.ck(sm_water_flood(map.ctx, &st));
     return st;
   }
   // WaterParticle::seep(map, vertexpool), water.h:335-343 / SoilMachine.cpp:300-301
   template <class VP> static sm_hydro_stats seep(Layermap& map, VP&) {
+    if (volumeFactor != 0.015) throw Error(SM_ERR_INVALID, "WaterParticle::volumeFactor is fixed at 0.015 on the device");
     sm_hydro_stats st{};
     map.ck(sm_seep(map.ctx, &st));
     return st;
   }
-  static void mapfrequency(Layermap& map) { map.ck(sm_frequency_update(map.ctx)); }   // water.h:358-365 (+ reset, fused)
-  static void resetfrequency(Layermap&) {}                                            // water.h:353-356
-  static std::vector<float> frequency(Layermap& map) {                                // water.h:345
+  // water.h:358-365 + 353-356 fused on the device: frequency <- blend(track), track <- 0
+  static void mapfrequency(Layermap& map) {
+    map.ck(sm_frequency_update(map.ctx));
+    if (frequency) map.ck(sm_get_frequency(map.ctx, frequency, track, nullptr));
+  }
+  static void resetfrequency(Layermap&) {}                                            // water.h:353-356 (done above)
+  static std::vector<float> download_frequency(Layermap& map) {                       // water.h:345
     std::vector<float> f((size_t)map.dim.x * map.dim.y);
     map.ck(sm_get_frequency(map.ctx, f.data(), nullptr, nullptr));
     return f;
@@ -234,14 +253,18 @@ struct WaterParticle : Particle {
 };
 // wind.h:11-140 -- the batch entry point replaces the loop SoilMachine.cpp:304-307
 struct WindParticle : Particle {
+  inline static float* frequency = nullptr;                   // wind.h:48; refreshed at the end of run()
   static void init() {}
+  static void init(int dimx, int dimy) { delete[] frequency; frequency = new float[(size_t)dimx * dimy](); }
   template <class VP> static sm_stats run(Layermap& map, VP&, int NWIND) {
+    map.push_tables();
     std::vector<float> xy = detail::spawn(map, NWIND);
     sm_stats st{};
     map.ck(sm_wind_run(map.ctx, NWIND, xy.data(), 0, &st));
+    if (frequency) map.ck(sm_get_frequency(map.ctx, nullptr, nullptr, frequency));
     return st;
   }
-  static std::vector<float> frequency(Layermap& map) {                                // wind.h:48
+  static std::vector<float> download_frequency(Layermap& map) {                       // wind.h:48
     std::vector<float> f((size_t)map.dim.x * map.dim.y);
     map.ck(sm_get_frequency(map.ctx, nullptr, nullptr, f.data()));
     return f;

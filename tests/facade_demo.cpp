@@ -27,7 +27,7 @@ int main(int argc, char** argv) {
   SurfLayer l1(2); l1.bias = 0.0f; l1.scale = 0.4f; l1.octaves = 6; l1.lacunarity = 2; l1.gain = 0.4f; l1.frequency = 2;
   layers.push_back(l0); layers.push_back(l1);
   }
-  WaterParticle::init(); WindParticle::init();               // :47-48
+  WaterParticle::init(SIZEX, SIZEY); WindParticle::init(SIZEX, SIZEY);   // :47-48 (host mirrors of the maps)
   try {
     Layermap map(SEED, ivec2(SIZEX, SIZEY), vertexpool, SCALE);   // :83
     for (int frame = 0; frame < 2; frame++) {                // the body of Tiny::loop, :287-320
@@ -37,6 +37,9 @@ int main(int argc, char** argv) {
       sm_stats d = WindParticle::run(map, vertexpool, NWIND);
       WaterParticle::mapfrequency(map);
       WaterParticle::resetfrequency(map);
+      float wf = 0.f, df = 0.f;                              // the texture loops of :315-326 read the mirrors
+      for (int i = 0; i < SIZEX * SIZEY; i++) { wf += WaterParticle::frequency[i]; df += WindParticle::frequency[i]; }
+      printf("  mean water frequency %.6g, mean wind frequency %.6g\n", wf / (SIZEX * SIZEY), df / (SIZEX * SIZEY));
       printf("frame %d: water %lld steps in %lld sweeps, %lld floods, seep pass over %lld cells, wind %lld steps; h(5,5)=%.17g surface=%zu\n", frame,
              (long long)w.steps, (long long)w.sweeps, (long long)fl.floods, (long long)se.cells, (long long)d.steps,
              map.height(ivec2(5, 5)), map.surface(ivec2(5, 5)));
