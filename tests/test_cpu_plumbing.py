@@ -108,3 +108,44 @@ def test_soil_file_parser_matches_reference_loader(ref):
         assert got["world"] == pre["world"], name
     with pytest.raises(capi.SoilMachineError):
         capi.parse_soil_file("/nonexistent/file.soil")
+
+
+def test_frame_loop_orders_calls_like_the_reference():
+    """host.Simulation.frame against a recording stand-in for the context: water batch(es), floods, seep
+    pass, wind batch, frequency update, in the order of SoilMachine.cpp:287-320; water_chunk splits the
+    batch and floods after every chunk."""
+    import numpy as np
+    from soilmachine_b200 import host
+
+    class Rec:
+        def __init__(self):
+            self.calls = []
+
+        def water_run(self, xy):
+            self.calls.append(("water", len(xy)))
+
+        def wind_run(self, xy):
+            self.calls.append(("wind", len(xy)))
+
+        def water_flood(self):
+            self.calls.append(("flood",))
+
+        def seep(self):
+            self.calls.append(("seep",))
+
+        def frequency_update(self):
+            self.calls.append(("freq",))
+
+    sim = object.__new__(host.Simulation)
+    sim.ctx, sim.dimx, sim.dimy = Rec(), 32, 24
+    host.srand(1)
+    sim.frame(10, 4)
+    assert sim.ctx.calls == [("water", 10), ("wind", 4), ("freq",)]
+    sim.ctx.calls.clear()
+    sim.frame(10, 4, hydrology=True)
+    assert sim.ctx.calls == [("water", 10), ("flood",), ("seep",), ("wind", 4), ("freq",)]
+    sim.ctx.calls.clear()
+    xy = np.zeros((10, 2), np.float32)
+    sim.frame(10, 0, water_xy=xy, hydrology=True, water_chunk=4)
+    assert sim.ctx.calls == [("water", 4), ("flood",), ("water", 4), ("flood",), ("water", 2), ("flood",), ("seep",), ("freq",)]
+    assert len(sim.last_hydrology[0]) == 3
