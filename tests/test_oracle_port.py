@@ -215,3 +215,51 @@ def test_hydrology_random_differential(port, ref, seed):
         else:
             ref.frequency_update(); port.frequency_update(); hs.frequency_update()
         check("op %d kind %d" % (it, op))
+
+
+def test_hydrology_edge_cases(port, ref):
+    """empty map, empty batch, puddles on the corners and edges of the map (the water cascade and the
+    active-cell index both clip their 3x3 blocks), a lone puddle on an otherwise empty map."""
+    import _hostsim
+    ref.init("rocksand", seed=9, dimx=10, dimy=7)
+    soils = ref.soils()
+    hs = _hostsim.HostSim()
+
+    def load(cols):
+        port.init(ref.dimx, ref.dimy, ref.scale, soils); port.set_columns(cols)
+        hs.init(ref.dimx, ref.dimy, ref.scale, soils); hs.set_columns(cols)
+
+    def check(tag):
+        a = ref.columns()
+        _golden.same_cols(a, port.columns(), tag + " (port)")
+        _golden.same_cols(a, hs.columns(), tag + " (product core)")
+
+    # 1. all-empty map: nothing to visit, nothing to flood
+    cells = ref.dimx * ref.dimy
+    empty = np.zeros(cells + 1, np.int64)
+    ref.set_columns(empty, np.zeros(0, np.int32), np.zeros(0))
+    load(ref.columns())
+    none = np.zeros((0, 2), np.float32)
+    ref.water_run(none); port.water_run(none); hs.water_run(none)
+    assert ref.water_flood() == 0 and port.water_flood().floods == 0 and hs.water_flood().floods == 0
+    ref.seep(); port.seep()
+    assert hs.seep(1).cells == 0                   # the active index finds no wet cell at all
+    check("empty map")
+    # 2. a lone puddle on the empty map: water spreads over bare ground, nested particles run on height 0
+    ref.add(4, 3, 0.3, 0); port.add(4, 3, 0.3, 0); hs.lib.hs_add(4, 3, 0.3, 0)
+    for k in range(3):
+        ref.seep(); port.seep(); hs.seep(k % 2)
+        check("lone puddle pass %d" % k)
+    # 3. terrain with puddles on every corner and along the edges
+    ref.init("rocksand", seed=9, dimx=10, dimy=7)
+    load(ref.columns())
+    spots = [(0, 0), (9, 0), (0, 6), (9, 6), (5, 0), (5, 6), (0, 3), (9, 3), (4, 4)]
+    for x, y in spots:
+        ref.add(x, y, 0.08, 0); port.add(x, y, 0.08, 0); hs.lib.hs_add(x, y, 0.08, 0)
+    for k in range(4):
+        ref.seep(); port.seep(); hs.seep((k + 1) % 2)
+        check("border puddles pass %d" % k)
+    xy = np.array([[0, 0], [9, 6], [0, 6], [9, 0], [5, 3], [8, 5]], np.float32)   # spawns on the corners too
+    ref.water_run(xy); port.water_run(xy); hs.water_run(xy)
+    ref.water_flood(); port.water_flood(); hs.water_flood()
+    check("floods on the border")
