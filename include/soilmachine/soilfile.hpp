@@ -1,16 +1,21 @@
-// include/soilmachine/soilfile.hpp -- the `.soil` text format, restated from the reference loader
-// loadsoil() (source/io.h:7-230) including its quirks, because presets written for the reference must
-// produce the same tables here:
-//   * `#` starts a comment; only exactly-empty lines are skipped (io.h:43-47);
-//   * ONE SurfParam object is reused for all SOIL blocks and never reset, so a block inherits every field
-//     it does not set from the previous block (io.h:35);
-//   * soil ids are assigned in order of first mention - `TRANSPORTS X` before `SOIL X` pushes a placeholder
-//     copy of the current parameters (io.h:125-152); "Air" is id 0 (surface.h:41-57);
-//   * `}` on its own line stores the block (io.h:50-58); LAYER order = deposition order (io.h:88-109);
-//   * WORLD accepts only SIZEX SIZEY SCALE NWIND NWATER (io.h:208-220; a SEED line is ignored);
-//   * colours are six upper-case hex digits -> rgb/255, alpha 1 (io.h:23-33).
-// Errors throw SoilFileError instead of the reference's `cout + exit(0)`.
+// include/soilmachine/soilfile.hpp -- reader for the `.soil` preset format.
+//
+// Presets written for the reference (its loader is loadsoil(), source/io.h:7-230) must produce the same soil /
+// layer / world tables here, so the reader keeps that loader's observable behaviour:
+//   * everything from `#` to the end of a line is a comment; a line that is empty after that is skipped, any other
+//     line needs a space between keyword and value;
+//   * three block kinds, `SOIL <name> {`, `LAYER <name> {`, `WORLD {`, closed by a line holding only `}`;
+//   * soil ids are handed out in order of first mention (a cross reference such as `TRANSPORTS Sand` may come
+//     before `SOIL Sand {`); "Air" is id 0;
+//   * soil parameters carry over from one SOIL block to the next unless a block sets them (the reference edits
+//     one running record); LAYER blocks are kept in file order = deposition order;
+//   * unknown keywords inside a block are ignored (e.g. a `SEED` line inside WORLD);
+//   * colours are six hex digits 0-9A-F -> rgb/255, alpha 1.
+// The implementation is table-driven: one descriptor per keyword names the block it belongs to, how its value
+// is decoded and where the result is stored.  Errors throw SoilFileError (the reference prints and exits).
 #pragma once
+#include <cstddef>
+#include <cstring>
 #include <fstream>
 #include <map>
 #include <stdexcept>
@@ -23,7 +28,7 @@ struct SoilFileError : std::runtime_error {
   using std::runtime_error::runtime_error;
 };
 
-struct SoilEntry {            // SurfParam, surface.h:11-39
+struct SoilEntry {            // numeric + name fields of SurfParam, surface.h:11-39
   std::string name;
   float density = 0.0f, porosity = 0.0f;
   float color[4] = {0.5f, 0.5f, 0.5f, 1.0f};
@@ -47,118 +52,146 @@ struct SoilFile {
   WorldEntry world;
 };
 
-inline SoilEntry air_entry() {  // surface.h:43-49
+inline SoilEntry air_entry() {  // the built-in soil 0, surface.h:43-49
   SoilEntry a;
-  a.name = "Air"; a.density = 0.0f; a.porosity = 1.0f;
+  a.name = "Air";
+  a.porosity = 1.0f;
   a.color[0] = 0.0f; a.color[1] = 0.2f; a.color[2] = 0.4f; a.color[3] = 1.0f;
-  a.transports = 0; a.solubility = 0.0f; a.equrate = 0.0f; a.friction = 0.0f;
-  a.erodes = 0; a.erosionrate = 0.0f; a.cascades = 0; a.maxdiff = 0.0f; a.settling = 0.0f;
-  a.abrades = 0; a.suspension = 0.0f; a.abrasion = 0.0f;
+  a.solubility = a.equrate = a.friction = a.maxdiff = 0.0f;
   return a;
 }
 
-// io.h:7-230.  `out` may already hold tables (the reference appends to its globals); pass a fresh SoilFile
-// for the usual one-file case.
-inline void parse_soil_file(const std::string& file, SoilFile& out) {
-  std::ifstream in(file, std::ios::in);
-  if (!in.is_open()) throw SoilFileError("Failed to open soil profile " + file);
-  if (out.soils.empty()) { out.soils.push_back(air_entry()); out.soilmap["Air"] = 0; }
-  std::string line;
-  int linenr = 0;
-  auto syntaxerr = [&]() { throw SoilFileError("Incorrect Syntax in Line " + std::to_string(linenr) + " of " + file); };
-  auto hexcol = [&](const std::string& h, float* c) {
-    if (h.size() < 6) syntaxerr();
-    const std::string allowed = "0123456789ABCDEF";
-    for (char ch : h) if (allowed.find(ch) == std::string::npos) syntaxerr();
-    const float R = 16 * allowed.find(h[0]) + allowed.find(h[1]);
-    const float G = 16 * allowed.find(h[2]) + allowed.find(h[3]);
-    const float B = 16 * allowed.find(h[4]) + allowed.find(h[5]);
-    c[0] = R / 255.0f; c[1] = G / 255.0f; c[2] = B / 255.0f; c[3] = (float)255.0 / 255.0f;
+namespace soilfile_detail {
+
+enum Block { NONE, SOIL, LAYER, WORLD };
+enum Decode { F32, I32, SOILREF, HEXRGB };
+struct Key { const char* word; Block block; Decode decode; size_t offset; };
+
+#define SM_SOIL_KEY(word, decode, field) {word, SOIL, decode, offsetof(SoilEntry, field)}
+#define SM_LAYER_KEY(word, field) {word, LAYER, F32, offsetof(LayerEntry, field)}
+#define SM_WORLD_KEY(word, field) {word, WORLD, I32, offsetof(WorldEntry, field)}
+inline const Key* keys(size_t& n) {
+  static const Key table[] = {
+      SM_SOIL_KEY("TRANSPORTS", SOILREF, transports), SM_SOIL_KEY("ERODES", SOILREF, erodes),
+      SM_SOIL_KEY("CASCADES", SOILREF, cascades),     SM_SOIL_KEY("ABRADES", SOILREF, abrades),
+      SM_SOIL_KEY("DENSITY", F32, density),           SM_SOIL_KEY("POROSITY", F32, porosity),
+      SM_SOIL_KEY("COLOR", HEXRGB, color),            SM_SOIL_KEY("SOLUBILITY", F32, solubility),
+      SM_SOIL_KEY("EQUILIBRIUM", F32, equrate),       SM_SOIL_KEY("FRICTION", F32, friction),
+      SM_SOIL_KEY("EROSIONRATE", F32, erosionrate),   SM_SOIL_KEY("MAXDIFF", F32, maxdiff),
+      SM_SOIL_KEY("SETTLING", F32, settling),         SM_SOIL_KEY("SUSPENSION", F32, suspension),
+      SM_SOIL_KEY("ABRASION", F32, abrasion),
+      {"Ka", SOIL, F32, offsetof(SoilEntry, phong) + 0},  {"Kd", SOIL, F32, offsetof(SoilEntry, phong) + 4},
+      {"Ks", SOIL, F32, offsetof(SoilEntry, phong) + 8},  {"Kk", SOIL, F32, offsetof(SoilEntry, phong) + 12},
+      SM_LAYER_KEY("MIN", min),         SM_LAYER_KEY("BIAS", bias),   SM_LAYER_KEY("SCALE", scale),
+      SM_LAYER_KEY("OCTAVES", octaves), SM_LAYER_KEY("LACUNARITY", lacunarity), SM_LAYER_KEY("GAIN", gain),
+      SM_LAYER_KEY("FREQUENCY", frequency),
+      SM_WORLD_KEY("SIZEX", sizex), SM_WORLD_KEY("SIZEY", sizey), SM_WORLD_KEY("SCALE", scale),
+      SM_WORLD_KEY("NWIND", nwind), SM_WORLD_KEY("NWATER", nwater),
   };
-  auto mention = [&](const std::string& name, const SoilEntry& param) {   // id by first mention
-    if (!out.soilmap.count(name)) { out.soilmap[name] = (int)out.soils.size(); out.soils.push_back(param); }
-    return out.soilmap[name];
-  };
-  SoilEntry param;            // reused, never reset
+  n = sizeof(table) / sizeof(table[0]);
+  return table;
+}
+#undef SM_SOIL_KEY
+#undef SM_LAYER_KEY
+#undef SM_WORLD_KEY
+
+inline int hexdigit(char ch) {
+  if (ch >= '0' && ch <= '9') return ch - '0';
+  if (ch >= 'A' && ch <= 'F') return ch - 'A' + 10;
+  return -1;
+}
+
+struct Reader {
+  const std::string& file;
+  SoilFile& out;
+  SoilEntry running;          // the record every SOIL block edits; never reset between blocks
+  Block block = NONE;
   bool open = false;
-  std::string soillayer;
-  while (std::getline(in, line)) {
-    linenr++;
-    size_t found = line.find('#');
-    if (found != std::string::npos) line = line.substr(0, found);
-    if (line == "") continue;
-    if (line == "}") {
-      if (!open) syntaxerr();
-      if (soillayer == "SOIL") out.soils[out.soilmap[param.name]] = param;
-      open = false;
-      continue;
-    }
-    found = line.find(' ');
-    if (found == std::string::npos) syntaxerr();
-    const std::string tag = line.substr(0, found);
-    const std::string val = line.substr(found + 1);
-    if (tag == "SOIL") {
-      found = val.find('{');
-      if (found == std::string::npos) syntaxerr();
-      param.name = val.substr(0, found - 1);
-      mention(param.name, param);
-      soillayer = tag; open = true;
-      continue;
-    }
-    if (tag == "LAYER") {
-      found = val.find('{');
-      if (found == std::string::npos) syntaxerr();
-      param.name = val.substr(0, found - 1);
-      if (!out.soilmap.count(param.name)) syntaxerr();
-      LayerEntry l; l.type = out.soilmap[param.name];
-      out.layers.push_back(l);
-      soillayer = tag; open = true;
-      continue;
-    }
-    if (tag == "WORLD") {
-      if (val.find('{') == std::string::npos) syntaxerr();
-      soillayer = tag; open = true;
-      continue;
-    }
-    if (soillayer == "SOIL") {
-      if (tag == "TRANSPORTS") param.transports = mention(val, param);
-      if (tag == "ERODES") param.erodes = mention(val, param);
-      if (tag == "CASCADES") param.cascades = mention(val, param);
-      if (tag == "ABRADES") param.abrades = mention(val, param);
-      if (tag == "DENSITY") param.density = std::stof(val);
-      if (tag == "POROSITY") param.porosity = std::stof(val);
-      if (tag == "COLOR") hexcol(val, param.color);
-      if (tag == "SOLUBILITY") param.solubility = std::stof(val);
-      if (tag == "EQUILIBRIUM") param.equrate = std::stof(val);
-      if (tag == "FRICTION") param.friction = std::stof(val);
-      if (tag == "EROSIONRATE") param.erosionrate = std::stof(val);
-      if (tag == "MAXDIFF") param.maxdiff = std::stof(val);
-      if (tag == "SETTLING") param.settling = std::stof(val);
-      if (tag == "SUSPENSION") param.suspension = std::stof(val);
-      if (tag == "ABRASION") param.abrasion = std::stof(val);
-      if (tag == "Ka") param.phong[0] = std::stof(val);
-      if (tag == "Kd") param.phong[1] = std::stof(val);
-      if (tag == "Ks") param.phong[2] = std::stof(val);
-      if (tag == "Kk") param.phong[3] = std::stof(val);
-    }
-    if (soillayer == "LAYER") {
-      LayerEntry& l = out.layers.back();
-      if (tag == "MIN") l.min = std::stof(val);
-      if (tag == "BIAS") l.bias = std::stof(val);
-      if (tag == "SCALE") l.scale = std::stof(val);
-      if (tag == "OCTAVES") l.octaves = std::stof(val);
-      if (tag == "LACUNARITY") l.lacunarity = std::stof(val);
-      if (tag == "GAIN") l.gain = std::stof(val);
-      if (tag == "FREQUENCY") l.frequency = std::stof(val);
-    }
-    if (soillayer == "WORLD") {
-      if (tag == "SIZEX") out.world.sizex = std::stoi(val);
-      if (tag == "SIZEY") out.world.sizey = std::stoi(val);
-      if (tag == "SCALE") out.world.scale = std::stoi(val);
-      if (tag == "NWIND") out.world.nwind = std::stoi(val);
-      if (tag == "NWATER") out.world.nwater = std::stoi(val);
+  int lineno = 0;
+
+  [[noreturn]] void bad() const {
+    throw SoilFileError("Incorrect Syntax in Line " + std::to_string(lineno) + " of " + file);
+  }
+  int soil_id(const std::string& name) {   // first mention allocates the id (with the running record as a placeholder)
+    auto it = out.soilmap.find(name);
+    if (it != out.soilmap.end()) return it->second;
+    const int id = (int)out.soils.size();
+    out.soilmap.emplace(name, id);
+    out.soils.push_back(running);
+    return id;
+  }
+  // "<name> {" -> name (the character before the brace is the separating blank)
+  std::string header_name(const std::string& rest) const {
+    const size_t brace = rest.find('{');
+    if (brace == std::string::npos) bad();
+    return rest.substr(0, brace - 1);
+  }
+  void store(void* base, const Key& k, const std::string& value) {
+    char* dst = static_cast<char*>(base) + k.offset;
+    switch (k.decode) {
+      case F32: { const float v = std::stof(value); std::memcpy(dst, &v, sizeof v); break; }
+      case I32: { const int v = std::stoi(value); std::memcpy(dst, &v, sizeof v); break; }
+      case SOILREF: { const int v = soil_id(value); std::memcpy(dst, &v, sizeof v); break; }
+      case HEXRGB: {
+        if (value.size() < 6) bad();
+        for (char ch : value) if (hexdigit(ch) < 0) bad();
+        float rgba[4];
+        for (int c = 0; c < 3; c++) rgba[c] = (float)(16 * hexdigit(value[2 * c]) + hexdigit(value[2 * c + 1])) / 255.0f;
+        rgba[3] = 1.0f;
+        std::memcpy(dst, rgba, sizeof rgba);
+        break;
+      }
     }
   }
+  void line(std::string text) {
+    lineno++;
+    const size_t hash = text.find('#');
+    if (hash != std::string::npos) text.erase(hash);
+    if (text.empty()) return;
+    if (text == "}") {
+      if (!open) bad();
+      if (block == SOIL) out.soils[(size_t)out.soilmap[running.name]] = running;
+      open = false;
+      return;
+    }
+    const size_t blank = text.find(' ');
+    if (blank == std::string::npos) bad();
+    const std::string word = text.substr(0, blank), rest = text.substr(blank + 1);
+    if (word == "SOIL") {
+      running.name = header_name(rest);
+      soil_id(running.name);
+      block = SOIL; open = true;
+    } else if (word == "LAYER") {
+      running.name = header_name(rest);
+      auto it = out.soilmap.find(running.name);
+      if (it == out.soilmap.end()) bad();              // a layer must name a soil that exists already
+      LayerEntry l; l.type = it->second;
+      out.layers.push_back(l);
+      block = LAYER; open = true;
+    } else if (word == "WORLD") {
+      if (rest.find('{') == std::string::npos) bad();
+      block = WORLD; open = true;
+    } else {
+      void* base = block == SOIL ? (void*)&running : block == LAYER ? (void*)&out.layers.back()
+                 : block == WORLD ? (void*)&out.world : nullptr;
+      if (!base) return;
+      size_t n; const Key* k = keys(n);
+      for (size_t i = 0; i < n; i++)
+        if (k[i].block == block && word == k[i].word) { store(base, k[i], rest); break; }
+    }
+  }
+};
+
+}  // namespace soilfile_detail
+
+// Reads `file` into `out`.  `out` may already hold tables (further files append, as the reference's globals
+// do); pass a fresh SoilFile for the usual one-file case.
+inline void parse_soil_file(const std::string& file, SoilFile& out) {
+  std::ifstream in(file);
+  if (!in.is_open()) throw SoilFileError("Failed to open soil profile " + file);
+  if (out.soils.empty()) { out.soils.push_back(air_entry()); out.soilmap["Air"] = 0; }
+  soilfile_detail::Reader rd{file, out};
+  for (std::string text; std::getline(in, text);) rd.line(text);
 }
 
 }  // namespace soilmachine

@@ -19,6 +19,7 @@
 // convert implicitly from/to any type with .x/.y(/.z) members (so glm::ivec2 etc. can be passed).
 #pragma once
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <deque>
 #include <map>
@@ -167,7 +168,13 @@ class Layermap {
   template <class VP> void update(VP&) {}
   template <class VP> void slice(VP&, double = 0) {}
 
-  void ck(int rc) const { if (rc != SM_OK) throw Error(rc, sm_last_error(ctx)); }
+  // A full section pool is not fatal upstream: secpool::get prints and returns NULL, add() drops the section
+  // (layermap.h:92-95,232-234) and the program keeps running.  Same here: the drop is reported, the call
+  // counts it in stats.pool_drops, and the status is per call.
+  void ck(int rc) const {
+    if (rc == SM_ERR_POOL) { std::fprintf(stderr, "Memory Pool Out-Of-Elements (%s)\n", sm_last_error(ctx)); return; }
+    if (rc != SM_OK) throw Error(rc, sm_last_error(ctx));
+  }
   void push_tables() {
     std::vector<sm_soil> t;
     for (auto& s : soils) t.push_back(sm_soil{(int32_t)s.transports, (int32_t)s.erodes, (int32_t)s.cascades, (int32_t)s.abrades,

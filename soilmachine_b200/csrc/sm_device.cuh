@@ -85,7 +85,6 @@ struct DevCtx {
   unsigned int* done;            // tag of the last sweep this particle completed (0xFFFFFFFF = dead)
   unsigned int* fin;             // exact kernel: tag of the last sweep whose map writes are complete
   unsigned long long* mv;        // exact kernel: tag<<32 | npos.x<<16 | npos.y, published right after move()
-  unsigned long long* pstate;    // async kernel: tag<<32 | x<<18 | y<<4 | reach  (tag 0xFFFFFFFF = dead)
   unsigned long long* head[2];   // bin heads per sweep parity
   uint2* node[2];                // per particle: .x = next particle in the bin list, .y = ipos x<<16|y
   int nbx, nby;                  // allocated bin grid (for the smallest bin edge)

@@ -53,8 +53,8 @@ __device__ __forceinline__ int particle_reach(const WindP& p) {
 #ifndef SM_MINBLOCKS
 #define SM_MINBLOCKS 3  // resident blocks per SM the sweep kernels are compiled for (register cap)
 #endif
-#define SM_ASYNC_DELTA 4   // sweeps per super-step of the barrier-free wind kernel
 #define SM_SWEEPS_NONE 0x40000000   // internal: run the prologue only
+#define SM_DONE_FLOODED 0xFFFFFFFEu  // done[] of a dead particle whose flood() has run (0xFFFFFFFF = dead)
 
 // ---------------------------------------------------------------------------------------------
 // bins
@@ -782,257 +782,6 @@ __global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run_exact(DevCtx c, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_run_async: the sweep kernel without a grid barrier per sweep (used for wind batches).
-//
-// A wind batch is sparse (half the particles die at spawn, the rest drift for up to ~13 000 sweeps) and
-// almost never conflicts, but with one barrier per sweep every sweep costs (chain depth) x (slowest
-// step) for everybody.  Here a SUPER-STEP of DELTA sweeps runs between two grid barriers:
-//   * at its start every particle collects, from the bins, the ids of all particles that can come
-//     within conflict range during the super-step (Verlet list: |dipos| <= 10 + 6*(DELTA-1));
-//   * then each particle advances through its own sweeps.  Before executing sweep s it checks every
-//     candidate B's published state (last completed sweep, position, reach - ONE 64-bit word):
-//     all of B's steps that precede (s, A) in the canonical order - sweeps <= s for B < A, <= s-1
-//     for B > A - must either be complete, or be unable to reach A's footprint even if B moved
-//     3 cells per missing sweep.  The step with the smallest (sweep, index) is always ready, so
-//     there is no deadlock; steps whose footprints can meet are executed in canonical order, so the
-//     result is bit-identical to the lockstep order.
-// Requires one thread slot per particle (all particles resident).
-template <int KIND, int DELTA>
-__global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run_async(DevCtx c, int n, const float* __restrict__ spawn,
-                                                        int max_sweeps, int lshift) {
-  typedef typename PType<KIND>::T P;
-  __shared__ SoilDev s_soils[SM_MAX_SOILS];
-  __shared__ unsigned int s_alive;
-  extern __shared__ __align__(32) unsigned char s_win[];
-  for (int i = threadIdx.x; i < c.nsoils; i += blockDim.x) s_soils[i] = c.soils[i];
-  if (threadIdx.x == 0) s_alive = 0;
-  __syncthreads();
-  Sec32* my_win = (Sec32*)(s_win + (size_t)(threadIdx.x >> lshift) * SM_WIN_BYTES);
-
-  RunCtl* ctl = c.ctl;
-  unsigned int epoch = 0;
-  const unsigned int tag0 = ctl->tag_base;
-  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool leader = (gtid & ((1 << lshift) - 1)) == 0;
-  const int pid = gtid >> lshift;
-  const bool mine = leader && pid < n;
-  const int G = Reach<KIND>::G;
-  const int nbx = (c.dimx + G - 1) / G, nby = (c.dimy + G - 1) / G;
-  const unsigned long long DEAD = 0xFFFFFFFFull << 32;
-
-  unsigned long long n_steps = 0, n_oob = 0, n_evap = 0, n_stall = 0;
-  unsigned int last_sweep = 0;   // 1 + index of the last sweep this particle took part in
-  bool live = false;
-  P p;
-
-  // ---- prologue ----
-  if (mine) {
-    if (spawn != nullptr) {
-      DevAccess a(c, s_soils, 0u);
-      const float x = spawn[2 * pid], y = spawn[2 * pid + 1];
-      if (KIND == KIND_WATER) {
-        WaterP w{x, y, 0.0f, 0.0f, 1.0, 0.0, 0u};
-        w.contains = spawn_contains(a, x, y);
-        store_particle(c, pid, w);
-        live = true;
-      } else {
-        WindP w{x, y, -2.0f, 0.0f, 1.0f, 0.0, 0.0, 0u};
-        w.contains = spawn_contains(a, x, y);
-        store_particle(c, pid, w);
-        live = !(s_soils[w.contains].suspension == 0.0);   // wind.h:56-57
-        if (!live) { n_oob++; last_sweep = 1u; }           // it dies inside the first sweep
-      }
-      c.alive[pid] = live ? 1 : 0;
-    } else {
-      live = c.alive[pid] != 0;
-    }
-    load_particle(c, pid, p);
-    const int ix = (int)roundf(p.px), iy = (int)roundf(p.py);
-    const int R = particle_reach(p);
-    c.pstate[pid] = live ? (((unsigned long long)(tag0 - 1u) << 32) | SM_PACK_NODE(ix, iy, R)) : DEAD;
-    if (live) {
-      // super-step parity 0 bins, tagged tag0
-      const int b = (ix / G) * nby + (iy / G);
-      unsigned long long old = atomicExch(&c.head[0][b], ((unsigned long long)tag0 << 32) | (unsigned long long)(uint32_t)pid);
-      c.node[0][pid] = make_uint2(((unsigned int)(old >> 32) == tag0) ? (uint32_t)old : SM_NIL, SM_PACK_NODE(ix, iy, R));
-      atomicAdd(&s_alive, 1u);
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    if (s_alive) atomicAdd(&ctl->alive_slot[0], s_alive);
-    s_alive = 0;
-  }
-  grid_barrier(&ctl->barrier, epoch);
-
-  int swept = 0;                 // sweeps completed by the batch so far
-  unsigned int total_alive = 0;
-  for (int ss = 0;; ss++) {
-    const unsigned int S0 = tag0 + (unsigned int)swept;
-    total_alive = ld_volatile_u32(&ctl->alive_slot[ss % 3]);
-    int q = DELTA;
-    if (max_sweeps >= 0 && max_sweeps - swept < q) q = max_sweeps - swept;
-    if (total_alive == 0 || q <= 0) break;
-    if (gtid == 0) st_volatile_u32(&ctl->alive_slot[(ss + 2) % 3], 0u);
-    const unsigned int par = (unsigned int)ss & 1u;
-
-    // ---- candidates: everybody who can get within range during this super-step ----
-    const int K = 12;
-    uint32_t cand[K];
-    int ncand = 0;
-    bool overflow = false;
-    int ix = 0, iy = 0, myR = 0;
-    const int Rc = 2 * 5 + 2 * (q - 1) * Reach<KIND>::STEP;
-    const int nb = (Rc + G - 1) / G;
-    if (live) {
-      ix = (int)roundf(p.px); iy = (int)roundf(p.py); myR = particle_reach(p);
-#pragma unroll
-      for (int k = 0; k < K; k++) cand[k] = SM_NIL;
-      const int bx = ix / G, by = iy / G;
-      for (int cx = bx - nb; cx <= bx + nb; cx++) {
-        if (cx < 0 || cx >= nbx) continue;
-        for (int cy = by - nb; cy <= by + nb; cy++) {
-          if (cy < 0 || cy >= nby) continue;
-          const unsigned long long h = *((volatile unsigned long long*)&c.head[par][cx * nby + cy]);
-          if ((unsigned int)(h >> 32) != S0) continue;
-          uint32_t j = (uint32_t)h;
-          while (j != SM_NIL) {
-            const uint2 nd = c.node[par][j];
-            if (j != (uint32_t)pid) {
-              int dx = (int)(nd.y >> 18) - ix, dy = (int)((nd.y >> 4) & 0x3FFFu) - iy;
-              dx = dx < 0 ? -dx : dx; dy = dy < 0 ? -dy : dy;
-              if (dx <= Rc && dy <= Rc) {
-                if (ncand < K) {
-#pragma unroll
-                  for (int k = 0; k < K; k++) if (k == ncand) cand[k] = j;
-                  ncand++;
-                } else overflow = true;
-              }
-            }
-            j = nd.x;
-          }
-        }
-      }
-    }
-
-    // ---- this particle's sweeps S0 .. S0+q-1, in warp-converged rounds ----
-    unsigned int s = S0;
-    const unsigned int s_end = S0 + (unsigned int)q;
-    for (;;) {
-      const bool pending = live && (int)(s - s_end) < 0;
-      bool ready = false;
-      if (pending) {
-        ready = true;
-        // one candidate: are all of its steps that precede (s, pid) complete or out of reach?
-#define SM_CHECK_CAND(J)                                                                           \
-        {                                                                                          \
-          const unsigned long long st_ = *((volatile unsigned long long*)&c.pstate[J]);            \
-          const unsigned int prog_ = (unsigned int)(st_ >> 32);                                    \
-          const unsigned int smax_ = ((J) < (uint32_t)pid) ? s : s - 1u;                           \
-          if (prog_ != 0xFFFFFFFFu && (int)(prog_ - smax_) < 0) {                                  \
-            const int lag_ = (int)(smax_ - prog_) - 1;                                             \
-            const uint32_t w_ = (uint32_t)st_;                                                     \
-            int dx_ = (int)(w_ >> 18) - ix, dy_ = (int)((w_ >> 4) & 0x3FFFu) - iy;                 \
-            dx_ = dx_ < 0 ? -dx_ : dx_; dy_ = dy_ < 0 ? -dy_ : dy_;                                \
-            const int thr_ = myR + (lag_ == 0 ? (int)(w_ & 0xFu) : 5) + lag_ * Reach<KIND>::STEP;  \
-            if (dx_ <= thr_ && dy_ <= thr_) ready = false;                                         \
-          }                                                                                        \
-        }
-        if (!overflow) {
-#pragma unroll
-          for (int k = 0; k < K; k++) {
-            if (k < ncand) SM_CHECK_CAND(cand[k])
-          }
-        } else {
-          // crowded neighbourhood: enumerate the candidates from the (static) bins every time
-          const uint32_t w0 = c.node[par][pid].y;                        // my position at S0
-          const int ox = (int)(w0 >> 18), oy = (int)((w0 >> 4) & 0x3FFFu);
-          const int bx = ox / G, by = oy / G;
-          for (int cx = bx - nb; cx <= bx + nb && ready; cx++) {
-            if (cx < 0 || cx >= nbx) continue;
-            for (int cy = by - nb; cy <= by + nb && ready; cy++) {
-              if (cy < 0 || cy >= nby) continue;
-              const unsigned long long h = *((volatile unsigned long long*)&c.head[par][cx * nby + cy]);
-              if ((unsigned int)(h >> 32) != S0) continue;
-              uint32_t j = (uint32_t)h;
-              while (j != SM_NIL && ready) {
-                const uint2 nd = c.node[par][j];
-                if (j != (uint32_t)pid) {
-                  int dx = (int)(nd.y >> 18) - ox, dy = (int)((nd.y >> 4) & 0x3FFFu) - oy;
-                  dx = dx < 0 ? -dx : dx; dy = dy < 0 ? -dy : dy;
-                  if (dx <= Rc && dy <= Rc) SM_CHECK_CAND(j)
-                }
-                j = nd.x;
-              }
-            }
-          }
-        }
-#undef SM_CHECK_CAND
-      }
-      if (__ballot_sync(0xffffffffu, pending) == 0u) break;
-      if (__ballot_sync(0xffffffffu, ready) == 0u) { __nanosleep(32); continue; }
-      if (ready) {
-        __threadfence();
-        WinAccess<KIND> a(c, s_soils, (unsigned int)ss, my_win);
-        const int r = do_step(a, p);
-        a.flush();
-        store_particle(c, pid, p);
-        last_sweep = (s - tag0) + 1u;
-        unsigned long long st;
-        if (r == SM_ALIVE) {
-          n_steps++;
-          const int jx = (int)roundf(p.px), jy = (int)roundf(p.py);
-          int ddx = jx - ix, ddy = jy - iy;
-          ddx = ddx < 0 ? -ddx : ddx; ddy = ddy < 0 ? -ddy : ddy;
-          const int lim = myR - Reach<KIND>::RING;
-          if (ddx > lim || ddy > lim) atomicOr(&ctl->err, 1u << 4);   // SM_ERR_REACH
-          ix = jx; iy = jy; myR = particle_reach(p);
-          st = ((unsigned long long)s << 32) | SM_PACK_NODE(ix, iy, myR);
-        } else {
-          live = false;
-          c.alive[pid] = 0;
-          if (r == SM_EXIT_OOB) n_oob++;
-          else if (r == SM_EXIT_STALL) n_stall++;
-          else { n_steps++; n_evap++; }
-          st = DEAD;
-        }
-        __threadfence();
-        *((volatile unsigned long long*)&c.pstate[pid]) = st;
-        s++;
-      }
-      __syncwarp();
-    }
-
-    // ---- end of super-step: bins for the next one, survivors, barrier ----
-    swept += q;
-    if (live) {
-      const unsigned int tagn = tag0 + (unsigned int)swept;
-      const int b = (ix / G) * nby + (iy / G);
-      unsigned long long old = atomicExch(&c.head[par ^ 1u][b], ((unsigned long long)tagn << 32) | (unsigned long long)(uint32_t)pid);
-      c.node[par ^ 1u][pid] = make_uint2(((unsigned int)(old >> 32) == tagn) ? (uint32_t)old : SM_NIL, SM_PACK_NODE(ix, iy, myR));
-      atomicAdd(&s_alive, 1u);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      if (s_alive) atomicAdd(&ctl->alive_slot[(ss + 1) % 3], s_alive);
-      s_alive = 0;
-    }
-    grid_barrier(&ctl->barrier, epoch);
-  }
-
-  // ---- epilogue ----
-  if (n_steps) atomicAdd(&ctl->steps, n_steps);
-  if (n_oob) atomicAdd(&ctl->exit_oob, n_oob);
-  if (n_evap) atomicAdd(&ctl->exit_evap, n_evap);
-  if (n_stall) atomicAdd(&ctl->exit_stall, n_stall);
-  if (last_sweep) atomicMax(&ctl->sweeps, (unsigned long long)last_sweep);
-  if (gtid == 0) {
-    ctl->alive = total_alive;
-    ctl->tag_base = tag0 + (unsigned int)swept + 2u;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 // full-grid and utility kernels
 // ---------------------------------------------------------------------------------------------
 // mapfrequency + resetfrequency, water.h:353-365 (one fused pass: 16 B per cell)
@@ -1329,7 +1078,9 @@ __global__ void __launch_bounds__(32) k_hydro_flood(DevCtx c, int n, HydroCount*
   for (int base = 0; base < n; base += 32) {
     const int i = base + lane;
     bool cand = false;
-    if (i < n) cand = (c.alive[i] == 0) && !(c.pb[i].x < SM_MINVOL);
+    // a particle floods exactly once (upstream: flood() ends the particle): flooded ones carry a marker
+    // in their `done` word, so a repeated call or flood -> more sweeps -> flood never deposits twice
+    if (i < n) cand = (c.alive[i] == 0) && !(c.pb[i].x < SM_MINVOL) && c.done[i] != SM_DONE_FLOODED;
     unsigned int m = __ballot_sync(0xFFFFFFFFu, cand);
     if (lane == 0) {
       while (m) {
@@ -1341,6 +1092,7 @@ __global__ void __launch_bounds__(32) k_hydro_flood(DevCtx c, int n, HydroCount*
         p.px = pa.x; p.py = pa.y; p.sx = pa.z; p.sy = pa.w;
         p.volume = pb.x; p.sediment = pb.y; p.contains = c.pc[j].x;
         hydro_flood_particle(a, p, hc);
+        c.done[j] = SM_DONE_FLOODED;
       }
     }
     __syncwarp();
@@ -1470,7 +1222,7 @@ void sm_destroy(sm_context* ctx) {
   DevCtx& d = ctx->d;
   cudaFree(d.top); cudaFree(d.pool); cudaFree(d.ringbuf[0]); cudaFree(d.ringbuf[1]);
   cudaFree(d.wfreq); cudaFree(d.wtrack); cudaFree(d.windfreq); cudaFree(ctx->d_soils);
-  cudaFree(d.ctl); cudaFree(d.pa); cudaFree(d.pb); cudaFree(d.pc); cudaFree(d.alive); cudaFree(d.done); cudaFree(d.pstate); cudaFree(d.fin); cudaFree(d.mv);
+  cudaFree(d.ctl); cudaFree(d.pa); cudaFree(d.pb); cudaFree(d.pc); cudaFree(d.alive); cudaFree(d.done); cudaFree(d.fin); cudaFree(d.mv);
   for (int i = 0; i < 2; i++) { cudaFree(d.head[i]); cudaFree(d.node[i]); }
   cudaFree(ctx->d_verts); cudaFree(ctx->d_colors); cudaFree(d.dbg);
   cudaFree(ctx->d_act); cudaFree(ctx->d_hydro);
@@ -1547,7 +1299,7 @@ static int create_impl(const sm_config* cfg, int nranks, int rank, int share, sm
     CK(cudaMalloc(&d.ctl, sizeof(RunCtl)));
     CK(cudaMemsetAsync(d.ctl, 0, sizeof(RunCtl), ctx->stream));
     CK(cudaMalloc(&d.pa, N * sizeof(float4))); CK(cudaMalloc(&d.pb, N * sizeof(double2)));
-    CK(cudaMalloc(&d.pc, N * sizeof(uint2))); CK(cudaMalloc(&d.alive, N)); CK(cudaMalloc(&d.done, N * 4)); CK(cudaMalloc(&d.pstate, N * 8));
+    CK(cudaMalloc(&d.pc, N * sizeof(uint2))); CK(cudaMalloc(&d.alive, N)); CK(cudaMalloc(&d.done, N * 4));
     CK(cudaMalloc(&d.fin, N * 4)); CK(cudaMalloc(&d.mv, N * 8));
     CK(cudaMemsetAsync(d.fin, 0, N * 4, ctx->stream)); CK(cudaMemsetAsync(d.mv, 0, N * 8, ctx->stream));
     d.nbx = (cfg->dimx + SM_MIN_BIN - 1) / SM_MIN_BIN; d.nby = (cfg->dimy + SM_MIN_BIN - 1) / SM_MIN_BIN;
@@ -1583,7 +1335,6 @@ static int create_impl(const sm_config* cfg, int nranks, int rank, int share, sm
     CK(cudaFuncSetAttribute(k_run_exact<KIND_WATER>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BLOCK * (SM_WIN_BYTES + SM_KX * 4)));
     CK(cudaFuncSetAttribute(k_run_exact<KIND_WIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BLOCK * (SM_WIN_BYTES + SM_KX * 4)));
     CK(cudaFuncSetAttribute(k_run<KIND_WIND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BLOCK * SM_WIN_BYTES));
-    CK(cudaFuncSetAttribute(k_run_async<KIND_WIND, SM_ASYNC_DELTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_BLOCK * SM_WIN_BYTES));
     CK(cudaStreamSynchronize(ctx->stream));
     return SM_OK;
   }();
@@ -1971,21 +1722,6 @@ static int launch_run(sm_context* ctx, int kind, int n, const float* d_spawn, in
       }
     }
   }
-  // wind: barrier-free super-steps when every particle can own a thread slot
-  bool use_async = false;
-  if (kind == KIND_WIND && !multi && !use_exact) {
-    // measured on config 3: 780 ms vs 650 ms for the per-sweep-barrier kernel - the clusters that
-    // bound a sweep are persistent (neighbouring particles alternate every sweep), so removing the
-    // barrier does not shorten the critical path.  Kept as an opt-in (SM_ASYNC=1).
-    const char* e = getenv("SM_ASYNC");
-    if (e && atoi(e) == 1) {
-      int occ = 0;
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_run_async<KIND_WIND, SM_ASYNC_DELTA>, threads, smem));
-      const long long need_threads = (long long)std::max(n, 1) << lshift;
-      const long long nb_ = (need_threads + threads - 1) / threads;
-      if (occ >= 1 && nb_ <= (long long)ctx->num_sms * occ) { use_async = true; blocks = (int)std::max<long long>(nb_, 1); }
-    }
-  }
   DevCtx d = ctx->d;
   if (max_sweeps <= 0) max_sweeps = -1;            // run until every particle is dead
   if (max_sweeps == SM_SWEEPS_NONE) max_sweeps = 0;  // prologue only (the *_begin calls)
@@ -2002,8 +1738,6 @@ static int launch_run(sm_context* ctx, int kind, int n, const float* d_spawn, in
     CK(cudaLaunchCooperativeKernel((void*)k_run_exact<KIND_WIND>, dim3(blocks), dim3(threads), args, smem, ctx->stream));
   else if (kind == KIND_WATER)
     CK(cudaLaunchCooperativeKernel((void*)k_run<KIND_WATER, false>, dim3(blocks), dim3(threads), args, smem, ctx->stream));
-  else if (use_async)
-    CK(cudaLaunchCooperativeKernel((void*)k_run_async<KIND_WIND, SM_ASYNC_DELTA>, dim3(blocks), dim3(threads), args, smem, ctx->stream));
   else
     CK(cudaLaunchCooperativeKernel((void*)k_run<KIND_WIND, false>, dim3(blocks), dim3(threads), args, smem, ctx->stream));
   CK(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -2013,8 +1747,11 @@ static int launch_run(sm_context* ctx, int kind, int n, const float* d_spawn, in
 }
 
 static int zero_counters(sm_context* ctx) {
-  // steps..alive are contiguous in RunCtl
+  // steps..alive are contiguous in RunCtl.  The error bits are per call as well: a pool exhaustion or a reach
+  // violation is reported by the call it happened in (stats.pool_drops says how many sections were dropped)
+  // and does not poison later calls - upstream prints and keeps running (layermap.h:92-95).
   CK(cudaMemsetAsync(&ctx->d.ctl->steps, 0, 7 * sizeof(unsigned long long), ctx->stream));
+  CK(cudaMemsetAsync(&ctx->d.ctl->err, 0, sizeof(unsigned int), ctx->stream));
   return SM_OK;
 }
 
@@ -2079,6 +1816,9 @@ static int hydro_ready(sm_context* ctx) {
     CK(cudaFuncSetAttribute(k_hydro_flood, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_HC_BYTES));
     CK(cudaFuncSetAttribute(k_hydro_seep, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_HC_BYTES));
   }
+  // status and drop counter are per call (see zero_counters)
+  CK(cudaMemsetAsync(&ctx->d.ctl->err, 0, sizeof(unsigned int), ctx->stream));
+  CK(cudaMemsetAsync(&ctx->d.ctl->drops, 0, sizeof(unsigned long long), ctx->stream));
   return SM_OK;
 }
 static int hydro_finish(sm_context* ctx, sm_hydro_stats* st) {
