@@ -9,6 +9,7 @@
 #include "../../soilmachine_b200/csrc/sm_core.cuh"
 #include "../../soilmachine_b200/csrc/sm_noise.cuh"
 #include "../../soilmachine_b200/csrc/sm_hydro.cuh"
+#include "../../soilmachine_b200/csrc/sm_coop.cuh"
 
 namespace {
 struct HostMap {
@@ -51,6 +52,46 @@ struct HostAccess {
   float water_frequency(int ind) { return M.wfreq[ind]; }
   void wind_frequency_touch(int ind) { M.windfreq[ind] = (float)(0.5 * M.windfreq[ind] + 0.5f); }
 };
+
+// ---- the warp-cooperative step (sm_coop.cuh) on the host: lanes become loops ---------------------------
+// each()/ballot() run the lanes one after the other; the code keeps to "a lane writes only its own slots and
+// reads only what earlier phases wrote", so the order of the lanes cannot matter.  G_lane_order reverses it
+// to let the tests check exactly that.
+int G_lane_order = 0;
+struct WarpHost {
+  template <class F> void each(int n, F f) {
+    if (G_lane_order == 0) for (int l = 0; l < n; l++) f(l);
+    else for (int l = n - 1; l >= 0; l--) f(l);
+  }
+  template <class F> unsigned int ballot(int n, F f) {
+    unsigned int m = 0;
+    if (G_lane_order == 0) { for (int l = 0; l < n; l++) if (f(l)) m |= 1u << l; }
+    else { for (int l = n - 1; l >= 0; l--) if (f(l)) m |= 1u << l; }
+    return m;
+  }
+  template <class F> void one(F f) { f(); }
+  bool lead() const { return true; }
+};
+struct HostBack {   // backing store of CoopWin on the host
+  HostAccess h;
+  int dimx() const { return M.dimx; }
+  int dimy() const { return M.dimy; }
+  int scale() const { return M.scale; }
+  const SoilDev* soilp(uint32_t t) const { return &M.soils[t]; }
+  Sec32* cell_ptr(int x, int y) { return &M.top[(size_t)x * M.dimy + y]; }
+  void focus(int, int) {}
+  Sec32 pool_load(uint32_t i) { return h.pool_load(i); }
+  void pool_store(uint32_t i, const Sec32& r) { h.pool_store(i, r); }
+  uint32_t pool_alloc() { return h.pool_alloc(); }
+  void pool_free(uint32_t i) { h.pool_free(i); }
+  float wfreq(int i) const { return M.wfreq[i]; }
+  float wtrack(int i) const { return M.wtrack[i]; }
+  float windfreq(int i) const { return M.windfreq[i]; }
+  void set_wtrack(int i, float v) { M.wtrack[i] = v; }
+  void set_windfreq(int i, float v) { M.windfreq[i] = v; }
+  void note_transfer() {}
+};
+int G_coop = 0;   // 1: the sweeps below run the warp-cooperative step
 
 struct Stats { int64_t steps, sweeps, exit_oob, exit_evap, exit_stall; double seconds; };
 std::vector<WaterP> W; std::vector<int> Wlive;
@@ -122,6 +163,7 @@ void hs_add(int x, int y, double s, int t) { HostAccess a; col_add(a, *a.rec(x, 
 double hs_remove(int x, int y, double h) { HostAccess a; return col_remove(a, *a.rec(x, y), h); }
 void hs_cascade(float x, float y, int loop) { HostAccess a; Cascade<3, HostAccess>::run(a, (int)roundf(x), (int)roundf(y), loop); }
 
+void hs_set_mode(int coop, int lane_order) { G_coop = coop; G_lane_order = lane_order; }
 void hs_water_begin(int n, const float* xy) {
   HostAccess a; W.clear(); Wlive.clear();
   for (int i = 0; i < n; i++) {
@@ -133,7 +175,12 @@ void hs_water_begin(int n, const float* xy) {
 int hs_water_sweep(Stats* st) {
   HostAccess a; std::vector<int> next;
   for (int i : Wlive) {
-    int r = water_step(a, W[i]);
+    int r;
+    if (G_coop) {
+      WarpHost w; HostBack b; CoopScratch sc; CoopWin<HostBack> cw(b, &sc);
+      r = water_step_coop(w, cw, W[i]);
+      cw.flush(w);
+    } else r = water_step(a, W[i]);
     if (r == SM_EXIT_OOB) { st->exit_oob++; continue; }
     if (r == SM_EXIT_STALL) { st->exit_stall++; continue; }
     st->steps++;
@@ -161,7 +208,12 @@ void hs_wind_begin(int n, const float* xy) {
 int hs_wind_sweep(Stats* st) {
   HostAccess a; std::vector<int> next;
   for (int i : Dlive) {
-    int r = wind_step(a, D[i]);
+    int r;
+    if (G_coop) {
+      WarpHost w; HostBack b; CoopScratch sc; CoopWin<HostBack> cw(b, &sc);
+      r = wind_step_coop(w, cw, D[i]);
+      cw.flush(w);
+    } else r = wind_step(a, D[i]);
     if (r != SM_ALIVE) { st->exit_oob++; continue; }
     st->steps++;
     next.push_back(i);

@@ -65,6 +65,22 @@ def test_product_arithmetic_replays_golden_frame(case):
 
 
 @pytest.mark.parametrize("case", _golden.FRAME_CASES)
+@pytest.mark.parametrize("lane_order", [0, 1], ids=["lanes_up", "lanes_down"])
+def test_warp_cooperative_step_replays_golden_frame(case, lane_order):
+    """sm_coop.cuh - the step as the sweep kernel's warps execute it (lane-parallel gathers and cascade
+    evaluation, single-lane commits, staged 3x3 windows with write-back) - with the lanes run as loops on the
+    host.  Both lane orders must reproduce the reference: inside a phase no lane may depend on another."""
+    g = _golden.load(case)
+    b = Backend(g)
+    b.hs.lib.hs_set_mode(1, lane_order)
+    try:
+        b.hs.set_columns(_golden.cols(g, "init"))
+        _golden.replay_frame(g, b, stats5)
+    finally:
+        b.hs.lib.hs_set_mode(0, 0)
+
+
+@pytest.mark.parametrize("case", _golden.FRAME_CASES)
 def test_product_noise_reproduces_initial_terrain(case):
     """sm_noise.cuh (OpenSimplex2/FBm restatement) == Layermap::initialize of the reference."""
     g = _golden.load(case)
