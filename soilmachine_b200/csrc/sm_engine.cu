@@ -68,8 +68,9 @@ __device__ __forceinline__ void bin_insert(const DevCtx& c, unsigned int tag, in
   const int b = (ix / G) * nby + (iy / G);
   unsigned long long* head = MULTI ? c.peer[q].head[par] : c.head[par];
   uint2* node = MULTI ? c.peer[q].node[par] : c.node[par];
-  unsigned long long old =
-      atomicExch(&head[b], ((unsigned long long)tag << 32) | (unsigned long long)(uint32_t)pid);
+  // a sharded map's bin heads are also updated from other GPUs (particles handed over): system scope
+  const unsigned long long ent = ((unsigned long long)tag << 32) | (unsigned long long)(uint32_t)pid;
+  unsigned long long old = MULTI ? atomicExch_system(&head[b], ent) : atomicExch(&head[b], ent);
   node[pid] = make_uint2(((unsigned int)(old >> 32) == tag) ? (uint32_t)old : SM_NIL, SM_PACK_NODE(ix, iy, R));
 }
 
@@ -197,6 +198,8 @@ template <> struct PType<KIND_WIND> { typedef WindP T; };
 
 template <class A> __device__ __forceinline__ int do_step(A& a, WaterP& p) { return water_step(a, p); }
 template <class A> __device__ __forceinline__ int do_step(A& a, WindP& p) { return wind_step(a, p); }
+
+#include "sm_sweep.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // the persistent sweep kernel
@@ -1721,6 +1724,37 @@ static int launch_run(sm_context* ctx, int kind, int n, const float* d_spawn, in
         if (ls == 0) break;
       }
     }
+  }
+  // default: the warp-per-particle kernel (sm_sweep.cuh).  SM_KERNEL=thread selects the thread-per-particle
+  // kernels above (kept for comparison measurements).
+  bool use_coop = true;
+  {
+    const char* e = getenv("SM_KERNEL");
+    if (e && strcmp(e, "thread") == 0) use_coop = false;
+  }
+  if (use_coop) {
+    const int cthreads = SM_SW_WARPS * 32;
+    int occ = 0;
+    void* fn = multi ? (kind == KIND_WATER ? (void*)k_sweep<KIND_WATER, true> : (void*)k_sweep<KIND_WIND, true>)
+                     : (kind == KIND_WATER ? (void*)k_sweep<KIND_WATER, false> : (void*)k_sweep<KIND_WIND, false>);
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)fn, cthreads, 0));
+    if (occ < 1) return fail(ctx, SM_ERR_CUDA, "sweep kernel does not fit an SM");
+    // contexts that share the device must all be resident at once (they meet in the cross-rank barrier)
+    const long long maxblocks = std::max<long long>(1, (long long)ctx->num_sms * occ / ctx->share);
+    const long long want = ((long long)std::max(n, 1) + SM_SW_WARPS - 1) / SM_SW_WARPS;
+    const int cblocks = (int)std::max<long long>(1, std::min(maxblocks, want));
+    DevCtx dd = ctx->d;
+    int ms = max_sweeps;
+    if (ms <= 0) ms = -1;
+    if (max_sweeps == SM_SWEEPS_NONE) ms = 0;
+    void* cargs[] = {&dd, &n, (void*)&d_spawn, &ms};
+    CK(cudaMemsetAsync(ctx->d.ctl, 0, 4 * sizeof(unsigned int), ctx->stream));  // barrier + alive_slot[3]
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(cudaLaunchCooperativeKernel(fn, dim3(cblocks), dim3(cthreads), cargs, 0, ctx->stream));
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->launches++;
+    ctx->timing_pending = true;
+    return SM_OK;
   }
   DevCtx d = ctx->d;
   if (max_sweeps <= 0) max_sweeps = -1;            // run until every particle is dead

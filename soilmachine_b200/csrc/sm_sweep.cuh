@@ -1,0 +1,366 @@
+// sm_sweep.cuh -- k_sweep<KIND, MULTI>: the persistent sweep kernel with ONE WARP PER PARTICLE.
+//
+// Same contract as before (one cooperative launch per batch, one grid barrier per sweep, every live particle
+// executes move() && interact() once per sweep, overlapping steps ordered by ascending particle index, results
+// bit-identical to the reference driven in lockstep), different mapping: a particle owns a whole warp for the
+// duration of its step and the step itself is lane-parallel (sm_coop.cuh).  What that buys:
+//   * the dependent chain of one step is several times shorter (gathers, cascade evaluation and write-back are
+//     spread over the lanes), and a sweep lasts as long as its longest chain of dependent steps;
+//   * particles never share a warp, so a ready particle never waits for a neighbour lane's step and divergent
+//     steps do not serialise each other;
+//   * conflict detection and the wait are lane-parallel too: nine lanes walk the nine bins around the particle,
+//     up to 32 blockers are polled at once.
+// Included by sm_engine.cu after the bin / particle-I/O helpers.
+#pragma once
+#include "sm_coop.cuh"
+
+#ifndef SM_SW_WARPS
+#define SM_SW_WARPS 8        // warps (= particles in flight) per block
+#endif
+#ifndef SM_SW_MINBLOCKS
+#define SM_SW_MINBLOCKS 3    // resident blocks per SM the kernel is compiled for (register cap)
+#endif
+#define SM_SW_NEAR 31        // in-range lower-index particles tracked exactly (one polling lane each)
+
+// warp policy of sm_coop.cuh on the device.  Every primitive is a full-warp synchronisation point on both
+// sides: __syncwarp() orders the memory accesses of the participating lanes, so what lanes wrote before a
+// phase is visible inside it and what the phase wrote is visible after it.
+struct WarpDev {
+  int lane;
+  template <class F> __device__ __forceinline__ void each(int n, F f) {
+    __syncwarp();
+    if (lane < n) f(lane);
+    __syncwarp();
+  }
+  template <class F> __device__ __forceinline__ unsigned int ballot(int n, F f) {
+    __syncwarp();
+    bool v = false;
+    if (lane < n) v = f(lane);
+    const unsigned int m = __ballot_sync(0xffffffffu, v);
+    __syncwarp();
+    return m;
+  }
+  template <class F> __device__ __forceinline__ void one(F f) {
+    __syncwarp();
+    if (lane == 0) f();
+    __syncwarp();
+  }
+  __device__ __forceinline__ bool lead() const { return lane == 0; }
+};
+
+// backing store of CoopWin on the device
+template <bool MULTI> struct DevBack {
+  const DevCtx& c;
+  const SoilDev* s_soils;   // shared-memory copy of the soil table
+  unsigned int phase;       // sweep parity for the pool rings
+  int cur_q;                // owner rank of the column the next col_* call works on
+  __device__ __forceinline__ DevBack(const DevCtx& ctx, const SoilDev* ss, unsigned int ph)
+      : c(ctx), s_soils(ss), phase(ph & 1u), cur_q(0) {}
+  __device__ __forceinline__ int dimx() const { return c.dimx; }
+  __device__ __forceinline__ int dimy() const { return c.dimy; }
+  __device__ __forceinline__ int scale() const { return c.scale; }
+  __device__ __forceinline__ const SoilDev* soilp(uint32_t t) const { return &s_soils[t]; }
+  __device__ __forceinline__ Sec32* cell_ptr(int x, int y) const { return ::cell_ptr<MULTI>(c, x, y); }
+  __device__ __forceinline__ void focus(int x, int) { if (MULTI) cur_q = owner_of_x<true>(c, x); }
+  __device__ __forceinline__ Sec32 pool_load(uint32_t i) { return MULTI ? c.peer[cur_q].pool[i] : c.pool[i]; }
+  __device__ __forceinline__ void pool_store(uint32_t i, const Sec32& r) {
+    if (MULTI) c.peer[cur_q].pool[i] = r; else c.pool[i] = r;
+  }
+  // ticket pop from the ring filled during the previous sweep, else bump allocation;
+  // on a sharded map the column's owner holds the pool, and its counters may live on another GPU
+  __device__ uint32_t pool_alloc() {
+    RunCtl* const ctl = MULTI ? c.peer[cur_q].ctl : c.ctl;
+    uint32_t* const ring = MULTI ? c.peer[cur_q].ringbuf[phase ^ 1u] : c.ringbuf[phase ^ 1u];
+    const unsigned long long cap = MULTI ? c.peer[cur_q].pool_cap : c.pool_cap;
+    PoolRing* R = &ctl->ring[phase ^ 1u];
+    const unsigned long long t = *((volatile unsigned long long*)&R->tail);
+    if (*((volatile unsigned long long*)&R->head) < t) {
+      const unsigned long long h = MULTI ? atomicAdd_system(&R->head, 1ull) : atomicAdd(&R->head, 1ull);
+      if (h < t) return ring[h % cap];
+      if (MULTI) atomicMin_system(&R->head, t); else atomicMin(&R->head, t);
+    }
+    const unsigned long long bmp = MULTI ? atomicAdd_system(&ctl->bump, 1ull) : atomicAdd(&ctl->bump, 1ull);
+    if (bmp < cap) return (uint32_t)bmp;
+    atomicOr(&c.ctl->err, 1u << 3);   // SM_ERR_POOL
+    atomicAdd(&c.ctl->drops, 1ull);
+    return SM_NIL;
+  }
+  __device__ void pool_free(uint32_t i) {
+    RunCtl* const ctl = MULTI ? c.peer[cur_q].ctl : c.ctl;
+    uint32_t* const ring = MULTI ? c.peer[cur_q].ringbuf[phase] : c.ringbuf[phase];
+    const unsigned long long cap = MULTI ? c.peer[cur_q].pool_cap : c.pool_cap;
+    PoolRing* R = &ctl->ring[phase];
+    const unsigned long long t = MULTI ? atomicAdd_system(&R->tail, 1ull) : atomicAdd(&R->tail, 1ull);
+    ring[t % cap] = i;
+  }
+  __device__ __forceinline__ float wfreq(int i) const { return c.wfreq[i]; }
+  __device__ __forceinline__ float wtrack(int i) const { return c.wtrack[i]; }
+  __device__ __forceinline__ float windfreq(int i) const { return c.windfreq[i]; }
+  __device__ __forceinline__ void set_wtrack(int i, float v) { c.wtrack[i] = v; }
+  __device__ __forceinline__ void set_windfreq(int i, float v) { c.windfreq[i] = v; }
+  __device__ __forceinline__ void note_transfer() {}
+};
+
+struct __align__(32) WarpSmem {
+  CoopScratch cs;
+  uint32_t blk[32];      // in-range lower-index particles of this sweep (rank in bits 28-31 on a sharded map)
+  uint32_t pred[12];     // per-bin predecessors (largest lower index in each of the 3x3 bins)
+  uint32_t cnt;
+  uint32_t pad_[3];
+};
+
+template <class W, class A> __device__ __forceinline__ int do_step_coop(W& w, A& a, WaterP& p) { return water_step_coop(w, a, p); }
+template <class W, class A> __device__ __forceinline__ int do_step_coop(W& w, A& a, WindP& p) { return wind_step_coop(w, a, p); }
+
+// Conflict detection for one particle and one sweep, nine lanes = the 3x3 bins around ipos.  Two steps are
+// ordered iff their published boxes can meet (|dipos|_inf <= R_A + R_B).  Sparse case: every lower-index
+// particle in range gets a polling lane, plus the own-bin predecessor.  Crowded case (more than SM_SW_NEAR in
+// range): the nine per-bin predecessors.  Every particle always waits for its own-bin predecessor, hence
+// "X done => every lower index in X's bin done", which makes the per-bin predecessors a complete (conservative)
+// blocker set however large the cluster is.  Returns this lane's wait target (SM_NIL = none).
+template <int KIND, bool MULTI>
+__device__ __forceinline__ uint32_t coop_scan(const DevCtx& c, WarpSmem& ws, int lane, unsigned int tag, int pid, int ix,
+                                              int iy, int R) {
+  const unsigned int par = tag & 1u;
+  const int G = Reach<KIND>::G;
+  const int nbx = (c.dimx + G - 1) / G, nby = (c.dimy + G - 1) / G;
+  if (lane == 0) ws.cnt = 0;
+  __syncwarp();
+  if (lane < 9) {
+    const int cx = ix / G + lane / 3 - 1, cy = iy / G + lane % 3 - 1;
+    uint32_t best = SM_NIL;
+    if (cx >= 0 && cx < nbx && cy >= 0 && cy < nby) {
+      const int bq = MULTI ? owner_of_x<MULTI>(c, cx * G) : 0;
+      const unsigned long long* hp = MULTI ? c.peer[bq].head[par] : c.head[par];
+      const unsigned long long h = *((volatile const unsigned long long*)&hp[cx * nby + cy]);
+      if ((unsigned int)(h >> 32) == tag) {
+        const uint2* nodes = MULTI ? c.peer[bq].node[par] : c.node[par];
+        const uint32_t qtag = MULTI ? ((uint32_t)bq << 28) : 0u;
+        uint32_t j = (uint32_t)h;
+        while (j != SM_NIL) {
+          const uint2 nd = nodes[j];
+          if (j < (uint32_t)pid) {
+            if (best == SM_NIL || (j | qtag) > best) best = j | qtag;
+            int dx = (int)(nd.y >> 18) - ix, dy = (int)((nd.y >> 4) & 0x3FFFu) - iy;
+            const int D = R + (int)(nd.y & 0xFu);
+            dx = dx < 0 ? -dx : dx;
+            dy = dy < 0 ? -dy : dy;
+            if (dx <= D && dy <= D) {
+              const unsigned int at = atomicAdd(&ws.cnt, 1u);
+              if (at < SM_SW_NEAR) ws.blk[at] = j | qtag;
+            }
+          }
+          j = nd.x;
+        }
+      }
+    }
+    ws.pred[lane] = best;
+  }
+  __syncwarp();
+  const unsigned int cnt = ws.cnt;
+  if (cnt <= SM_SW_NEAR) {
+    if (lane < (int)cnt) return ws.blk[lane];
+    if (lane == 31) return ws.pred[4];
+    return SM_NIL;
+  }
+  return lane < 9 ? ws.pred[lane] : SM_NIL;
+}
+
+// spin until every lane's target has published this sweep
+template <bool MULTI>
+__device__ __forceinline__ void coop_wait(const DevCtx& c, unsigned int tag, uint32_t tgt) {
+  bool ok = (tgt == SM_NIL);
+  const unsigned int* dp = nullptr;
+  bool remote = false;
+  if (!ok) {
+    if (MULTI) {
+      const int bq = (int)(tgt >> 28);
+      dp = &c.peer[bq].done[tgt & 0x0FFFFFFFu];
+      remote = (bq != c.rank);      // polled over NVLink: system scope
+    } else dp = &c.done[tgt];
+  }
+  for (;;) {
+    if (!ok) {
+      const unsigned int v = remote ? ld_acquire_sys_u32(dp) : ld_acquire_u32(dp);
+      ok = v >= tag;
+    }
+    if (__all_sync(0xffffffffu, ok)) break;
+  }
+}
+
+template <int KIND, bool MULTI>
+__global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(DevCtx c, int n, const float* __restrict__ spawn,
+                                                                            int max_sweeps) {
+  typedef typename PType<KIND>::T P;
+  __shared__ SoilDev s_soils[SM_MAX_SOILS];
+  __shared__ unsigned int s_alive;
+  __shared__ WarpSmem s_w[SM_SW_WARPS];
+  for (int i = threadIdx.x; i < c.nsoils; i += blockDim.x) s_soils[i] = c.soils[i];
+  if (threadIdx.x == 0) s_alive = 0;
+  __syncthreads();
+
+  RunCtl* ctl = c.ctl;
+  unsigned int epoch = 0;
+  const unsigned int tag0 = ctl->tag_base;   // constant during the launch (rewritten at the very end)
+  const unsigned int gbase = MULTI ? ctl->epoch_base : 0u;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int slot = blockIdx.x * SM_SW_WARPS + wib;
+  const int nslots = gridDim.x * SM_SW_WARPS;
+  WarpSmem& ws = s_w[wib];
+  WarpDev w{lane};
+
+  unsigned long long n_steps = 0, n_oob = 0, n_evap = 0, n_stall = 0;   // warp-uniform from the sweep loop on
+  bool any_doa = false;
+
+  // ---- prologue: spawn (ctor bodies water.h:13-17 / wind.h:15-20) or resume, fill the bins; one thread per particle ----
+  unsigned int total_alive = 0;
+  {
+    unsigned int my_alive = 0;
+    unsigned long long doa = 0;
+    const int nthreads = gridDim.x * blockDim.x;
+    for (int pid = gtid; pid < n; pid += nthreads) {
+      bool alive;
+      if (spawn != nullptr) {
+        const float x = spawn[2 * pid], y = spawn[2 * pid + 1];
+        const int sx = (int)roundf(x), sy = (int)roundf(y);
+        if (MULTI && owner_of_x<MULTI>(c, sx) != c.rank) {     // another rank spawns this one
+          c.alive[pid] = 0;
+          continue;
+        }
+        const uint32_t contains = s_soils[rec_surface(*cell_ptr<MULTI>(c, sx, sy))].transports;
+        if (KIND == KIND_WATER) {
+          WaterP q{x, y, 0.0f, 0.0f, 1.0, 0.0, contains};
+          store_particle(c, pid, q);
+          alive = true;
+        } else {
+          WindP q{x, y, -2.0f, 0.0f, 1.0f, 0.0, 0.0, contains};
+          store_particle(c, pid, q);
+          // wind.h:56-57: a particle whose load cannot be suspended dies in its first move() without
+          // touching anything
+          alive = !(s_soils[contains].suspension == 0.0);
+          if (!alive) { doa++; any_doa = true; }
+        }
+        c.alive[pid] = alive ? 1 : 0;
+        c.done[pid] = alive ? (tag0 - 1u) : 0xFFFFFFFFu;
+      } else {
+        alive = c.alive[pid] != 0;
+        if (MULTI && alive) c.alive[pid] = 1;      // drop the arrival mark of a hand-over (see the sweep loop)
+      }
+      if (alive) {
+        P q;
+        load_particle(c, pid, q);
+        bin_insert<KIND, MULTI>(c, tag0, pid, (int)roundf(q.px), (int)roundf(q.py), particle_reach(q), c.rank);
+        my_alive++;
+      }
+    }
+    if (doa) atomicAdd(&ctl->exit_oob, doa);
+    if (my_alive) atomicAdd(&s_alive, my_alive);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (s_alive) atomicAdd(&ctl->alive_slot[0], s_alive);
+      s_alive = 0;
+    }
+    if (MULTI) total_alive = grid_barrier_multi(c, epoch, gbase, 0u);
+    else grid_barrier(&ctl->barrier, epoch);
+  }
+
+  int s = 0;
+  for (;; s++) {
+    const unsigned int tag = tag0 + (unsigned int)s;
+    if (!MULTI) total_alive = ld_volatile_u32(&ctl->alive_slot[s % 3]);
+    if (total_alive == 0 || (max_sweeps >= 0 && s >= max_sweeps)) break;
+    if (gtid == 0) st_volatile_u32(&ctl->alive_slot[(s + 2) % 3], 0u);
+
+    unsigned int my_alive = 0;
+    for (int pid = slot; pid < n; pid += nslots) {      // ascending index within a warp: no wait can cycle
+      const unsigned int av = c.alive[pid];
+      if (av == 0) continue;
+      // sharded map: a particle handed over during this very sweep carries the arrival mark 2 + parity of the
+      // sweep it arrived in; it has completed this sweep already and becomes runnable with the next one
+      // (the rank that handed it over counted it among the survivors of this sweep)
+      if (MULTI && av >= 2u && (av - 2u) == (tag & 1u)) continue;
+      P p;
+      load_particle(c, pid, p);
+      const int ix = (int)roundf(p.px), iy = (int)roundf(p.py);
+      const int myR = particle_reach(p);
+      const uint32_t tgt = coop_scan<KIND, MULTI>(c, ws, lane, tag, pid, ix, iy, myR);
+      coop_wait<MULTI>(c, tag, tgt);
+
+      DevBack<MULTI> back(c, s_soils, tag);
+      CoopWin<DevBack<MULTI> > a(back, &ws.cs);
+      const int r = do_step_coop(w, a, p);
+      // hand-off first: the map writes are all the successors of this step wait for
+      a.flush(w);
+      const int jx = (int)roundf(p.px), jy = (int)roundf(p.py);
+      if (lane == 0) {
+        const unsigned int pub = (r == SM_ALIVE) ? tag : 0xFFFFFFFFu;
+        if (MULTI) {
+          // only particles within two bins of a strip edge can have touched a peer's records or be polled
+          // from another rank: they release at system scope, the interior ones at gpu scope
+          const int xlo = c.rank * c.strip_w, xhi = xlo + c.strip_w;
+          const bool edge = (ix < xlo + 32 && c.rank > 0) || (ix >= xhi - 32 && c.rank < c.nranks - 1);
+          if (edge) st_release_sys_u32(&c.done[pid], pub);
+          else st_release_u32(&c.done[pid], pub);
+        } else {
+          st_release_u32(&c.done[pid], pub);
+        }
+        // own state and next sweep's bins are only needed after the grid barrier
+        if (r == SM_ALIVE) {
+          int ddx = jx - ix, ddy = jy - iy;
+          ddx = ddx < 0 ? -ddx : ddx; ddy = ddy < 0 ? -ddy : ddy;
+          const int lim = myR - Reach<KIND>::RING;      // the step promised to stay within ipos +- lim
+          if (ddx > lim || ddy > lim) atomicOr(&ctl->err, 1u << 4);  // SM_ERR_REACH
+          const int nq = owner_of_x<MULTI>(c, jx);
+          if (MULTI && nq != c.rank) {
+            // the particle leaves this strip: hand it to the new owner (its arrays, its bins)
+            DevCtx o = c;   // view of the owner's particle arrays
+            o.pa = c.peer[nq].pa; o.pb = c.peer[nq].pb; o.pc = c.peer[nq].pc;
+            store_particle(o, pid, p);
+            c.peer[nq].done[pid] = tag;            // it has completed this sweep, wherever it is asked
+            c.peer[nq].alive[pid] = (unsigned char)(2u + (tag & 1u));
+            c.alive[pid] = 0;
+          } else {
+            store_particle(c, pid, p);
+            if (MULTI && av != 1u) c.alive[pid] = 1;
+          }
+          bin_insert<KIND, MULTI>(c, tag + 1u, pid, jx, jy, particle_reach(p), nq);
+        } else {
+          store_particle(c, pid, p);
+          c.alive[pid] = 0;
+        }
+      }
+      if (r == SM_ALIVE) { n_steps++; my_alive++; }
+      else if (r == SM_EXIT_OOB) n_oob++;
+      else if (r == SM_EXIT_STALL) n_stall++;
+      else { n_steps++; n_evap++; }
+      __syncwarp();
+    }
+    if (lane == 0 && my_alive) atomicAdd(&s_alive, my_alive);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (s_alive) atomicAdd(&ctl->alive_slot[(s + 1) % 3], s_alive);
+      s_alive = 0;
+    }
+    if (MULTI) total_alive = grid_barrier_multi(c, epoch, gbase, (unsigned int)((s + 1) % 3));
+    else grid_barrier(&ctl->barrier, epoch);
+  }
+
+  // ---- epilogue ----
+  if (lane == 0) {
+    if (n_steps) atomicAdd(&ctl->steps, n_steps);
+    if (n_oob) atomicAdd(&ctl->exit_oob, n_oob);
+    if (n_evap) atomicAdd(&ctl->exit_evap, n_evap);
+    if (n_stall) atomicAdd(&ctl->exit_stall, n_stall);
+  }
+  // tag_base was read by every block before its first barrier; barrier/alive_slot are reset by the host
+  // before the next launch
+  if (any_doa) atomicMax(&ctl->sweeps, 1ull);
+  if (gtid == 0) {
+    atomicMax(&ctl->sweeps, (unsigned long long)s);
+    ctl->alive = total_alive;
+    ctl->tag_base = tag0 + (unsigned int)s + 2u;
+    if (MULTI) ctl->epoch_base = gbase + epoch;
+  }
+}
