@@ -122,6 +122,10 @@ int sm_download_columns(sm_context* ctx, int64_t capacity, int64_t* offsets, int
 int sm_download_height(sm_context* ctx, double* height);     /* Layermap::height(ivec2), layermap.h:422 */
 int sm_download_surface(sm_context* ctx, int32_t* surface);  /* Layermap::surface, layermap.h:417 */
 int sm_height_sum(sm_context* ctx, double* sum);             /* deterministic tree sum on device */
+/* Position-sensitive 64-bit checksum of every section (size, floor, saturation, type, cell, depth) of this
+ * context's columns; the checksums of the strips of a sharded map add up (mod 2^64) to the checksum of the
+ * whole map.  soilmachine_b200/checksum.py computes the same number from downloaded / reference columns. */
+int sm_checksum(sm_context* ctx, uint64_t* checksum);
 
 /* WaterParticle::frequency/track, WindParticle::frequency (water.h:345-346, wind.h:48).
  * Any pointer may be NULL. */

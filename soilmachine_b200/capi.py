@@ -29,7 +29,7 @@ LAYER_DTYPE = np.dtype([
 SYMBOLS = [
     "sm_create", "sm_destroy", "sm_last_error", "sm_sync", "sm_set_soils", "sm_initialize",
     "sm_upload_columns", "sm_section_count", "sm_download_columns", "sm_download_height",
-    "sm_download_surface", "sm_height_sum", "sm_get_frequency", "sm_set_frequency",
+    "sm_download_surface", "sm_height_sum", "sm_checksum", "sm_get_frequency", "sm_set_frequency",
     "sm_frequency_update", "sm_cell_add", "sm_cell_remove", "sm_cell_cascade", "sm_cell_query",
     "sm_height_bilinear", "sm_water_run", "sm_wind_run", "sm_water_run_device", "sm_wind_run_device",
     "sm_last_stats", "sm_water_begin", "sm_water_sweeps", "sm_water_state", "sm_wind_begin",
@@ -218,6 +218,12 @@ class Context:
         s = C.c_double()
         self._ck(self.lib.sm_height_sum(self.h, C.byref(s)))
         return s.value
+
+    def checksum(self):
+        """position-sensitive checksum of all sections of this context's columns (see checksum.py)"""
+        v = C.c_uint64()
+        self._ck(self.lib.sm_checksum(self.h, C.byref(v)))
+        return int(v.value)
 
     def frequency(self):
         a = [np.zeros(self.map_cells, np.float32) for _ in range(3)]

@@ -847,6 +847,50 @@ __global__ void k_height_sum2(const double* __restrict__ partial, double* __rest
   if (threadIdx.x == 0) *out = sh[0];
 }
 
+// Position-sensitive checksum of every section of every column of this rank's strip (parity evidence for runs
+// too large to download: equal checksums on 1, 2, 4, 8 GPUs, equal to the oracle's columns hashed by
+// soilmachine_b200/checksum.py).  Each section contributes mix(cell, depth from the top, size, floor,
+// saturation, type); contributions are summed modulo 2^64, so the sum over the strips of a sharded map is the
+// checksum of the whole map and the order of summation does not matter.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {   // splitmix64 finaliser
+  z ^= z >> 30; z *= 0xbf58476d1ce4e5b9ull;
+  z ^= z >> 27; z *= 0x94d049bb133111ebull;
+  z ^= z >> 31;
+  return z;
+}
+__device__ __forceinline__ unsigned long long section_hash(unsigned long long cell, unsigned int depth, const Sec32& r) {
+  unsigned long long h = mix64(cell * 0x9e3779b97f4a7c15ull + depth);
+  h = mix64(h ^ (unsigned long long)__double_as_longlong(r.size));
+  h = mix64(h ^ (unsigned long long)__double_as_longlong(r.floor));
+  h = mix64(h ^ (unsigned long long)__double_as_longlong(r.saturation));
+  return mix64(h ^ (unsigned long long)r.type);
+}
+__global__ void __launch_bounds__(256) k_checksum(DevCtx c, unsigned long long* __restrict__ out) {
+  __shared__ unsigned long long sh[256];
+  const int x0 = c.rank * c.strip_w;
+  const int x1 = (x0 + c.strip_w < c.dimx) ? x0 + c.strip_w : c.dimx;
+  const size_t cells = (size_t)(x1 - x0) * c.dimy;
+  const unsigned long long base = (unsigned long long)x0 * c.dimy;        // global index of this strip's first cell
+  unsigned long long acc = 0;
+  for (size_t cell = (size_t)blockIdx.x * blockDim.x + threadIdx.x; cell < cells; cell += (size_t)gridDim.x * blockDim.x) {
+    Sec32 r = c.top[cell];
+    if (r.type == SM_EMPTY) continue;
+    unsigned int depth = 0;
+    for (;;) {
+      acc += section_hash(base + cell, depth++, r);
+      if (r.below == SM_NIL) break;
+      r = c.pool[r.below];
+    }
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s2 = 128; s2 > 0; s2 >>= 1) {
+    if (threadIdx.x < s2) sh[threadIdx.x] += sh[threadIdx.x + s2];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(out, sh[0]);
+}
+
 // Layermap::initialize, layermap.h:163-216: one thread per cell replays add() for every layer
 #define SM_MAX_LAYERS 16
 struct LayerSet { LayerDev L[SM_MAX_LAYERS]; int zslice[SM_MAX_LAYERS]; int n; };
@@ -1585,6 +1629,19 @@ int sm_height_sum(sm_context* ctx, double* sum) {
   ctx->launches += 2;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(sum, ctx->d_scratch + SUM_BLOCKS, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SM_OK;
+}
+
+int sm_checksum(sm_context* ctx, uint64_t* out) {
+  if (!out) return fail(ctx, SM_ERR_INVALID, "null argument");
+  CK(cudaSetDevice(ctx->cfg.device));
+  unsigned long long* d_out = (unsigned long long*)(ctx->d_scratch + SUM_BLOCKS + 1);
+  CK(cudaMemsetAsync(d_out, 0, 8, ctx->stream));
+  k_checksum<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(ctx->d, d_out);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, d_out, 8, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return SM_OK;
 }

@@ -115,13 +115,15 @@ class VirtualShards:
 class DistShard:
     """This process's rank of a map sharded over torch.distributed ranks (one GPU each)."""
 
-    def __init__(self, dimx, dimy, scale, device, max_particles=0, pool_capacity=0):
+    def __init__(self, dimx, dimy, scale, device, max_particles=0, pool_capacity=0, share=1):
+        """share > 1: that many ranks (processes) run their kernels on the SAME device - used by the one-GPU
+        test of the CUDA-IPC path; every rank's grid must then be resident at the same time."""
         import torch.distributed as dist
         self.dist = dist
         self.nranks, self.rank = dist.get_world_size(), dist.get_rank()
         self.dimx, self.dimy = dimx, dimy
         self.ctx = capi.Context(dimx, dimy, scale, device=device, max_particles=max_particles,
-                                pool_capacity=pool_capacity, nranks=self.nranks, rank=self.rank, share=1)
+                                pool_capacity=pool_capacity, nranks=self.nranks, rank=self.rank, share=share)
         mine = bytes(self.ctx.peer_export())
         blobs = [None] * self.nranks
         dist.all_gather_object(blobs, mine)

@@ -1,13 +1,17 @@
-"""Run under torchrun on N GPUs (gpurun --gpus N): the map sharded over the ranks (CUDA-IPC peers over
-NVLink) must be bit-identical to the same frames on one GPU.  Rank 0 runs the unsharded context too and
-compares; prints one line per check and exits non-zero on any difference.
+"""The map sharded over several PROCESSES (CUDA-IPC peer mappings, system-scope hand-offs, cross-rank barrier)
+must be bit-identical to the same frames on one unsharded context.  Rank 0 runs the unsharded context too and
+compares heights, every column section (checksum), frequency maps and the counters; prints one line and exits
+non-zero on any difference.
 
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
-      tests/multigpu_check.py [dim] [particles]
+  N GPUs (gpurun --gpus N), one rank per GPU, NCCL for the plumbing:
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        tests/multigpu_check.py [dim] [particles] [soil]
+  ONE GPU, N processes sharing it (what the 1-GPU test tier runs, tests/test_gpu_parity.py): SM_ONE_GPU=1 in the
+  environment - every rank uses device 0, gloo carries the plumbing (NCCL refuses two ranks on one device), the
+  data path is the same CUDA-IPC peer memory as across GPUs.
 """
 import os
 import sys
-import time
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -19,16 +23,23 @@ from soilmachine_b200 import capi, presets, host, sharded  # noqa: E402
 def main():
     dim = int(sys.argv[1]) if len(sys.argv) > 1 else 512
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 4000
+    soil = sys.argv[3] if len(sys.argv) > 3 else "rockgravelpebblessand"
+    frames_n = int(sys.argv[4]) if len(sys.argv) > 4 else 2
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    local = int(os.environ["LOCAL_RANK"])
+    one_gpu = os.environ.get("SM_ONE_GPU") == "1"
+    local = 0 if one_gpu else int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    pre = presets.load("rockgravelpebblessand")
-    sh = sharded.DistShard(dim, dim, pre["world"]["scale"], device=local, max_particles=n)
+    if one_gpu:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pre = presets.load(soil)
+    sh = sharded.DistShard(dim, dim, pre["world"]["scale"], device=local, max_particles=n,
+                           share=world if one_gpu else 1)
     sh.ctx.set_soils(pre["soils"])
     sh.ctx.initialize(42, pre["layers"])
     host.srand(42)
-    frames = [(host.spawn_list(n, dim, dim), host.spawn_list(n, dim, dim)) for _ in range(2)]
+    frames = [(host.spawn_list(n, dim, dim), host.spawn_list(n, dim, dim)) for _ in range(frames_n)]
     tot = np.zeros(4)
     t_ms = 0.0
     for xw, xd in frames:
@@ -37,48 +48,43 @@ def main():
         a = sh.run("water", dw, n)
         b = sh.run("wind", dd, n)
         sh.ctx.frequency_update()
-        tot += [a.steps, b.steps, a.sweeps, b.sweeps]
+        tot += [a.steps, b.steps, a.exit_oob + a.exit_evap + a.exit_stall, b.exit_oob]
         t_ms += a.device_ms + b.device_ms
         sh.ctx.device_free(dw); sh.ctx.device_free(dd)
-    h = torch.from_numpy(sh.ctx.heights().copy()).cuda()
-    parts = [torch.empty((c1 - c0, dim), dtype=torch.float64, device="cuda") for c0, c1 in _ranges(dim, world)]
-    dist.all_gather(parts, h) if len(set(p.shape for p in parts)) == 1 else _gather_ragged(parts, h, rank, world)
-    steps = torch.tensor(tot[:2], dtype=torch.float64, device="cuda")
-    dist.all_reduce(steps)
-    tmax = torch.tensor([t_ms], dtype=torch.float64, device="cuda")
-    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    mine = {"h": sh.ctx.heights().copy(), "cs": sh.ctx.checksum(), "freq": sh.ctx.frequency(), "tot": tot,
+            "ms": t_ms, "range": (sh.ctx.x0, sh.ctx.x1)}
+    parts = [None] * world
+    dist.all_gather_object(parts, mine)
     ok = True
     if rank == 0:
-        full = torch.cat(parts, 0).cpu().numpy()
+        full = np.concatenate([p["h"] for p in parts], axis=0)
+        cs = sum(p["cs"] for p in parts) & ((1 << 64) - 1)
+        freq = sharded.merge_frequency([p["freq"] for p in parts], [p["range"] for p in parts], dim, dim)
+        counts = sum(p["tot"] for p in parts)
         one = capi.Context(dim, dim, pre["world"]["scale"], device=local, max_particles=n)
         one.set_soils(pre["soils"]); one.initialize(42, pre["layers"])
-        s1 = np.zeros(2); t1 = 0.0
+        c1 = np.zeros(4); t1 = 0.0
         for xw, xd in frames:
             a = one.water_run(xw); b = one.wind_run(xd); one.frequency_update()
-            s1 += [a.steps, b.steps]; t1 += a.device_ms + b.device_ms
+            c1 += [a.steps, b.steps, a.exit_oob + a.exit_evap + a.exit_stall, b.exit_oob]
+            t1 += a.device_ms + b.device_ms
         same_h = np.array_equal(full.view(np.uint8), one.heights().view(np.uint8))
-        same_s = np.array_equal(s1, steps.cpu().numpy())
-        ok = same_h and same_s
-        print("multigpu_check world=%d dim=%d n=%d: heights %s, steps %s (%s) | sharded %.1f ms vs one GPU %.1f ms"
-              % (world, dim, n, "IDENTICAL" if same_h else "DIFFER", "IDENTICAL" if same_s else "DIFFER",
-                 steps.cpu().numpy().tolist(), tmax.item(), t1), flush=True)
-    flag = torch.tensor([1 if ok else 0], device="cuda")
-    dist.broadcast(flag, 0)
+        same_c = cs == one.checksum()
+        f1 = one.frequency()
+        same_f = all(np.array_equal(freq[k].view(np.uint8), f1[k].view(np.uint8)) for k in f1)
+        same_s = np.array_equal(c1, counts)
+        ok = same_h and same_c and same_f and same_s
+        w = lambda b: "IDENTICAL" if b else "DIFFER"
+        print("multigpu_check world=%d%s dim=%d n=%d %s: heights %s, column checksum %s (%016x), frequency maps %s, "
+              "counters %s (%s) | sharded %.1f ms vs one context %.1f ms"
+              % (world, " (one GPU, CUDA IPC between processes)" if one_gpu else "", dim, n, soil, w(same_h), w(same_c),
+                 cs, w(same_f), w(same_s), counts.tolist(), max(p["ms"] for p in parts), t1), flush=True)
+        one.close()
+    flag = [ok]
+    dist.broadcast_object_list(flag, 0)
     sh.close()
     dist.destroy_process_group()
-    sys.exit(0 if flag.item() == 1 else 1)
-
-
-def _ranges(dim, world):
-    w = ((((dim + world - 1) // world) + 15) // 16) * 16
-    return [(q * w, min(dim, (q + 1) * w)) for q in range(world)]
-
-
-def _gather_ragged(parts, h, rank, world):
-    for q in range(world):
-        if q == rank:
-            parts[q].copy_(h)
-        dist.broadcast(parts[q], q)
+    sys.exit(0 if flag[0] else 1)
 
 
 if __name__ == "__main__":

@@ -449,3 +449,113 @@ def test_gpu_replays_golden_hydrology(case):
     ctx.upload_columns(c["offsets"], c["type"], c["size"], c["saturation"])
     counters = _golden.replay_hydro(g, ctx)
     assert all(h.floods >= f for h, f in zip(counters, g["floods"]))
+
+
+# ---- BASELINE.json configs at their own sizes -------------------------------------------------------------
+def _compare_big(ref, ctx, what):
+    """Full-size comparison without downloading 10^7 sections through Python lists: every height and every
+    frequency/track entry byte for byte, every section of every column through the position-sensitive checksum
+    (device: sm_checksum; reference: the same hash over its columns in numpy)."""
+    from soilmachine_b200 import checksum
+    _same(ref.heights(), ctx.heights(), what + ": height")
+    f1, f2 = ref.frequency(), ctx.frequency()
+    for k in f1:
+        _same(f1[k], f2[k], what + ": " + k)
+    want = checksum.columns_checksum(ref.columns())
+    assert ctx.checksum() == want, what + ": column checksum"
+    return want
+
+
+def test_config3_frame_matches_reference(ref):
+    """BASELINE.json configs[2] at its own size - 4096^2 rockgravelpebblessand, terrain from sm_initialize, the
+    bench's own first-frame spawn lists (srand(42), 25 000 water then 25 000 wind), both batches run to
+    completion (~460 water sweeps, ~13 700 wind sweeps), frequency update - against the reference's functions
+    driven in lockstep.  The checksum of the final columns is the one bench.py prints after its first frame."""
+    import json
+    import os
+    import soilmachine_b200 as smb
+    from soilmachine_b200 import host, presets
+    dim, n = 4096, 25000
+    pre = presets.load("rockgravelpebblessand")
+    ctx = smb.Context(dim, dim, pre["world"]["scale"], max_particles=n)
+    ctx.set_soils(pre["soils"])
+    ctx.initialize(42, pre["layers"])
+    ref.init("rockgravelpebblessand", seed=42, dimx=dim, dimy=dim, poolsize=dim * dim * 2 + 2000000)
+    _compare_big(ref, ctx, "terrain")
+    host.srand(42)
+    xw, xd = host.spawn_list(n, dim, dim), host.spawn_list(n, dim, dim)
+    r, g = ref.water_run(xw), ctx.water_run(xw)
+    assert (g.steps, g.sweeps, g.exit_oob, g.exit_evap, g.exit_stall, g.pool_drops) == \
+        (r.steps, r.sweeps, r.exit_oob, r.exit_evap, r.exit_stall, 0)
+    _compare_big(ref, ctx, "after the water batch")
+    r, g = ref.wind_run(xd), ctx.wind_run(xd)
+    assert (g.steps, g.exit_oob, g.pool_drops) == (r.steps, r.exit_oob, 0)
+    assert g.sweeps > 10000
+    s1, s2 = ref.wind_state(), ctx.wind_state()
+    for k in s1:
+        _same(s1[k], s2[k], "wind particles: " + k)
+    ref.frequency_update(); ctx.frequency_update()
+    cs = _compare_big(ref, ctx, "after the frame")
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cfg3_frame1_checksum.json")
+    if os.path.exists(gold):
+        with open(gold) as f:
+            assert int(json.load(f)["checksum"], 16) == cs, "bench.py's golden first-frame checksum is stale"
+    else:                         # first run on a GPU box: written to gpurun_out/ so that it can be committed
+        out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "cfg3_frame1_checksum.json"), "w") as f:
+            json.dump({"checksum": "%016x" % cs, "what": "columns after frame 1 of bench.py's config 3 "
+                       "(srand(42): 25000 water, 25000 wind, frequency update), equal to oracle/_ref in lockstep"}, f)
+    ctx.close()
+
+
+@pytest.mark.parametrize("soil,dim,nw,nd,sweeps,poolf", [("bigbutte", 4096, 50000, 0, 80, 2.2),
+                                                         ("rockgravelpebbles_big", 8192, 100000, 100000, 80, 1.1)])
+def test_config4_config5_shapes_match_reference(ref, soil, dim, nw, nd, sweeps, poolf):
+    """BASELINE.json configs[3] and [4] at their own sizes (single context): terrain from sm_initialize, the
+    frame's spawn lists, the first `sweeps` lockstep sweeps of the water batch (the oracle needs minutes for
+    a whole batch at these sizes), then the wind batch of config 5 - inert: no soil of that preset can be
+    suspended (wind.h:56-57)."""
+    import soilmachine_b200 as smb
+    from soilmachine_b200 import host, presets
+    pre = presets.load(soil)
+    ctx = smb.Context(dim, dim, pre["world"]["scale"], max_particles=max(nw, nd))
+    ctx.set_soils(pre["soils"])
+    ctx.initialize(42, pre["layers"])
+    ref.init(soil, seed=42, dimx=dim, dimy=dim, poolsize=int(dim * dim * poolf) + 2000000)   # layers x cells + headroom
+    host.srand(42)
+    xw = host.spawn_list(nw, dim, dim)
+    r, g = ref.water_run(xw, max_sweeps=sweeps), ctx.water_run(xw, max_sweeps=sweeps)
+    assert (g.steps, g.sweeps, g.exit_oob, g.exit_evap, g.exit_stall, g.pool_drops) == \
+        (r.steps, r.sweeps, r.exit_oob, r.exit_evap, r.exit_stall, 0)
+    s1, s2 = ref.water_state(), ctx.water_state()
+    for k in s1:
+        _same(s1[k], s2[k], "water particles: " + k)
+    if nd:
+        xd = host.spawn_list(nd, dim, dim)
+        r, g = ref.wind_run(xd), ctx.wind_run(xd)
+        assert (g.steps, g.exit_oob) == (r.steps, r.exit_oob) == (0, nd)
+    _compare_big(ref, ctx, "%s %d^2 after %d sweeps" % (soil, dim, sweeps))
+    ctx.close()
+
+
+def test_ipc_sharded_two_processes_one_gpu():
+    """The real multi-process data path on the 1-GPU tier: two processes share this GPU, each owns one x-strip,
+    and reach the other's arrays through CUDA-IPC mappings - peer loads/stores of halo records, system-scope
+    hand-off words and atomics, the cross-rank barrier, particle hand-over - exactly as two GPUs do over NVLink
+    (tests/multigpu_check.py, which also runs on N GPUs).  Must be bit-identical to the unsharded context."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SM_ONE_GPU="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29617", os.path.join(root, "tests", "multigpu_check.py"),
+           "96", "300", "rocksand", "1"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=root, env=env)
+    line = [l for l in out.stdout.splitlines() if l.startswith("multigpu_check")]
+    assert out.returncode == 0 and line and "DIFFER" not in line[0], (out.stdout[-2000:], out.stderr[-2000:])
+    logdir = os.path.join(root, "gpurun_out")
+    os.makedirs(logdir, exist_ok=True)
+    with open(os.path.join(logdir, "ipc_one_gpu.log"), "w") as f:
+        f.write(line[0] + "\n")

@@ -1,6 +1,8 @@
-"""CPU, world_size 2 over gloo: the N>1 path of bench.py.  The hot path itself runs as independent
-replicas per rank ('replicas only'), so what N>1 adds is the aggregation - device
-time is the MAX over ranks, particle-steps the SUM - and the rank-0-only reference arm."""
+"""CPU, world_size 2 over gloo: the host-side logic of bench.py's N>1 path.  On the GPUs the map is sharded
+into x-strips and the data path is peer memory inside the sweep kernel; what the host
+adds at N>1 is the aggregation - device time is the MAX over ranks, particle-steps the SUM, column checksums
+add up modulo 2^64 - and the rank-0-only reference arm.  The sharded kernels themselves are covered on the GPU
+tier (virtual ranks and two CUDA-IPC processes on one GPU, tests/test_gpu_parity.py)."""
 import json
 import os
 import subprocess
