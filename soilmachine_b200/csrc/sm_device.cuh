@@ -38,7 +38,7 @@ struct RunCtl {
   unsigned int err;             // SM_ERR_* bits raised on device
   unsigned long long steps, sweeps, exit_oob, exit_evap, exit_stall, drops, alive;
   unsigned long long bump;      // pool high-water mark
-  PoolRing ring[2];
+  PoolRing ring[3];             // k_sweep: frees of sweep s go to ring[s%3], allocations pop ring[(s+1)%3] (filled in sweep s-2)
   unsigned long long prof[16];  // clock64() phase totals (built with -DSM_PROFILE only)
   unsigned long long marks[8];  // finer marks inside interact()
   // sharded maps: cross-rank barrier (every rank writes its arrival into every peer's copy)
@@ -47,6 +47,9 @@ struct RunCtl {
   unsigned int alive_total[2];  // sum over ranks, for the local blocks
   unsigned int release;         // global epoch the local blocks may pass
   unsigned int epoch_base;      // global epoch at the start of the next launch (never reset)
+  // k_sweep's cross-rank barrier: xw[ge & 1][r] = (global epoch ge << 32) | live particles of rank r, written by
+  // rank r into the copy of every rank it synchronises with at that epoch (its own included)
+  unsigned long long xw[2][8];
 };
 
 // Pointers of one rank's arrays, as seen from this rank (own arrays, same-process contexts, or CUDA-IPC
@@ -55,7 +58,7 @@ struct RunCtl {
 struct PeerPtrs {
   Sec32* top;                    // that rank's strip of top records
   Sec32* pool;
-  uint32_t* ringbuf[2];
+  uint32_t* ringbuf[3];
   unsigned long long pool_cap;
   RunCtl* ctl;
   float4* pa; double2* pb; uint2* pc;
@@ -68,7 +71,7 @@ struct PeerPtrs {
 struct DevCtx {
   Sec32* top;
   Sec32* pool;
-  uint32_t* ringbuf[2];
+  uint32_t* ringbuf[3];
   unsigned long long pool_cap;
   float* wfreq;
   float* wtrack;
@@ -131,6 +134,15 @@ __device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int* p
 }
 __device__ __forceinline__ void st_release_sys_u32(unsigned int* p, unsigned int v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 // Grid-wide barrier for a co-resident (cooperative) grid: one arrival per block on a monotone

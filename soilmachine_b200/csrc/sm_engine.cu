@@ -1267,7 +1267,7 @@ void sm_destroy(sm_context* ctx) {
   cudaDeviceSynchronize();
   for (int q = 0; q < SM_MAX_RANKS; q++) for (int i = 0; i < 16; i++) if (ctx->ipc_opened[q][i]) cudaIpcCloseMemHandle(ctx->ipc_opened[q][i]);
   DevCtx& d = ctx->d;
-  cudaFree(d.top); cudaFree(d.pool); cudaFree(d.ringbuf[0]); cudaFree(d.ringbuf[1]);
+  cudaFree(d.top); cudaFree(d.pool); cudaFree(d.ringbuf[0]); cudaFree(d.ringbuf[1]); cudaFree(d.ringbuf[2]);
   cudaFree(d.wfreq); cudaFree(d.wtrack); cudaFree(d.windfreq); cudaFree(ctx->d_soils);
   cudaFree(d.ctl); cudaFree(d.pa); cudaFree(d.pb); cudaFree(d.pc); cudaFree(d.alive); cudaFree(d.done); cudaFree(d.fin); cudaFree(d.mv);
   for (int i = 0; i < 2; i++) { cudaFree(d.head[i]); cudaFree(d.node[i]); }
@@ -1287,11 +1287,12 @@ static int alloc_pool(sm_context* ctx, unsigned long long cap) {
   DevCtx& d = ctx->d;
   if (d.pool && d.pool_cap >= cap) return SM_OK;
   if (d.pool && ctx->nranks > 1) return fail(ctx, SM_ERR_POOL, "sharded context: pool_capacity is fixed at creation and too small");
-  cudaFree(d.pool); cudaFree(d.ringbuf[0]); cudaFree(d.ringbuf[1]);
-  d.pool = nullptr; d.ringbuf[0] = d.ringbuf[1] = nullptr;
+  cudaFree(d.pool); cudaFree(d.ringbuf[0]); cudaFree(d.ringbuf[1]); cudaFree(d.ringbuf[2]);
+  d.pool = nullptr; d.ringbuf[0] = d.ringbuf[1] = d.ringbuf[2] = nullptr;
   CK(cudaMalloc(&d.pool, cap * sizeof(Sec32)));
   CK(cudaMalloc(&d.ringbuf[0], cap * sizeof(uint32_t)));
   CK(cudaMalloc(&d.ringbuf[1], cap * sizeof(uint32_t)));
+  CK(cudaMalloc(&d.ringbuf[2], cap * sizeof(uint32_t)));
   d.pool_cap = cap;
   return SM_OK;
 }
@@ -1409,12 +1410,14 @@ static void own_ptrs(sm_context* ctx, void** p) {
   DevCtx& d = ctx->d;
   p[0] = d.top; p[1] = d.pool; p[2] = d.ringbuf[0]; p[3] = d.ringbuf[1]; p[4] = d.ctl; p[5] = d.pa; p[6] = d.pb;
   p[7] = d.pc; p[8] = d.alive; p[9] = d.done; p[10] = d.head[0]; p[11] = d.head[1]; p[12] = d.node[0]; p[13] = d.node[1];
+  p[14] = d.ringbuf[2];
 }
 static void fill_peer(PeerPtrs& P, void* const* p, unsigned long long pool_cap) {
   P.top = (Sec32*)p[0]; P.pool = (Sec32*)p[1]; P.ringbuf[0] = (uint32_t*)p[2]; P.ringbuf[1] = (uint32_t*)p[3];
   P.ctl = (RunCtl*)p[4]; P.pa = (float4*)p[5]; P.pb = (double2*)p[6]; P.pc = (uint2*)p[7];
   P.alive = (unsigned char*)p[8]; P.done = (unsigned int*)p[9]; P.head[0] = (unsigned long long*)p[10];
   P.head[1] = (unsigned long long*)p[11]; P.node[0] = (uint2*)p[12]; P.node[1] = (uint2*)p[13];
+  P.ringbuf[2] = (uint32_t*)p[14];
   P.pool_cap = pool_cap;
 }
 int sm_peer_export(sm_context* ctx, sm_peer_blob* out) {
@@ -1511,6 +1514,7 @@ static int reset_pool_ctl(sm_context* ctx, unsigned long long used) {
   h.bump = used;
   h.ring[0].head = h.ring[0].tail = 0;
   h.ring[1].head = h.ring[1].tail = 0;
+  h.ring[2].head = h.ring[2].tail = 0;
   h.err = 0; h.drops = 0;
   CK(cudaMemcpy(ctx->d.ctl, &h, sizeof(RunCtl), cudaMemcpyHostToDevice));
   return SM_OK;

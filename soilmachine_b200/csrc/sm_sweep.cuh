@@ -52,10 +52,10 @@ struct WarpDev {
 template <bool MULTI> struct DevBack {
   const DevCtx& c;
   const SoilDev* s_soils;   // shared-memory copy of the soil table
-  unsigned int phase;       // sweep parity for the pool rings
+  unsigned int phase;       // sweep number mod 3: frees go to ring[phase], allocations pop ring[(phase+1)%3]
   int cur_q;                // owner rank of the column the next col_* call works on
-  __device__ __forceinline__ DevBack(const DevCtx& ctx, const SoilDev* ss, unsigned int ph)
-      : c(ctx), s_soils(ss), phase(ph & 1u), cur_q(0) {}
+  __device__ __forceinline__ DevBack(const DevCtx& ctx, const SoilDev* ss, unsigned int tag)
+      : c(ctx), s_soils(ss), phase(tag % 3u), cur_q(0) {}
   __device__ __forceinline__ int dimx() const { return c.dimx; }
   __device__ __forceinline__ int dimy() const { return c.dimy; }
   __device__ __forceinline__ int scale() const { return c.scale; }
@@ -66,13 +66,17 @@ template <bool MULTI> struct DevBack {
   __device__ __forceinline__ void pool_store(uint32_t i, const Sec32& r) {
     if (MULTI) c.peer[cur_q].pool[i] = r; else c.pool[i] = r;
   }
-  // ticket pop from the ring filled during the previous sweep, else bump allocation;
-  // on a sharded map the column's owner holds the pool, and its counters may live on another GPU
+  // Ticket pop from the ring that was filled two sweeps ago, else bump allocation.
+  // Three rings instead of two: on a sharded map the strips two ranks apart may be one sweep apart (the
+  // per-sweep barrier only couples neighbouring strips) and both reach the pool of the strip between them,
+  // so the ring being popped in sweep s must not be the one sweep s-1 or s+1 appends to.  The column's
+  // owner holds the pool; its counters may live on another GPU (system-scope atomics).
   __device__ uint32_t pool_alloc() {
+    const unsigned int pr = (phase + 1u) % 3u;
     RunCtl* const ctl = MULTI ? c.peer[cur_q].ctl : c.ctl;
-    uint32_t* const ring = MULTI ? c.peer[cur_q].ringbuf[phase ^ 1u] : c.ringbuf[phase ^ 1u];
+    uint32_t* const ring = MULTI ? c.peer[cur_q].ringbuf[pr] : c.ringbuf[pr];
     const unsigned long long cap = MULTI ? c.peer[cur_q].pool_cap : c.pool_cap;
-    PoolRing* R = &ctl->ring[phase ^ 1u];
+    PoolRing* R = &ctl->ring[pr];
     const unsigned long long t = *((volatile unsigned long long*)&R->tail);
     if (*((volatile unsigned long long*)&R->head) < t) {
       const unsigned long long h = MULTI ? atomicAdd_system(&R->head, 1ull) : atomicAdd(&R->head, 1ull);
@@ -188,12 +192,65 @@ __device__ __forceinline__ void coop_wait(const DevCtx& c, unsigned int tag, uin
   }
 }
 
+// ---- barrier across the blocks of every rank of a sharded map ---------------------------------------------
+// A sweep of rank q only interacts with the strips q-1 and q+1 (halo records within +-5 cells, the bins one bin
+// beyond the strip edge, particles handed over to the adjacent strip, the neighbours' pools), so the per-sweep
+// barrier couples NEIGHBOURING ranks only; every SM_XSYNC_K-th sweep - and whenever a launch may end - all
+// ranks meet and exchange their live-particle counts (termination is decided at those sweeps, identically on
+// every rank).  Between two such sweeps strips that are d ranks apart may be up to d-1 sweeps apart.
+// Protocol: every block arrives on the local counter (fence + atomic); the block that arrives LAST publishes
+// (epoch << 32 | live count) with one system-scope release store per rank involved - lane q of its first warp
+// serves rank q, its own rank included - and the first warp of EVERY block polls the words of the ranks
+// involved in its own rank's memory (acquire), lane q polling rank q.  No leader round trip, no serial loop over
+// the peers.  Words are double-buffered by epoch parity: a rank can be at most one epoch ahead of a rank it
+// synchronises with.  Returns the live particles over all ranks after a global barrier (undefined otherwise).
+#define SM_XSYNC_K 8
+__device__ __forceinline__ unsigned int grid_barrier_x(const DevCtx& c, unsigned int& epoch, unsigned int gbase,
+                                                       unsigned int local_alive_slot, bool global,
+                                                       unsigned int* s_total) {
+  RunCtl* ctl = c.ctl;
+  __syncthreads();
+  epoch++;
+  const unsigned int ge = gbase + epoch;           // global epoch of this barrier (never reset)
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    unsigned int prev = 0;
+    if (lane == 0) {
+      __threadfence();
+      prev = atomicAdd(&ctl->barrier, 1u);
+      __threadfence();
+    }
+    prev = __shfl_sync(0xffffffffu, prev, 0);
+    const int d = lane - c.rank;
+    const bool involved = lane < c.nranks && (global || (d >= -1 && d <= 1));
+    if (prev == epoch * gridDim.x - 1u) {
+      const unsigned int mine = ld_volatile_u32(&ctl->alive_slot[local_alive_slot]);
+      if (involved)
+        st_release_sys_u64(&c.peer[lane].ctl->xw[ge & 1u][c.rank], ((unsigned long long)ge << 32) | mine);
+    }
+    unsigned int cnt = 0;
+    bool ok = !involved;
+    for (;;) {
+      if (!ok) {
+        const unsigned long long wv = ld_acquire_sys_u64(&ctl->xw[ge & 1u][lane]);
+        if ((int)((unsigned int)(wv >> 32) - ge) >= 0) { ok = true; cnt = (unsigned int)wv; }
+      }
+      if (__all_sync(0xffffffffu, ok)) break;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) *s_total = cnt;
+  }
+  __syncthreads();
+  return *s_total;
+}
+
 template <int KIND, bool MULTI>
 __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(DevCtx c, int n, const float* __restrict__ spawn,
                                                                             int max_sweeps) {
   typedef typename PType<KIND>::T P;
   __shared__ SoilDev s_soils[SM_MAX_SOILS];
-  __shared__ unsigned int s_alive;
+  __shared__ unsigned int s_alive, s_total;
   __shared__ WarpSmem s_w[SM_SW_WARPS];
   for (int i = threadIdx.x; i < c.nsoils; i += blockDim.x) s_soils[i] = c.soils[i];
   if (threadIdx.x == 0) s_alive = 0;
@@ -262,15 +319,21 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
       if (s_alive) atomicAdd(&ctl->alive_slot[0], s_alive);
       s_alive = 0;
     }
-    if (MULTI) total_alive = grid_barrier_multi(c, epoch, gbase, 0u);
+    if (MULTI) total_alive = grid_barrier_x(c, epoch, gbase, 0u, true, &s_total);
     else grid_barrier(&ctl->barrier, epoch);
   }
+  // neighbour-only barriers need the bins a rank's neighbours scan and the bins a rank two strips away inserts
+  // into to be different ones: at least three bins per strip
+  const bool xnb = MULTI && c.strip_w >= 3 * Reach<KIND>::G;
+  bool xglobal = true;          // was the barrier that opened this sweep a global one (total_alive valid)?
+  int last_active = -1;         // last sweep in which this warp executed a particle
 
   int s = 0;
   for (;; s++) {
     const unsigned int tag = tag0 + (unsigned int)s;
     if (!MULTI) total_alive = ld_volatile_u32(&ctl->alive_slot[s % 3]);
-    if (total_alive == 0 || (max_sweeps >= 0 && s >= max_sweeps)) break;
+    if (max_sweeps >= 0 && s >= max_sweeps) break;
+    if ((!MULTI || xglobal) && total_alive == 0) break;
     if (gtid == 0) st_volatile_u32(&ctl->alive_slot[(s + 2) % 3], 0u);
 
     unsigned int my_alive = 0;
@@ -281,6 +344,7 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
       // sweep it arrived in; it has completed this sweep already and becomes runnable with the next one
       // (the rank that handed it over counted it among the survivors of this sweep)
       if (MULTI && av >= 2u && (av - 2u) == (tag & 1u)) continue;
+      last_active = s;
       P p;
       load_particle(c, pid, p);
       const int ix = (int)roundf(p.px), iy = (int)roundf(p.py);
@@ -343,8 +407,10 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
       if (s_alive) atomicAdd(&ctl->alive_slot[(s + 1) % 3], s_alive);
       s_alive = 0;
     }
-    if (MULTI) total_alive = grid_barrier_multi(c, epoch, gbase, (unsigned int)((s + 1) % 3));
-    else grid_barrier(&ctl->barrier, epoch);
+    if (MULTI) {
+      xglobal = !xnb || ((s + 1) % SM_XSYNC_K == 0) || (max_sweeps >= 0 && s + 1 >= max_sweeps);
+      total_alive = grid_barrier_x(c, epoch, gbase, (unsigned int)((s + 1) % 3), xglobal, &s_total);
+    } else grid_barrier(&ctl->barrier, epoch);
   }
 
   // ---- epilogue ----
@@ -357,8 +423,11 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
   // tag_base was read by every block before its first barrier; barrier/alive_slot are reset by the host
   // before the next launch
   if (any_doa) atomicMax(&ctl->sweeps, 1ull);
+  // sharded map: termination is noticed at the next global barrier, up to SM_XSYNC_K - 1 empty sweeps late; the
+  // sweep count of the batch is the last sweep in which any rank executed a particle (the host takes the max)
+  if (MULTI && lane == 0 && last_active >= 0) atomicMax(&ctl->sweeps, (unsigned long long)(last_active + 1));
   if (gtid == 0) {
-    atomicMax(&ctl->sweeps, (unsigned long long)s);
+    if (!MULTI) atomicMax(&ctl->sweeps, (unsigned long long)s);
     ctl->alive = total_alive;
     ctl->tag_base = tag0 + (unsigned int)s + 2u;
     if (MULTI) ctl->epoch_base = gbase + epoch;
