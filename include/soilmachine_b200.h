@@ -190,6 +190,7 @@ typedef struct sm_hydro_stats {
   int64_t transfers;     /* partial water-table transfers (water.h:260-272) */
   int64_t cells;         /* sm_seep: cells visited (the cells where a visit can change anything) */
   double device_ms;      /* CUDA-event time of the call's kernels */
+  double classify_ms;    /* sm_seep: the full-grid classification kernel alone (32 B per cell read) */
 } sm_hydro_stats;
 /* WaterParticle::flood (water.h:123-145) for every finished particle of the last water batch, in
  * ascending particle index; each flood is atomic, i.e. the water-table cascade (water.h:151-283) and the

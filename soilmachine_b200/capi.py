@@ -56,7 +56,8 @@ class Stats(C.Structure):
 
 class HydroStats(C.Structure):
     _fields_ = [("floods", C.c_int64), ("nested", C.c_int64), ("nested_steps", C.c_int64),
-                ("transfers", C.c_int64), ("cells", C.c_int64), ("device_ms", C.c_double)]
+                ("transfers", C.c_int64), ("cells", C.c_int64), ("device_ms", C.c_double),
+                ("classify_ms", C.c_double)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -7,6 +7,7 @@
 // result is bit-identical to the reference functions driven sweep by sweep in index order
 // (oracle lockstep mode).  One grid barrier per sweep; no kernel launch per sweep.
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -1852,7 +1853,9 @@ static int zero_counters(sm_context* ctx) {
 
 int sm_last_stats(sm_context* ctx, sm_stats* st) {
   CK(cudaSetDevice(ctx->cfg.device));
-  CK(cudaMemcpyAsync(ctx->h_ctl, ctx->d.ctl, sizeof(RunCtl), cudaMemcpyDeviceToHost, ctx->stream));
+  // only the counters travel: barrier .. bump (SM_STATS_READBACK_BYTES, what bench.py counts as d2h per batch)
+  static_assert(offsetof(RunCtl, ring) == 88, "bench.py counts 88 bytes read back per batch");
+  CK(cudaMemcpyAsync(ctx->h_ctl, ctx->d.ctl, offsetof(RunCtl, ring), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   const RunCtl& h = *ctx->h_ctl;
   float ms = 0.f;
@@ -1927,7 +1930,7 @@ static int hydro_finish(sm_context* ctx, sm_hydro_stats* st) {
   ctx->mesh_valid = false;
   if (st) {
     st->floods = (int64_t)hc.floods; st->nested = (int64_t)hc.nested; st->nested_steps = (int64_t)hc.nested_steps;
-    st->transfers = (int64_t)hc.transfers; st->cells = (int64_t)hc.cells; st->device_ms = ms;
+    st->transfers = (int64_t)hc.transfers; st->cells = (int64_t)hc.cells; st->device_ms = ms; st->classify_ms = 0.0;
   }
   if (hc.overflow) return fail(ctx, SM_ERR_REACH, "water cascade nesting exceeded its bound");
   unsigned int err = 0;
@@ -1960,11 +1963,18 @@ int sm_seep(sm_context* ctx, sm_hydro_stats* st) {
   for (int l = 0; l < am.nlevels; l++) { am.lvl[l] = ctx->d_act + off; off += am.nwords[l]; }
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   CK(cudaMemsetAsync(ctx->d_act, 0, total * sizeof(unsigned long long), ctx->stream));
+  CK(cudaEventRecord(ctx->evt0, ctx->stream));
   k_hydro_classify<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(ctx->d, am);
+  CK(cudaEventRecord(ctx->evt1, ctx->stream));
   k_hydro_seep<<<1, 32, SM_HC_BYTES, ctx->stream>>>(ctx->d, am, ctx->d_hydro);
   ctx->launches += 2;
   CK(cudaGetLastError());
-  return hydro_finish(ctx, st);
+  int rc2 = hydro_finish(ctx, st);
+  if (st) {     // the full-grid classification alone (the HBM-bound part of the pass)
+    float cms = 0.f;
+    if (cudaEventElapsedTime(&cms, ctx->evt0, ctx->evt1) == cudaSuccess) st->classify_ms = cms;
+  }
+  return rc2;
 }
 
 // stepping interface: *_begin runs the prologue only (spawn + bins), *_sweeps(k) resumes the batch

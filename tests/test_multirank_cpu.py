@@ -21,9 +21,11 @@ def _worker(rank, world, port, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import bench
     ev, e2e, steps, esteps = bench.aggregate(100.0 + 50.0 * rank, 200.0 - 30.0 * rank, 1000 * (rank + 1), 10 * (rank + 1))
+    # strip checksums add up modulo 2^64 (one of them above 2^63, the sum wraps)
+    cs = bench.checksum_sum([0xF000000000000001, 0x2000000000000005][rank])
     if rank == 0:
         with open(out, "w") as f:
-            json.dump([ev, e2e, steps, esteps], f)
+            json.dump([ev, e2e, steps, esteps, cs], f)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -31,9 +33,10 @@ def _worker(rank, world, port, out):
 def test_aggregate_max_time_sum_steps(tmp_path):
     out = str(tmp_path / "agg.json")
     mp.spawn(_worker, args=(2, 29531, out), nprocs=2, join=True)
-    ev, e2e, steps, esteps = json.load(open(out))
+    ev, e2e, steps, esteps, cs = json.load(open(out))
     assert ev == 150.0 and e2e == 200.0          # max over ranks
     assert steps == 3000.0 and esteps == 30.0    # sum over ranks
+    assert cs == (0xF000000000000001 + 0x2000000000000005) % (1 << 64)
 
 
 def test_reference_arm_only_rank0_prints():
