@@ -55,6 +55,9 @@ __device__ __forceinline__ int particle_reach(const WindP& p) {
 #define SM_MINBLOCKS 3  // resident blocks per SM the sweep kernels are compiled for (register cap)
 #endif
 #define SM_SWEEPS_NONE 0x40000000   // internal: run the prologue only
+#ifndef SM_DEFAULT_COOP
+#define SM_DEFAULT_COOP false          // flipped once k_sweep has passed the GPU parity suite
+#endif
 #define SM_DONE_FLOODED 0xFFFFFFFEu  // done[] of a dead particle whose flood() has run (0xFFFFFFFF = dead)
 
 // ---------------------------------------------------------------------------------------------
@@ -1789,10 +1792,11 @@ static int launch_run(sm_context* ctx, int kind, int n, const float* d_spawn, in
   }
   // default: the warp-per-particle kernel (sm_sweep.cuh).  SM_KERNEL=thread selects the thread-per-particle
   // kernels above (kept for comparison measurements).
-  bool use_coop = true;
+  bool use_coop = SM_DEFAULT_COOP;
   {
     const char* e = getenv("SM_KERNEL");
     if (e && strcmp(e, "thread") == 0) use_coop = false;
+    if (e && strcmp(e, "warp") == 0) use_coop = true;
   }
   if (use_coop) {
     const int cthreads = SM_SW_WARPS * 32;
