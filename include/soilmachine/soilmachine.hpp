@@ -149,24 +149,88 @@ class Layermap {
     push_tables();
     std::vector<sm_layer> L;
     for (auto& l : layers) L.push_back(sm_layer{(int32_t)l.type, l.min, l.bias, l.scale, l.octaves, l.lacunarity, l.gain, l.frequency});
+    touch();
     ck(sm_initialize(ctx, SEED, L.data(), (int32_t)L.size()));
   }
-  double height(ivec2 p) { double h; ck(sm_cell_query(ctx, p.x, p.y, &h, nullptr, nullptr)); return h; }   // :422
+  // ---- per-cell reads (legacy call sites: GUI picking, custom initialisation) -------------------------------
+  // A handful of reads between two mutations go to the device one cell at a time (one tiny kernel each).  Code
+  // that reads many cells - a loop over the map - gets a HOST MIRROR instead: after kMirrorAfter single reads the
+  // height and surface fields are downloaded once and served from host memory until the next call that
+  // changes the map marks them dirty.
+  static constexpr int kMirrorAfter = 64;
+  double height(ivec2 p) {                                   // :422
+    if (mirror_ready()) return h_height[(size_t)p.x * dim.y + p.y];
+    double h; ck(sm_cell_query(ctx, p.x, p.y, &h, nullptr, nullptr)); return h;
+  }
   double height(vec2 p) { double h; ck(sm_height_bilinear(ctx, p.x, p.y, &h)); return h; }                  // :427
   vec3 normal(ivec2 p) { float n[3]; ck(sm_cell_query(ctx, p.x, p.y, nullptr, nullptr, n)); return vec3{n[0], n[1], n[2]}; }  // :341
   template <class VP> vec3 normal(ivec2 p, VP&) { return normal(p); }
-  SurfType surface(ivec2 p) { int32_t s; ck(sm_cell_query(ctx, p.x, p.y, nullptr, &s, nullptr)); return (SurfType)s; }       // :417
+  vec3 normal(vec2 pos) {                                    // :379-390 (weights cross-wired exactly as upstream)
+    const float fx = std::floor(pos.x), fy = std::floor(pos.y);
+    const ivec2 p((int)fx, (int)fy);
+    const float wx = pos.x - fx, wy = pos.y - fy;
+    vec3 n{0.f, 0.f, 0.f};
+    auto acc = [&](float w, ivec2 q) { const vec3 m = normal(q); n.x += w * m.x; n.y += w * m.y; n.z += w * m.z; };
+    acc((1.0f - wx) * (1.0f - wy), p);
+    acc((1.0f - wx) * wy, ivec2(p.x + 1, p.y));
+    acc(wx * (1.0f - wy), ivec2(p.x, p.y + 1));
+    acc(wx * wy, ivec2(p.x + 1, p.y + 1));
+    return n;
+  }
+  SurfType surface(ivec2 p) {                                // :417
+    if (mirror_ready()) return (SurfType)h_surface[(size_t)p.x * dim.y + p.y];
+    int32_t s; ck(sm_cell_query(ctx, p.x, p.y, nullptr, &s, nullptr)); return (SurfType)s;
+  }
+  // Layermap::top(ivec2), layermap.h:150-152: the top section of a column; ->prev walks down.  The sections
+  // are host COPIES (valid until the next top() call); the columns themselves live on the device.
+  sec* top(ivec2 p) {
+    int32_t n = 0;
+    std::vector<int32_t> t(64); std::vector<double> sz(64), fl(64), sa(64);
+    ck(sm_cell_column(ctx, p.x, p.y, 64, &n, t.data(), sz.data(), fl.data(), sa.data()));
+    if (n > 64) {
+      t.resize(n); sz.resize(n); fl.resize(n); sa.resize(n);
+      ck(sm_cell_column(ctx, p.x, p.y, n, &n, t.data(), sz.data(), fl.data(), sa.data()));
+    }
+    column_copy.assign((size_t)n, sec());
+    for (int i = 0; i < n; i++) {                            // bottom -> top
+      sec& e = column_copy[(size_t)i];
+      e.type = (SurfType)t[i]; e.size = sz[i]; e.floor = fl[i]; e.saturation = sa[i];
+      e.prev = i > 0 ? &column_copy[(size_t)i - 1] : nullptr;
+      e.next = i + 1 < n ? &column_copy[(size_t)i + 1] : nullptr;
+    }
+    return n ? &column_copy[(size_t)n - 1] : nullptr;
+  }
   void add(ivec2 p, sec* E) {                               // :230 (E is consumed, as upstream)
     if (!E) return;
+    touch();
     ck(sm_cell_add(ctx, p.x, p.y, E->size, (int32_t)E->type));
     pool.unget(E);
   }
-  double remove(ivec2 p, double h) { double d; ck(sm_cell_remove(ctx, p.x, p.y, h, &d)); return d; }        // :310
-  // meshing belongs to the renderer (layermap.h:443-555): accepted and ignored
-  template <class VP> void meshpool(VP&) {}
-  template <class VP> void update(ivec2, VP&) {}
-  template <class VP> void update(VP&) {}
-  template <class VP> void slice(VP&, double = 0) {}
+  double remove(ivec2 p, double h) { double d; touch(); ck(sm_cell_remove(ctx, p.x, p.y, h, &d)); return d; }   // :310
+
+  // ---- meshing (layermap.h:443-555) --------------------------------------------------------------------------
+  // The renderer's vertex pool is outside the boundary; what crosses it is the vertex data.  update(vp) meshes
+  // the whole map on the device (one 44-byte Vertex {position[3], normal[3], color[4], index} per cell, cell order
+  // x*dim.y + y, cut at the slice plane) into `vertices`, and hands it to the pool if the pool type offers
+  // upload(const float*, size_t nvertices).  update(ivec2, vp) - upstream's per-cell refresh after every column
+  // change - only has to mark the mesh stale: the next update(vp)/meshpool(vp)/slice(vp, s) rebuilds all of it
+  // in one bandwidth-bound pass.
+  std::vector<float> vertices;
+  int slice_plane = 160;                                     // SLICE = 2*SCALE (SoilMachine.cpp:12)
+  bool mesh_stale = true;
+  template <class VP> void meshpool(VP& vp) { update(vp); }                                                  // :443-473
+  template <class VP> void update(ivec2, VP&) { mesh_stale = true; }                                         // :475-549
+  template <class VP> void update(VP& vp) {                                                                  // :551-555
+    vertices.resize((size_t)dim.x * dim.y * 11);
+    ck(sm_mesh_update(ctx, slice_plane, vertices.data()));
+    mesh_stale = false;
+    upload_if_possible(vp, 0);
+  }
+  template <class VP> void slice(VP& vp, double s) { slice_plane = (int)s; update(vp); }                     // :557-
+  template <class VP> void slice(VP& vp) { update(vp); }
+
+  // every call that may change columns goes through here
+  void touch() { mirror_valid = false; mirror_reads = 0; mesh_stale = true; }
 
   // A full section pool is not fatal upstream: secpool::get prints and returns NULL, add() drops the section
   // (layermap.h:92-95,232-234) and the program keeps running.  Same here: the drop is reported, the call
@@ -181,8 +245,25 @@ class Layermap {
                                               s.density, s.porosity, s.solubility, s.equrate, s.friction, s.erosionrate,
                                               s.maxdiff, s.settling, s.suspension, s.abrasion});
     ck(sm_set_soils(ctx, t.data(), (int32_t)t.size()));
+    std::vector<float> col;
+    for (auto& sp : soils) { col.push_back(sp.color.x); col.push_back(sp.color.y); col.push_back(sp.color.z); col.push_back(sp.color.w); }
+    ck(sm_set_soil_colors(ctx, col.data(), (int32_t)soils.size()));
   }
  private:
+  std::vector<double> h_height; std::vector<int32_t> h_surface; std::vector<sec> column_copy;
+  bool mirror_valid = false; int mirror_reads = 0;
+  bool mirror_ready() {
+    if (mirror_valid) return true;
+    if (++mirror_reads <= kMirrorAfter) return false;
+    h_height.resize((size_t)dim.x * dim.y); h_surface.resize((size_t)dim.x * dim.y);
+    ck(sm_download_height(ctx, h_height.data()));
+    ck(sm_download_surface(ctx, h_surface.data()));
+    return mirror_valid = true;
+  }
+  template <class VP> auto upload_if_possible(VP& vp, int) -> decltype(vp.upload((const float*)nullptr, (size_t)0), void()) {
+    vp.upload(vertices.data(), (size_t)dim.x * dim.y);
+  }
+  template <class VP> void upload_if_possible(VP&, long) {}
   void open(ivec2 _dim, int SCALE, int device) {
     dim = _dim;
     sm_config cfg{dim.x, dim.y, SCALE, device, 0, 0, 0};
@@ -195,6 +276,7 @@ class Layermap {
 struct Particle {
   vec2 pos; vec2 speed; bool isalive = true;
   template <class VP> static void cascade(vec2 p, Layermap& map, VP&, int transferloop = 0) {               // particle.h:24
+    map.touch();
     map.ck(sm_cell_cascade(map.ctx, p.x, p.y, transferloop));
   }
 };
@@ -207,6 +289,10 @@ inline std::vector<float> spawn(const Layermap& map, int n) {
   for (int i = 0; i < n; i++) { int y = rand() % map.dim.y; int x = rand() % map.dim.x; xy[2 * i] = (float)x; xy[2 * i + 1] = (float)y; }
   return xy;
 }
+// Upstream's water-table cascade constructs every nested particle with `WaterParticle particle(map)`
+// (water.h:243), which draws two rand() values for a position that is overwritten right away.  The device never
+// needs them, but an application that seeds rand() expects the same stream afterwards: consume them here.
+inline void nested_ctor_draws(int64_t nested) { for (int64_t i = 0; i < 2 * nested; i++) (void)rand(); }
 }  // namespace detail
 
 // water.h:9-373 -- the batch entry point replaces the loop SoilMachine.cpp:288-298
@@ -217,33 +303,87 @@ struct WaterParticle : Particle {
   // (SoilMachine.cpp:314-319).  A headless loop that never calls init(...) pays no download.
   inline static float* frequency = nullptr;
   inline static float* track = nullptr;
-  inline static double volumeFactor = 0.015;                  // water.h:368 (fixed on the device; see flood())
+  inline static double volumeFactor = 0.015;                  // water.h:33,368: a mutable static, passed to the device
   static void init() {}                                       // maps live on the device; no host mirror
   static void init(int dimx, int dimy) {
     delete[] frequency; delete[] track;
     frequency = new float[(size_t)dimx * dimy]();
     track = new float[(size_t)dimx * dimy]();
   }
+
+  // ---- the reference's per-particle interface (water.h:11-19,43,75,123): the loop SoilMachine.cpp:288-298 compiles
+  // unchanged against it.  Each particle is a batch of ONE on the device - a kernel launch and a read-back per
+  // step - so this is the slow, source-compatible path; run() below is the same loop as one batch.
+  double volume = 1.0, sediment = 0.0;
+  int spill = 3;
+  ivec2 ipos;
+  SurfType contains = 0;
+  explicit WaterParticle(Layermap& map) {                     // water.h:11-19
+    map.push_tables();
+    const std::vector<float> xy = detail::spawn(map, 1);
+    map.touch();
+    map.ck(sm_water_begin(map.ctx, 1, xy.data()));
+    refresh(map);
+  }
+  // move() runs the whole particle-step (move && interact are one fused step on the device) and remembers
+  // how it ended; interact() reports it.  `while (p.move(..) && p.interact(..));` therefore behaves as upstream:
+  // move() is false when the particle stalled or left the map (water.h:56-57,65-69), interact() is false when
+  // it evaporated (water.h:119).
+  template <class VP> bool move(Layermap& map, VP&) {
+    sm_stats st{};
+    map.touch();
+    map.ck(sm_water_sweeps(map.ctx, 1, &st));
+    refresh(map);
+    survived = st.alive > 0;
+    return st.steps > 0;
+  }
+  template <class VP> bool interact(Layermap&, VP&) { return survived; }
+  template <class VP> bool flood(Layermap& map, VP&) {        // water.h:123-145 (always returns false)
+    map.touch();
+    map.ck(sm_set_volume_factor(map.ctx, volumeFactor));
+    sm_hydro_stats st{};
+    map.ck(sm_water_flood(map.ctx, &st));
+    detail::nested_ctor_draws(st.nested);
+    return false;
+  }
+  // static WaterParticle::cascade(vec2, ..., spill) / seep(vec2, ...) for one cell (water.h:151,285)
+  template <class VP> static void cascade(vec2 p, Layermap& map, VP&, int spill_ = 0) {
+    map.touch();
+    map.ck(sm_set_volume_factor(map.ctx, volumeFactor));
+    map.ck(sm_cell_water_cascade(map.ctx, (int)p.x, (int)p.y, spill_));      // ivec2 ipos = pos truncates (:153)
+  }
+  template <class VP> static void seep(vec2 p, Layermap& map, VP&) {
+    map.touch();
+    map.ck(sm_cell_seep(map.ctx, (int)p.x, (int)p.y));
+  }
+
+  // ---- the batch entry points ------------------------------------------------------------------------------------
+  WaterParticle() {}
   template <class VP> static sm_stats run(Layermap& map, VP&, int NWATER) {
     map.push_tables();                                        // upstream reads soils[] live (GUI sliders, :165-200)
     std::vector<float> xy = detail::spawn(map, NWATER);
     sm_stats st{};
+    map.touch();
     map.ck(sm_water_run(map.ctx, NWATER, xy.data(), 0, &st));
     return st;
   }
   // The flood tail of the per-particle loop (SoilMachine.cpp:292-296, water.h:123-145) for the whole batch:
   // every finished particle of the last run() floods, in ascending particle index.
-  template <class VP> static sm_hydro_stats flood(Layermap& map, VP&) {
-    if (volumeFactor != 0.015) throw Error(SM_ERR_INVALID, "WaterParticle::volumeFactor is fixed at 0.015 on the device");
+  template <class VP> static sm_hydro_stats flood_batch(Layermap& map, VP&) {
     sm_hydro_stats st{};
+    map.touch();
+    map.ck(sm_set_volume_factor(map.ctx, volumeFactor));
     map.ck(sm_water_flood(map.ctx, &st));
+    detail::nested_ctor_draws(st.nested);
     return st;
   }
   // WaterParticle::seep(map, vertexpool), water.h:335-343 / SoilMachine.cpp:300-301
   template <class VP> static sm_hydro_stats seep(Layermap& map, VP&) {
-    if (volumeFactor != 0.015) throw Error(SM_ERR_INVALID, "WaterParticle::volumeFactor is fixed at 0.015 on the device");
     sm_hydro_stats st{};
+    map.touch();
+    map.ck(sm_set_volume_factor(map.ctx, volumeFactor));
     map.ck(sm_seep(map.ctx, &st));
+    detail::nested_ctor_draws(st.nested);
     return st;
   }
   // water.h:358-365 + 353-356 fused on the device: frequency <- blend(track), track <- 0
@@ -257,16 +397,49 @@ struct WaterParticle : Particle {
     map.ck(sm_get_frequency(map.ctx, f.data(), nullptr, nullptr));
     return f;
   }
+ private:
+  bool survived = true;
+  void refresh(Layermap& map) {
+    float p2[2], s2[2]; double v, sed; int32_t c, al;
+    map.ck(sm_water_state(map.ctx, p2, s2, &v, &sed, &c, &al));
+    pos = vec2(p2[0], p2[1]); speed = vec2(s2[0], s2[1]); volume = v; sediment = sed; contains = (SurfType)c;
+    isalive = al != 0;
+    ipos = ivec2((int)std::round(pos.x), (int)std::round(pos.y));
+  }
 };
 // wind.h:11-140 -- the batch entry point replaces the loop SoilMachine.cpp:304-307
 struct WindParticle : Particle {
   inline static float* frequency = nullptr;                   // wind.h:48; refreshed at the end of run()
   static void init() {}
   static void init(int dimx, int dimy) { delete[] frequency; frequency = new float[(size_t)dimx * dimy](); }
+
+  // per-particle interface (wind.h:13-22,54,94), see WaterParticle
+  vec3 speed{-2.f, 0.f, 1.f};                                 // shadows Particle::speed, as upstream (wind.h:29)
+  double sediment = 0.0, height = 0.0;
+  ivec2 ipos;
+  SurfType contains = 0;
+  explicit WindParticle(Layermap& map) {
+    map.push_tables();
+    const std::vector<float> xy = detail::spawn(map, 1);
+    map.touch();
+    map.ck(sm_wind_begin(map.ctx, 1, xy.data()));
+    refresh(map);
+  }
+  template <class VP> bool move(Layermap& map, VP&) {         // false: the particle died in move() (wind.h:56,83-88)
+    sm_stats st{};
+    map.touch();
+    map.ck(sm_wind_sweeps(map.ctx, 1, &st));
+    refresh(map);
+    return st.steps > 0;
+  }
+  template <class VP> bool interact(Layermap&, VP&) { return true; }   // wind.h:94-136 always returns true
+
+  WindParticle() {}
   template <class VP> static sm_stats run(Layermap& map, VP&, int NWIND) {
     map.push_tables();
     std::vector<float> xy = detail::spawn(map, NWIND);
     sm_stats st{};
+    map.touch();
     map.ck(sm_wind_run(map.ctx, NWIND, xy.data(), 0, &st));
     if (frequency) map.ck(sm_get_frequency(map.ctx, nullptr, nullptr, frequency));
     return st;
@@ -275,6 +448,14 @@ struct WindParticle : Particle {
     std::vector<float> f((size_t)map.dim.x * map.dim.y);
     map.ck(sm_get_frequency(map.ctx, nullptr, nullptr, f.data()));
     return f;
+  }
+ private:
+  void refresh(Layermap& map) {
+    float p2[2], s3[3]; double h, sed; int32_t c, al;
+    map.ck(sm_wind_state(map.ctx, p2, s3, &h, &sed, &c, &al));
+    pos = vec2(p2[0], p2[1]); speed = vec3{s3[0], s3[1], s3[2]}; height = h; sediment = sed; contains = (SurfType)c;
+    isalive = al != 0;
+    ipos = ivec2((int)std::round(pos.x), (int)std::round(pos.y));
   }
 };
 

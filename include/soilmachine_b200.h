@@ -157,6 +157,16 @@ int sm_cell_cascade(sm_context* ctx, float x, float y, int32_t transferloop);  /
 int sm_cell_query(sm_context* ctx, int32_t x, int32_t y, double* height, int32_t* surface,
                   float* normal3);  /* layermap.h:422,417,341 */
 int sm_height_bilinear(sm_context* ctx, float x, float y, double* height); /* layermap.h:427 */
+/* one whole column bottom -> top (Layermap::top(ivec2) and its prev chain, layermap.h:150-152); *n = number of
+ * sections in the column, at most `capacity` of them are written */
+int sm_cell_column(sm_context* ctx, int32_t x, int32_t y, int32_t capacity, int32_t* n, int32_t* type, double* size,
+                   double* floor, double* saturation);
+/* static WaterParticle::seep(vec2, ...) (water.h:285-333) and WaterParticle::cascade(vec2, ..., spill)
+ * (water.h:151-283, nested particles included) for one cell */
+int sm_cell_seep(sm_context* ctx, int32_t x, int32_t y);
+int sm_cell_water_cascade(sm_context* ctx, int32_t x, int32_t y, int32_t spill);
+/* WaterParticle::volumeFactor (water.h:33,368: a mutable static upstream, default 0.015) for later floods */
+int sm_set_volume_factor(sm_context* ctx, double volume_factor);
 
 /* ---- the hot path --------------------------------------------------------------------------- */
 /* One batch of n particles run to completion in lockstep sweeps: in every sweep each live particle,

@@ -212,6 +212,10 @@ class Ref:
         self.lib.smref_water_run(len(xy), _p(xy, C.c_float), int(max_sweeps), C.byref(st))
         return st
 
+    def set_volume_factor(self, v):
+        self.lib.smref_set_volume_factor.argtypes = [C.c_double]
+        self.lib.smref_set_volume_factor(float(v))
+
     def water_flood(self):
         """flood() for every finished particle of the last water batch, ascending index; returns the count."""
         self.lib.smref_water_flood.restype = C.c_int64

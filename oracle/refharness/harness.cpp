@@ -360,6 +360,8 @@ void smref_water_run(int n, const float* xy, int max_sweeps, Stats* st) {
 // (water.h:123-145), in ascending particle index.  A flood is atomic: the nested particles
 // WaterParticle::cascade (water.h:151-283) spawns run to completion inside it, as upstream.  flood()
 // itself decides who floods (volume >= minvol and spill left).  Returns how many did.
+// WaterParticle::volumeFactor is a mutable static upstream (water.h:33,368)
+void smref_set_volume_factor(double v) { WaterParticle::volumeFactor = v; }
 int64_t smref_water_flood(void) {
   vector<char> live(g.water.size(), 0);
   for (int i : g.water_live) live[i] = 1;

@@ -31,7 +31,7 @@ SYMBOLS = [
     "sm_upload_columns", "sm_section_count", "sm_download_columns", "sm_download_height",
     "sm_download_surface", "sm_height_sum", "sm_checksum", "sm_get_frequency", "sm_set_frequency",
     "sm_frequency_update", "sm_cell_add", "sm_cell_remove", "sm_cell_cascade", "sm_cell_query",
-    "sm_height_bilinear", "sm_water_run", "sm_wind_run", "sm_water_run_device", "sm_wind_run_device",
+    "sm_height_bilinear", "sm_cell_column", "sm_cell_seep", "sm_cell_water_cascade", "sm_set_volume_factor", "sm_water_run", "sm_wind_run", "sm_water_run_device", "sm_wind_run_device",
     "sm_last_stats", "sm_water_begin", "sm_water_sweeps", "sm_water_state", "sm_wind_begin",
     "sm_wind_sweeps", "sm_wind_state", "sm_launch_count", "sm_device_alloc", "sm_device_free",
     "sm_device_upload", "sm_timer_start", "sm_timer_stop", "sm_set_soil_colors", "sm_mesh_update",
@@ -298,6 +298,24 @@ class Context:
     def wind_run(self, xy, max_sweeps=0):
         self._n["wind"] = len(xy)
         return self._run(self.lib.sm_wind_run, xy, max_sweeps)
+
+    def set_volume_factor(self, v):
+        self.lib.sm_set_volume_factor.argtypes = [C.c_void_p, C.c_double]
+        self._ck(self.lib.sm_set_volume_factor(self.h, float(v)))
+
+    def cell_column(self, x, y, capacity=64):
+        n = C.c_int32()
+        typ = np.zeros(capacity, np.int32); size = np.zeros(capacity); fl = np.zeros(capacity); sat = np.zeros(capacity)
+        self._ck(self.lib.sm_cell_column(self.h, int(x), int(y), int(capacity), C.byref(n), _p(typ, C.c_int32),
+                                         _p(size, C.c_double), _p(fl, C.c_double), _p(sat, C.c_double)))
+        m = min(n.value, capacity)
+        return {"n": n.value, "type": typ[:m], "size": size[:m], "floor": fl[:m], "saturation": sat[:m]}
+
+    def cell_seep(self, x, y):
+        self._ck(self.lib.sm_cell_seep(self.h, int(x), int(y)))
+
+    def cell_water_cascade(self, x, y, spill=0):
+        self._ck(self.lib.sm_cell_water_cascade(self.h, int(x), int(y), int(spill)))
 
     def water_flood(self):
         """flood() of every finished particle of the last water batch (water.h:123-145), ascending index."""

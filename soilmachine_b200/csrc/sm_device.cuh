@@ -79,6 +79,7 @@ struct DevCtx {
   const SoilDev* soils;
   int nsoils;
   int dimx, dimy, scale;
+  double volume_factor;          // WaterParticle::volumeFactor (water.h:368), default 0.015
   RunCtl* ctl;
   // particle batch
   float4* pa;        // water: px,py,sx,sy        | wind: px,py,sx,sy
@@ -234,6 +235,8 @@ struct DevAccess {
   __device__ __forceinline__ void cascade_prefetch(int, int) {}
   __device__ __forceinline__ void mark(int) {}
   __device__ __forceinline__ void note_transfer() {}
+  __device__ __forceinline__ void wet_mark(int, int) {}
+  __device__ __forceinline__ double volume_factor() const { return c.volume_factor; }
   __device__ __forceinline__ void focus(int, int) {}
   __device__ __forceinline__ Sec32 pool_load(uint32_t i) { return c.pool[i]; }
   __device__ __forceinline__ void pool_store(uint32_t i, const Sec32& r) { c.pool[i] = r; }

@@ -1023,7 +1023,29 @@ __global__ void k_cell_op(DevCtx c, CellOp o, CellRes* res) {
     sm_f3 n = map_normal(a, o.x, o.y);
     r.n[0] = n.x; r.n[1] = n.y; r.n[2] = n.z;
   } else if (o.op == 4) r.d = map_height_bilinear(a, o.fx, o.fy);
+  else if (o.op == 5) hydro_seep_cell(a, o.x, o.y);                 // WaterParticle::seep(vec2,...), water.h:285-333
+  else if (o.op == 6) {                                             // WaterParticle::cascade(vec2,...,spill), water.h:151-283
+    HydroCount hc{};
+    WFrame st[SM_WSTACK];
+    int sp = 0;
+    hydro_push(a, st, sp, o.x, o.y, o.t, hc);
+    hydro_drain(a, st, sp, hc);
+  }
   *res = r;
+}
+// one whole column, bottom -> top, for the facade's Layermap::top(ivec2) (layermap.h:150-152)
+__global__ void k_cell_column(DevCtx c, int x, int y, int cap, int* n_out, Sec32* out) {
+  Sec32 r = c.top[(size_t)x * c.dimy + y];
+  int n = 0;
+  if (r.type != SM_EMPTY) {
+    for (;;) {
+      if (n < cap) out[n] = r;
+      n++;
+      if (r.below == SM_NIL) break;
+      r = c.pool[r.below];
+    }
+  }
+  *n_out = n;       // top first; the host reverses
 }
 
 
@@ -1334,6 +1356,7 @@ static int create_impl(const sm_config* cfg, int nranks, int rank, int share, sm
     CK(cudaEventCreate(&ctx->evt1));
     DevCtx& d = ctx->d;
     d.dimx = cfg->dimx; d.dimy = cfg->dimy; d.scale = cfg->scale;
+    d.volume_factor = SM_VOLUME_FACTOR;
     ctx->cells = (size_t)cfg->dimx * cfg->dimy;
     ctx->nranks = nranks; ctx->rank = rank; ctx->share = share; ctx->x0 = sx0; ctx->x1 = sx1;
     ctx->lcells = (size_t)(sx1 - sx0) * cfg->dimy;
@@ -1718,6 +1741,50 @@ int sm_cell_query(sm_context* ctx, int32_t x, int32_t y, double* height, int32_t
   if (height) *height = r.d;
   if (surface) *surface = r.surface;
   if (normal3) { normal3[0] = r.n[0]; normal3[1] = r.n[1]; normal3[2] = r.n[2]; }
+  return SM_OK;
+}
+int sm_cell_seep(sm_context* ctx, int32_t x, int32_t y) {
+  if (!inb(ctx, x, y)) return fail(ctx, SM_ERR_INVALID, "sm_cell_seep: range");
+  ctx->mesh_valid = false;
+  return cell_op(ctx, CellOp{5, x, y, 0.f, 0.f, 0.0, 0}, nullptr);
+}
+int sm_cell_water_cascade(sm_context* ctx, int32_t x, int32_t y, int32_t spill) {
+  if (!inb(ctx, x, y) || spill < 0 || spill > 3) return fail(ctx, SM_ERR_INVALID, "sm_cell_water_cascade: range (spill 0..3)");
+  ctx->mesh_valid = false;
+  return cell_op(ctx, CellOp{6, x, y, 0.f, 0.f, 0.0, spill}, nullptr);
+}
+int sm_cell_column(sm_context* ctx, int32_t x, int32_t y, int32_t capacity, int32_t* n, int32_t* type, double* size,
+                   double* floor_, double* saturation) {
+  if (!inb(ctx, x, y) || !n || capacity < 0) return fail(ctx, SM_ERR_INVALID, "sm_cell_column: range");
+  if (ctx->nranks > 1) return fail(ctx, SM_ERR_INVALID, "single-cell operations are not available on a sharded context");
+  CK(cudaSetDevice(ctx->cfg.device));
+  const int cap = std::min(capacity, 1024);
+  Sec32* d_out = nullptr; int* d_n = nullptr;
+  CK(cudaMalloc(&d_out, (size_t)std::max(cap, 1) * sizeof(Sec32)));
+  if (cudaMalloc(&d_n, sizeof(int)) != cudaSuccess) { cudaFree(d_out); return fail(ctx, SM_ERR_CUDA, "cudaMalloc"); }
+  k_cell_column<<<1, 1, 0, ctx->stream>>>(ctx->d, x, y, cap, d_n, d_out);
+  ctx->launches++;
+  std::vector<Sec32> tmp((size_t)std::max(cap, 1));
+  int cnt = 0;
+  cudaError_t e = cudaMemcpyAsync(&cnt, d_n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(tmp.data(), d_out, tmp.size() * sizeof(Sec32), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_out); cudaFree(d_n);
+  if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return SM_ERR_CUDA; }
+  *n = cnt;
+  const int m = std::min(cnt, cap);
+  for (int i = 0; i < m; i++) {       // bottom -> top
+    const Sec32& r = tmp[(size_t)(m - 1 - i)];
+    if (type) type[i] = (int32_t)r.type;
+    if (size) size[i] = r.size;
+    if (floor_) floor_[i] = r.floor;
+    if (saturation) saturation[i] = r.saturation;
+  }
+  return SM_OK;
+}
+int sm_set_volume_factor(sm_context* ctx, double v) {
+  if (!(v > 0.0)) return fail(ctx, SM_ERR_INVALID, "sm_set_volume_factor: must be positive");
+  ctx->d.volume_factor = v;
   return SM_OK;
 }
 int sm_height_bilinear(sm_context* ctx, float x, float y, double* height) {

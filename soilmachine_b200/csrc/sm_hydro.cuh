@@ -20,7 +20,7 @@
 #pragma once
 #include "sm_core.cuh"
 
-#define SM_VOLUME_FACTOR 0.015   // WaterParticle::volumeFactor, water.h:368
+#define SM_VOLUME_FACTOR 0.015   // default of WaterParticle::volumeFactor (water.h:368, a mutable static upstream: a.volume_factor())
 #define SM_MINVOL 0.01           // WaterParticle::minvol, water.h:31
 #define SM_WSTACK 6              // open water-cascade frames (4 needed, see above)
 
@@ -135,7 +135,7 @@ template <class A> SM_HD_NOINLINE void hydro_flood(A& a, const WaterP& p, int sp
   a.dirty_rec(r, ix, iy);
   Cascade<0, A>::run(a, (int)roundf(p.px), (int)roundf(p.py), 0);   // :134
   a.focus(ix, iy);
-  col_add(a, *r, p.volume * SM_VOLUME_FACTOR, SM_AIR);              // :138
+  col_add(a, *r, p.volume * a.volume_factor(), SM_AIR);            // :138
   a.dirty_rec(r, ix, iy);
   hydro_seep_cell(a, ix, iy);                                       // :139
   hydro_push(a, st, sp, ix, iy, spill, hc);                         // :140
@@ -189,7 +189,7 @@ template <class A> SM_HD_NOINLINE void hydro_drain(A& a, WFrame* st, int& sp, Hy
         q.sx = SM_SQRT2F * (dx * inv);
         q.sy = SM_SQRT2F * (dy * inv);
       }
-      q.volume = transfer / SM_VOLUME_FACTOR;                       // :250
+      q.volume = transfer / a.volume_factor();                     // :250
       q.sediment = 0.0;
       // the ctor reads `contains` at a rand() position (water.h:13-17); the value cannot reach the map:
       // deposits need sediment > 0, which only an erosion produces, and every erosion re-derives contains

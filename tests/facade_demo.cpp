@@ -32,7 +32,7 @@ int main(int argc, char** argv) {
     Layermap map(SEED, ivec2(SIZEX, SIZEY), vertexpool, SCALE);   // :83
     for (int frame = 0; frame < 2; frame++) {                // the body of Tiny::loop, :287-320
       sm_stats w = WaterParticle::run(map, vertexpool, NWATER);
-      sm_hydro_stats fl = WaterParticle::flood(map, vertexpool);   // :296, for the whole batch
+      sm_hydro_stats fl = WaterParticle::flood_batch(map, vertexpool);   // :296, for the whole batch
       sm_hydro_stats se = WaterParticle::seep(map, vertexpool);    // :300-301
       sm_stats d = WindParticle::run(map, vertexpool, NWIND);
       WaterParticle::mapfrequency(map);

@@ -19,6 +19,7 @@ struct HostMap {
   std::vector<SoilDev> soils;
   std::vector<float> wfreq, wtrack, windfreq;
   int64_t drops = 0;
+  double volume_factor = SM_VOLUME_FACTOR;
 } M;
 ActiveMap* G_act = nullptr;   // seep pass with the active-cell index: cells the executor makes wet are flagged
 
@@ -36,6 +37,7 @@ struct HostAccess {
   void dirty(int x, int y) { dirty_rec(rec(x, y), x, y); }
   void dirty_rec(Sec32* r, int x, int y) { if (G_act && r->type == SM_AIR) active_mark_block(*G_act, x, y, M.dimx, M.dimy); }
   void wet_mark(int x, int y) { if (G_act) active_set(*G_act, (unsigned long long)x * M.dimy + y); }
+  double volume_factor() const { return M.volume_factor; }
   void cascade_prefetch(int, int) {}
   void mark(int) {}
   void note_transfer() {}
@@ -164,6 +166,7 @@ double hs_remove(int x, int y, double h) { HostAccess a; return col_remove(a, *a
 void hs_cascade(float x, float y, int loop) { HostAccess a; Cascade<3, HostAccess>::run(a, (int)roundf(x), (int)roundf(y), loop); }
 
 void hs_set_mode(int coop, int lane_order) { G_coop = coop; G_lane_order = lane_order; }
+void hs_set_volume_factor(double v) { M.volume_factor = v; }
 void hs_water_begin(int n, const float* xy) {
   HostAccess a; W.clear(); Wlive.clear();
   for (int i = 0; i < n; i++) {

@@ -83,6 +83,15 @@ def test_cpp_facade_compiles_and_links():
         assert "legacy ops ok" in out.stdout
     else:
         assert out.returncode == 77 and "no CUDA device" in out.stdout
+    # the reference's per-particle loop, unchanged, against the facade (runs on the GPU tier)
+    exe2 = os.path.join(ROOT, "tests", "hostsim", "facade_loop")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", os.path.join(ROOT, "tests", "facade_loop.cpp"),
+                           "-o", exe2, "-L" + libdir, "-lsoilmachine_b200", "-Wl,-rpath," + libdir])
+    if not torch.cuda.is_available():
+        from oracle import refapi
+        out = subprocess.run([exe2, refapi.soil_path("default"), "32", "2", "1", "1", "/dev/null"], capture_output=True,
+                             text=True, timeout=120)
+        assert out.returncode == 77 and "no CUDA device" in out.stdout
 
 
 def test_soil_file_parser_matches_reference_loader(ref):

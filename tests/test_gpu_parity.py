@@ -559,3 +559,46 @@ def test_ipc_sharded_two_processes_one_gpu():
     os.makedirs(logdir, exist_ok=True)
     with open(os.path.join(logdir, "ipc_one_gpu.log"), "w") as f:
         f.write(line[0] + "\n")
+
+
+@pytest.mark.parametrize("soil,dim,nw,nd", [("default", 64, 40, 0), ("rocksand", 64, 24, 16)])
+def test_facade_per_particle_loop_matches_reference(ref, soil, dim, nw, nd, tmp_path):
+    """tests/facade_loop.cpp = the reference's frame loop with its per-particle calls (construct, `while (move &&
+    interact);`, flood, seep pass, wind particles, frequency maps), compiled UNCHANGED against the C++ facade.  Run
+    particle by particle it is upstream's own sequential order, so the map must equal the reference's sequential loop
+    on the same seed bit for bit - spawn positions included, because the facade consumes the rand() draws upstream's
+    nested particle constructors make (water.h:243)."""
+    import os
+    import struct
+    import subprocess
+    from oracle import refapi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "hostsim", "facade_loop")
+    libdir = os.path.join(root, "soilmachine_b200", "lib")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", os.path.join(root, "tests", "facade_loop.cpp"), "-o", exe,
+                           "-L" + libdir, "-lsoilmachine_b200", "-Wl,-rpath," + libdir])
+    outbin = str(tmp_path / "map.bin")
+    out = subprocess.run([exe, refapi.soil_path(soil), str(dim), str(nw), str(nd), "1", outbin], capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0 and "facade loop ok: 2 mesh uploads of %d vertices" % (dim * dim) in out.stdout, \
+        out.stdout + out.stderr
+    ref.init(soil, seed=42, dimx=dim, dimy=dim, poolsize=dim * dim * 4 + 1000000)
+    ref.lib.smref_srand(42)
+    ref.water_seq(nw, flood=True, seep=True)
+    if nd:
+        ref.wind_seq(nd)
+    ref.frequency_update()
+    cols, hts = ref.columns(), ref.heights().reshape(-1)
+    raw = open(outbin, "rb").read()
+    pos = 0
+    for c in range(dim * dim):
+        (n,) = struct.unpack_from("<i", raw, pos); pos += 4
+        lo, hi = int(cols["offsets"][c]), int(cols["offsets"][c + 1])
+        assert n == hi - lo, "cell %d: %d sections vs %d" % (c, n, hi - lo)
+        for k in range(n):                       # the dump walks top -> bottom
+            t, size, floor, sat = struct.unpack_from("<qddd", raw, pos); pos += 32
+            j = hi - 1 - k
+            assert (t, size, floor, sat) == (int(cols["type"][j]), cols["size"][j], cols["floor"][j], cols["saturation"][j]), \
+                "cell %d section %d" % (c, k)
+        (h,) = struct.unpack_from("<d", raw, pos); pos += 8
+        assert h == hts[c], "cell %d height" % c
