@@ -53,8 +53,9 @@ typedef struct sm_config {
   int32_t device;           /* CUDA device ordinal */
   int64_t pool_capacity;    /* buried-section pool slots (POOLSIZE, SoilMachine.cpp:16); 0 = auto */
   int32_t max_particles;    /* largest batch a *_run call will be given; 0 = 262144 */
-  int32_t flags;            /* reserved, 0 */
+  int32_t flags;            /* SM_FLAG_* */
 } sm_config;
+#define SM_FLAG_BUDGET 1      /* keep the per-particle mass budget (sm_last_budget); a few % slower */
 
 /* Per-call counters (all accumulated over the call). */
 typedef struct sm_stats {
@@ -84,7 +85,7 @@ int sm_sync(sm_context* ctx);
  * (x - x0)*dimy + y) and sm_*_run_device must be called on EVERY rank (the kernels meet in a cross-rank
  * barrier every sweep); results are bit-identical to the unsharded run.  share = number of contexts
  * that run their kernels concurrently on this device. */
-#define SM_PEER_ARRAYS 15
+#define SM_PEER_ARRAYS 16
 typedef struct sm_peer_blob {
   uint64_t ptr[16];
   unsigned char ipc[16][64];
@@ -181,6 +182,27 @@ int sm_wind_run(sm_context* ctx, int32_t n, const float* spawn_xy, int32_t max_s
 int sm_water_run_device(sm_context* ctx, int32_t n, const float* d_spawn_xy, int32_t max_sweeps);
 int sm_wind_run_device(sm_context* ctx, int32_t n, const float* d_spawn_xy, int32_t max_sweeps);
 int sm_last_stats(sm_context* ctx, sm_stats* stats);
+
+/* Mass budget of the last batch (contexts created with SM_FLAG_BUDGET).  The reference is not conservative -
+ * sediment is discarded when a particle dies, clamped at 1 (water.h:117), cascade transfers are narrowed to f32
+ * (particle.h:87-91), negative wind forces lower sediment without touching the map (wind.h:107-110) - so "mass
+ * conservation" is a budget: every term is accumulated per particle in step order and summed in particle order,
+ * bit-identical to the oracle port's accumulators (oracle/sm_oracle.cpp) on any number of GPUs.
+ * Identity: change of (sum of all column heights) = deposited - eroded + cascade_net, to rounding. */
+typedef struct sm_budget {
+  double eroded;         /* height taken off the map by erosion           (water.h:98-100, wind.h:109) */
+  double deposited;      /* height put on the map by deposition           (water.h:109, wind.h:123-124) */
+  double cascade_net;    /* net height change of the cascade transfers    (particle.h:87-92) */
+  double discarded;      /* water: sediment x volume lost at evaporation / map exit (water.h:65-69,118-119);
+                            wind: sediment lost when the particle dies (wind.h:83-88) */
+  double clamped;        /* water.h:117: (sediment - 1) x volume cut off */
+  double wind_negative;  /* wind.h:107-110: sum of the negative suspension*force terms */
+  int64_t particles;     /* particles of the batch */
+} sm_budget;
+int sm_last_budget(sm_context* ctx, sm_budget* budget);
+/* the raw accumulators, 6 per particle (order as in sm_budget), for reductions over the ranks of a sharded map:
+ * exactly one rank holds a particle's sums, the others hold zeros */
+int sm_budget_particles(sm_context* ctx, int32_t n, double* out6n);
 
 /* Stepping interface for parity tests: begin a batch, advance k sweeps, read particle state. */
 int sm_water_begin(sm_context* ctx, int32_t n, const float* spawn_xy);

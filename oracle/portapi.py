@@ -143,6 +143,15 @@ class Port:
         self._nd = len(xy)
         return self._run(self.lib.smo_wind_run, xy, max_sweeps)
 
+    def budget(self):
+        """mass budget of the last lockstep batch: (per-particle accumulators [n, 6], their sums in particle order
+        [6]) - eroded, deposited, cascade_net, discarded, clamped, wind_negative (sm_coop.cuh)"""
+        self.lib.smo_budget.restype = C.c_int64
+        n = int(self.lib.smo_budget(None, None))
+        per = np.zeros((n, 6)); sums = np.zeros(6)
+        self.lib.smo_budget(_p(per, C.c_double), _p(sums, C.c_double))
+        return per, sums
+
     def water_seq(self, xy):
         return self._run(self.lib.smo_water_seq, xy)
 

@@ -121,6 +121,12 @@ double remove(int x, int y, double h) {                      // Layermap::remove
   return 0.0;
 }
 
+// ---- mass budget -------------------------------------------------------------------------
+// Six accumulators per particle-step, same definitions and same order of additions as the product's step
+// (soilmachine_b200/csrc/sm_coop.cuh: eroded, deposited, cascade_net, discarded, clamped, wind_negative).  ACC
+// points at the current step's six slots, or is null (hydrology, single-cell calls).
+double* ACC = nullptr;
+
 // ---- Particle::cascade, particle.h:24-101 ------------------------------------------------------------
 void cascade(V2 pos, int transferloop) {
   const int ix = (int)std::round(pos.x), iy = (int)std::round(pos.y);
@@ -154,8 +160,10 @@ void cascade(V2 pos, int transferloop) {
     bool recascade = false;
     const double topsize = at(tx, ty).empty() ? 0.0 : at(tx, ty).back().size;
     if (transfer > topsize) transfer = topsize;              // :87-88 narrowing f64 -> f32
+    const double ht0 = height(tx, ty), hb0 = height(bx, by);
     if (remove(tx, ty, transfer) != 0) recascade = true;
     add(bx, by, transfer, param.cascades);
+    if (ACC) ACC[2] += (height(tx, ty) - ht0) + (height(bx, by) - hb0);
     if (recascade && transferloop > 0) cascade({(float)nx, (float)ny}, --transferloop);
   }
 }
@@ -198,6 +206,7 @@ bool water_move(Water& p) {                                  // water.h:43-73
   p.pos.x += p.speed.x; p.pos.y += p.speed.y;
   if (!(p.pos.x >= 0.0f && p.pos.y >= 0.0f) ||
       !(p.pos.x < (float)W.dimx - 1.0f && p.pos.y < (float)W.dimy - 1.0f)) {
+    if (ACC) ACC[3] += p.sediment * p.volume;
     p.volume = 0.0;
     return false;
   }
@@ -213,16 +222,25 @@ bool water_interact(Water& p) {                              // water.h:75-121
   if (cdiff > 0) {
     p.sediment += p.param.equrate * cdiff;
     p.contains = W.soils[surface(p.ix, p.iy)].transports;
+    const double h0 = height(p.ix, p.iy);
     double diff = remove(p.ix, p.iy, p.param.equrate * cdiff * p.volume);
     while (std::fabs(diff) > 1E-8) diff = remove(p.ix, p.iy, diff);
+    if (ACC) ACC[0] += h0 - height(p.ix, p.iy);
   } else if (cdiff < 0) {
     p.sediment += W.soils[p.contains].equrate * cdiff;
+    const double h0 = height(p.ix, p.iy);
     add(p.ix, p.iy, -W.soils[p.contains].equrate * cdiff * p.volume, p.contains);
+    if (ACC) ACC[1] += height(p.ix, p.iy) - h0;
   }
   cascade(p.pos, 0);
   p.sediment /= (1.0 - p.evaprate);
+  const double over = p.sediment - 1.0;
   if (p.sediment > 1.0) p.sediment = 1.0;
   p.volume *= (1.0 - p.evaprate);
+  if (ACC) {
+    if (over > 0.0) ACC[4] += over * p.volume;
+    if (!(p.volume > 0.01)) ACC[3] += p.sediment * p.volume;
+  }
   return p.volume > 0.01;
 }
 
@@ -366,9 +384,11 @@ bool wind_move(Wind& p) {                                    // wind.h:54-92
   p.speed = mixd(p.speed, {-2, 0, 1}, 0.2);
   p.pos.x += p.speed.x; p.pos.y += p.speed.z;
   p.height += p.speed.y;
-  if (!(p.pos.x >= 0.0f && p.pos.y >= 0.0f) || !((int)p.pos.x < W.dimx - 1 && (int)p.pos.y < W.dimy - 1))
+  if (!(p.pos.x >= 0.0f && p.pos.y >= 0.0f) || !((int)p.pos.x < W.dimx - 1 && (int)p.pos.y < W.dimy - 1) ||
+      std::sqrt(p.speed.x * p.speed.x + p.speed.y * p.speed.y + p.speed.z * p.speed.z) < 0.01) {
+    if (ACC) ACC[3] += p.sediment;
     return false;
-  if (std::sqrt(p.speed.x * p.speed.x + p.speed.y * p.speed.y + p.speed.z * p.speed.z) < 0.01) return false;
+  }
   return true;
 }
 bool wind_interact(Wind& p) {                                // wind.h:94-136
@@ -377,14 +397,20 @@ bool wind_interact(Wind& p) {                                // wind.h:94-136
     if (p.param.transports == p.contains) {
       const float len = std::sqrt(p.speed.x * p.speed.x + p.speed.y * p.speed.y + p.speed.z * p.speed.z);
       double force = len * (height(nx, ny) - p.height) * (float)W.SCALE / 80.0f * (1.0f - p.sediment);
+      const double h0 = height(p.ix, p.iy);
       double diff = remove(p.ix, p.iy, p.param.suspension * force);
+      if (ACC) { ACC[0] += h0 - height(p.ix, p.iy); if (p.param.suspension * force < 0.0) ACC[5] += p.param.suspension * force; }
       p.sediment += (p.param.suspension * force - diff);
       cascade({(float)p.ix, (float)p.iy}, 1);
     }
   } else if (p.param.suspension > 0.0) {
     p.sediment -= W.soils[p.contains].suspension * p.sediment;
+    double h0 = height(nx, ny);
     add(nx, ny, 0.5f * W.soils[p.contains].suspension * p.sediment, p.contains);
+    if (ACC) ACC[1] += height(nx, ny) - h0;
+    h0 = height(p.ix, p.iy);
     add(p.ix, p.iy, 0.5f * W.soils[p.contains].suspension * p.sediment, p.contains);
+    if (ACC) ACC[1] += height(p.ix, p.iy) - h0;
     cascade({(float)p.ix, (float)p.iy}, 1);
     cascade({(float)nx, (float)ny}, 1);
   }
@@ -393,6 +419,15 @@ bool wind_interact(Wind& p) {                                // wind.h:94-136
 
 std::vector<Water> WP; std::vector<int> Wlive;
 std::vector<Wind> DP; std::vector<int> Dlive;
+std::vector<double> BUD;          // 6 accumulators per particle of the current lockstep batch
+// run one particle-step with the budget attached: the step's six sums are added to the particle's totals
+template <class F> inline void with_budget(int i, F f) {
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  ACC = acc;
+  f();
+  ACC = nullptr;
+  for (int k = 0; k < 6; k++) BUD[(size_t)i * 6 + k] += acc[k];
+}
 double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 }  // namespace
@@ -449,20 +484,32 @@ double smo_remove(int x, int y, double h) { return remove(x, y, h); }
 void smo_cascade(float x, float y, int loop) { cascade({x, y}, loop); }
 
 void smo_water_begin(int n, const float* xy) {
-  WP.assign(n, Water()); Wlive.clear();
+  WP.assign(n, Water()); Wlive.clear(); BUD.assign((size_t)n * 6, 0.0);
   for (int i = 0; i < n; i++) { water_spawn(WP[i], xy[2 * i], xy[2 * i + 1]); Wlive.push_back(i); }
 }
 int smo_water_sweep(smo_stats* st) {
   std::vector<int> next;
   for (int i : Wlive) {
     Water& p = WP[i];
-    if (!water_move(p)) { if (p.volume == 0.0) st->exit_oob++; else st->exit_stall++; continue; }
+    bool moved = false, lives = false;
+    with_budget(i, [&]() { moved = water_move(p); if (moved) lives = water_interact(p); });
+    if (!moved) { if (p.volume == 0.0) st->exit_oob++; else st->exit_stall++; continue; }
     st->steps++;
-    if (!water_interact(p)) { st->exit_evap++; continue; }
+    if (!lives) { st->exit_evap++; continue; }
     next.push_back(i);
   }
   Wlive.swap(next); st->sweeps++;
   return (int)Wlive.size();
+}
+// mass budget of the current lockstep batch: per-particle accumulators (n x 6) and their sums in particle order
+int64_t smo_budget(double* per_particle, double* sums6) {
+  const size_t n = BUD.size() / 6;
+  if (per_particle) memcpy(per_particle, BUD.data(), BUD.size() * sizeof(double));
+  if (sums6) {
+    for (int k = 0; k < 6; k++) sums6[k] = 0.0;
+    for (size_t i = 0; i < n; i++) for (int k = 0; k < 6; k++) sums6[k] += BUD[i * 6 + k];
+  }
+  return (int64_t)n;
 }
 void smo_water_state(float* pos, float* speed, double* vol, double* sed, int32_t* cont, int32_t* alive) {
   for (size_t i = 0; i < WP.size(); i++) {
@@ -497,16 +544,18 @@ void smo_seep(smo_hydro* out) {
   if (out) *out = H;
 }
 void smo_wind_begin(int n, const float* xy) {
-  DP.assign(n, Wind()); Dlive.clear();
+  DP.assign(n, Wind()); Dlive.clear(); BUD.assign((size_t)n * 6, 0.0);
   for (int i = 0; i < n; i++) { wind_spawn(DP[i], xy[2 * i], xy[2 * i + 1]); Dlive.push_back(i); }
 }
 int smo_wind_sweep(smo_stats* st) {
   std::vector<int> next;
   for (int i : Dlive) {
     Wind& p = DP[i];
-    if (!wind_move(p)) { st->exit_oob++; continue; }
+    bool moved = false, lives = false;
+    with_budget(i, [&]() { moved = wind_move(p); if (moved) lives = wind_interact(p); });
+    if (!moved) { st->exit_oob++; continue; }
     st->steps++;
-    if (!wind_interact(p)) { st->exit_evap++; continue; }
+    if (!lives) { st->exit_evap++; continue; }
     next.push_back(i);
   }
   Dlive.swap(next); st->sweeps++;

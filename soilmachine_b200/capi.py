@@ -36,7 +36,7 @@ SYMBOLS = [
     "sm_wind_sweeps", "sm_wind_state", "sm_launch_count", "sm_device_alloc", "sm_device_free",
     "sm_device_upload", "sm_timer_start", "sm_timer_stop", "sm_set_soil_colors", "sm_mesh_update",
     "sm_mesh_device_ptr", "sm_export_height", "sm_export_color", "sm_create_sharded", "sm_shard_range",
-    "sm_peer_export", "sm_peer_attach", "sm_parse_soil_file", "sm_water_flood", "sm_seep",
+    "sm_peer_export", "sm_peer_attach", "sm_parse_soil_file", "sm_water_flood", "sm_seep", "sm_last_budget", "sm_budget_particles",
 ]
 
 
@@ -58,6 +58,15 @@ class HydroStats(C.Structure):
     _fields_ = [("floods", C.c_int64), ("nested", C.c_int64), ("nested_steps", C.c_int64),
                 ("transfers", C.c_int64), ("cells", C.c_int64), ("device_ms", C.c_double),
                 ("classify_ms", C.c_double)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class Budget(C.Structure):
+    _fields_ = [("eroded", C.c_double), ("deposited", C.c_double), ("cascade_net", C.c_double),
+                ("discarded", C.c_double), ("clamped", C.c_double), ("wind_negative", C.c_double),
+                ("particles", C.c_int64)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -127,10 +136,11 @@ class Context:
     """One sm_context (one GPU, or one rank of a sharded map)."""
 
     def __init__(self, dimx, dimy, scale=80, device=0, pool_capacity=0, max_particles=0,
-                 nranks=1, rank=0, share=1):
+                 nranks=1, rank=0, share=1, budget=False):
         self.lib = load()
         self.dimx, self.dimy, self.scale = int(dimx), int(dimy), int(scale)
-        cfg = Config(self.dimx, self.dimy, self.scale, int(device), int(pool_capacity), int(max_particles), 0)
+        cfg = Config(self.dimx, self.dimy, self.scale, int(device), int(pool_capacity), int(max_particles),
+                     1 if budget else 0)                       # SM_FLAG_BUDGET
         h = C.c_void_p()
         if nranks == 1:
             rc = self.lib.sm_create(C.byref(cfg), C.byref(h))
@@ -316,6 +326,17 @@ class Context:
 
     def cell_water_cascade(self, x, y, spill=0):
         self._ck(self.lib.sm_cell_water_cascade(self.h, int(x), int(y), int(spill)))
+
+    def budget_particles(self, n):
+        """raw mass-budget accumulators [n, 6] of the last batch (context created with budget=True)"""
+        per = np.zeros((int(n), 6))
+        self._ck(self.lib.sm_budget_particles(self.h, int(n), _p(per, C.c_double)))
+        return per
+
+    def last_budget(self):
+        b = Budget()
+        self._ck(self.lib.sm_last_budget(self.h, C.byref(b)))
+        return b
 
     def water_flood(self):
         """flood() of every finished particle of the last water batch (water.h:123-145), ascending index."""

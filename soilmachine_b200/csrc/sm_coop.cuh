@@ -34,6 +34,20 @@
 
 #define SM_CW_SLOTS 18   // patch A = 3x3 around ipos (slots 0-8), patch B = 3x3 around npos (slots 9-17)
 
+// Mass budget (the reference is not conservative, so "mass conservation" is a budget): six f64
+// accumulators per particle, summed in step order, identical in the oracle port (oracle/sm_oracle.cpp).  Heights
+// are column heights (floor + size of the top section) read right before and right after the column operation.
+//   0 eroded        height taken off the map by a particle's erosion      (water.h:98-100, wind.h:109)
+//   1 deposited     height put on the map by a particle's deposition      (water.h:109, wind.h:123-124)
+//   2 cascade_net   (height gained by the lower cell + height lost by the higher cell) summed over the cascade
+//                   transfers: zero but for the f64->f32 narrowing of `transfer` (particle.h:87-91) and rounding
+//   3 discarded     water: sediment x volume the particle still held when it evaporated or left the map
+//                   (water.h:65-69,118-119); wind: sediment it held when it died (wind.h:83-88)
+//   4 clamped       water.h:117: (sediment - 1) x volume cut off by the clamp
+//   5 wind_negative wind.h:107-110: negative suspension*force, i.e. sediment lowered without touching the map
+// Budget identity: d(sum of heights) = deposited - eroded + cascade_net (+ rounding), checked by the tests.
+#define SM_BUDGET_SLOTS 6
+
 // per-warp scratch (shared memory on the device)
 struct
 #if defined(__CUDACC__)
@@ -48,6 +62,8 @@ struct
   uint32_t u;
   unsigned char ord[2][8];    // cascade: ord[depth][rank] = neighbour index
   uint32_t pad_[3];
+  double acc[SM_BUDGET_SLOTS]; // mass budget of the current step (single lane; only with B::kBudget)
+  double pad2_[2];
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -64,6 +80,7 @@ template <class B> struct CoopWin {
   uint32_t valid, dirtym;
   bool has_b;
   float f_freq, f_track;
+  static constexpr bool kBudget = B::kBudget;
   SM_HD CoopWin(B& b_, CoopScratch* s_) : b(b_), s(s_), ax(0), ay(0), bx(0), by(0), valid(0), dirtym(0), has_b(false),
                                           f_freq(0.f), f_track(0.f) {}
   SM_HD int dimx() const { return b.dimx(); }
@@ -217,10 +234,13 @@ template <int DEPTH, class W, class A> struct CascadeCoop {
         Sec32* const tr = ctop ? pc : pn;
         Sec32* const br = ctop ? pn : pc;
         a.b.note_transfer();
+        double ht0 = 0.0, hb0 = 0.0;
+        if (A::kBudget) { ht0 = rec_height(*tr); hb0 = rec_height(*br); }
         a.focus(ctop ? cx : nx, ctop ? cy : ny);
         const bool re = col_remove(a, *tr, (double)transfer) != 0;          // :90-91
         a.focus(ctop ? nx : cx, ctop ? ny : cy);
         col_add(a, *br, (double)transfer, casc);                            // :92
+        if (A::kBudget) a.s->acc[2] += (rec_height(*tr) - ht0) + (rec_height(*br) - hb0);
         a.s->u = re ? 1u : 0u;
       });
       a.dirty_rec(pc);
@@ -254,6 +274,7 @@ template <int DEPTH, class W, class A> struct CascadeCoop {
 template <class W, class A> SM_HD int water_step_coop(W& w, A& a, WaterP& p) {
   const int dimx = a.dimx(), dimy = a.dimy();
   const int SCALE = a.scale();
+  if (A::kBudget && w.lead()) { for (int k = 0; k < SM_BUDGET_SLOTS; k++) a.s->acc[k] = 0.0; }
   // ---- move ----
   const int ix = (int)roundf(p.px), iy = (int)roundf(p.py);        // :45
   a.begin(w, ix, iy, 0);
@@ -282,6 +303,7 @@ template <class W, class A> SM_HD int water_step_coop(W& w, A& a, WaterP& p) {
   p.py += p.sy;
   if (!(p.px >= 0.0f && p.py >= 0.0f) ||                            // :65-69
       !(p.px < (float)dimx - 1.0f && p.py < (float)dimy - 1.0f)) {
+    if (A::kBudget && w.lead()) a.s->acc[3] += p.sediment * p.volume;
     p.volume = 0.0;
     return SM_EXIT_OOB;
   }
@@ -300,10 +322,12 @@ template <class W, class A> SM_HD int water_step_coop(W& w, A& a, WaterP& p) {
     p.contains = a.soil(rec_surface(*ir)).transports;
     const double amount = param.equrate * cdiff * p.volume;
     w.one([&]() {
+      const double h0 = A::kBudget ? rec_height(*ir) : 0.0;
       a.focus(ix, iy);
       double diff = col_remove(a, *ir, amount);
       SM_UNROLL1
       while (fabs(diff) > 1E-8) diff = col_remove(a, *ir, diff);
+      if (A::kBudget) a.s->acc[0] += h0 - rec_height(*ir);
     });
     a.dirty_rec(ir);
   } else if (cdiff < 0) {                                           // :105-110
@@ -312,16 +336,24 @@ template <class W, class A> SM_HD int water_step_coop(W& w, A& a, WaterP& p) {
     const double amount = -eq * cdiff * p.volume;
     const uint32_t what = p.contains;
     w.one([&]() {
+      const double h0 = A::kBudget ? rec_height(*ir) : 0.0;
       a.focus(ix, iy);
       col_add(a, *ir, amount, what);
+      if (A::kBudget) a.s->acc[1] += rec_height(*ir) - h0;
     });
     a.dirty_rec(ir);
   }
   CascadeCoop<0, W, A>::run(w, a, nx, ny, 0);                       // :113
   p.sediment /= (1.0 - evaprate);                                   // :116-119
+  const double over = p.sediment - 1.0;
   if (p.sediment > 1.0) p.sediment = 1.0;
   p.volume *= (1.0 - evaprate);
-  return (p.volume > 0.01) ? SM_ALIVE : SM_EXIT_EVAP;
+  const bool lives = p.volume > 0.01;
+  if (A::kBudget && w.lead()) {
+    if (over > 0.0) a.s->acc[4] += over * p.volume;
+    if (!lives) a.s->acc[3] += p.sediment * p.volume;
+  }
+  return lives ? SM_ALIVE : SM_EXIT_EVAP;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -330,6 +362,7 @@ template <class W, class A> SM_HD int water_step_coop(W& w, A& a, WaterP& p) {
 template <class W, class A> SM_HD int wind_step_coop(W& w, A& a, WindP& p) {
   const int dimx = a.dimx(), dimy = a.dimy();
   const int SCALE = a.scale();
+  if (A::kBudget && w.lead()) { for (int k = 0; k < SM_BUDGET_SLOTS; k++) a.s->acc[k] = 0.0; }
   // ---- move ----
   if (a.soil(p.contains).suspension == 0.0) return SM_EXIT_OOB;     // :56-57
   const int ix = (int)roundf(p.px), iy = (int)roundf(p.py);         // :60
@@ -362,10 +395,11 @@ template <class W, class A> SM_HD int wind_step_coop(W& w, A& a, WindP& p) {
   p.py += p.sz;
   p.height += p.sy;                                                 // :80
   if (!(p.px >= 0.0f && p.py >= 0.0f) ||                            // :83-85
-      !((int)p.px < dimx - 1 && (int)p.py < dimy - 1))
+      !((int)p.px < dimx - 1 && (int)p.py < dimy - 1) ||
+      sqrtf(p.sx * p.sx + p.sy * p.sy + p.sz * p.sz) < 0.01) {      // :87-88
+    if (A::kBudget && w.lead()) a.s->acc[3] += p.sediment;
     return SM_EXIT_OOB;
-  if (sqrtf(p.sx * p.sx + p.sy * p.sy + p.sz * p.sz) < 0.01)        // :87-88
-    return SM_EXIT_OOB;
+  }
   // ---- interact (always returns true upstream) ----
   const int nx = (int)roundf(p.px), ny = (int)roundf(p.py);         // :99
   a.target(w, nx, ny);
@@ -377,8 +411,10 @@ template <class W, class A> SM_HD int wind_step_coop(W& w, A& a, WindP& p) {
                            (1.0f - p.sediment);                     // :107
       const double amount = suspension * force;
       w.one([&]() {
+        const double h0 = A::kBudget ? rec_height(*ir) : 0.0;
         a.focus(ix, iy);
         a.s->d = col_remove(a, *ir, amount);                        // :109
+        if (A::kBudget) { a.s->acc[0] += h0 - rec_height(*ir); if (amount < 0.0) a.s->acc[5] += amount; }
       });
       a.dirty_rec(ir);
       p.sediment += (amount - a.s->d);                              // :110
@@ -391,10 +427,13 @@ template <class W, class A> SM_HD int wind_step_coop(W& w, A& a, WindP& p) {
     const uint32_t what = p.contains;
     Sec32* const nr = a.rec(nx, ny);
     w.one([&]() {
+      double h0 = A::kBudget ? rec_height(*nr) : 0.0;
       a.focus(nx, ny);
       col_add(a, *nr, amount, what);                                // :123
+      if (A::kBudget) { a.s->acc[1] += rec_height(*nr) - h0; h0 = rec_height(*ir); }
       a.focus(ix, iy);
       col_add(a, *ir, amount, what);                                // :124
+      if (A::kBudget) a.s->acc[1] += rec_height(*ir) - h0;
     });
     a.dirty_rec(nr);
     a.dirty_rec(ir);

@@ -1295,7 +1295,7 @@ void sm_destroy(sm_context* ctx) {
   DevCtx& d = ctx->d;
   cudaFree(d.top); cudaFree(d.pool); cudaFree(d.ringbuf[0]); cudaFree(d.ringbuf[1]); cudaFree(d.ringbuf[2]);
   cudaFree(d.wfreq); cudaFree(d.wtrack); cudaFree(d.windfreq); cudaFree(ctx->d_soils);
-  cudaFree(d.ctl); cudaFree(d.pa); cudaFree(d.pb); cudaFree(d.pc); cudaFree(d.alive); cudaFree(d.done); cudaFree(d.fin); cudaFree(d.mv);
+  cudaFree(d.ctl); cudaFree(d.pa); cudaFree(d.pb); cudaFree(d.pc); cudaFree(d.alive); cudaFree(d.done); cudaFree(d.fin); cudaFree(d.mv); cudaFree(d.bud);
   for (int i = 0; i < 2; i++) { cudaFree(d.head[i]); cudaFree(d.node[i]); }
   cudaFree(ctx->d_verts); cudaFree(ctx->d_colors); cudaFree(d.dbg);
   cudaFree(ctx->d_act); cudaFree(ctx->d_hydro);
@@ -1376,6 +1376,10 @@ static int create_impl(const sm_config* cfg, int nranks, int rank, int share, sm
     CK(cudaMalloc(&d.pa, N * sizeof(float4))); CK(cudaMalloc(&d.pb, N * sizeof(double2)));
     CK(cudaMalloc(&d.pc, N * sizeof(uint2))); CK(cudaMalloc(&d.alive, N)); CK(cudaMalloc(&d.done, N * 4));
     CK(cudaMalloc(&d.fin, N * 4)); CK(cudaMalloc(&d.mv, N * 8));
+    if (cfg->flags & SM_FLAG_BUDGET) {
+      CK(cudaMalloc(&d.bud, N * SM_BUDGET_SLOTS * sizeof(double)));
+      CK(cudaMemsetAsync(d.bud, 0, N * SM_BUDGET_SLOTS * sizeof(double), ctx->stream));
+    }
     CK(cudaMemsetAsync(d.fin, 0, N * 4, ctx->stream)); CK(cudaMemsetAsync(d.mv, 0, N * 8, ctx->stream));
     d.nbx = (cfg->dimx + SM_MIN_BIN - 1) / SM_MIN_BIN; d.nby = (cfg->dimy + SM_MIN_BIN - 1) / SM_MIN_BIN;
     for (int i = 0; i < 2; i++) {
@@ -1437,14 +1441,14 @@ static void own_ptrs(sm_context* ctx, void** p) {
   DevCtx& d = ctx->d;
   p[0] = d.top; p[1] = d.pool; p[2] = d.ringbuf[0]; p[3] = d.ringbuf[1]; p[4] = d.ctl; p[5] = d.pa; p[6] = d.pb;
   p[7] = d.pc; p[8] = d.alive; p[9] = d.done; p[10] = d.head[0]; p[11] = d.head[1]; p[12] = d.node[0]; p[13] = d.node[1];
-  p[14] = d.ringbuf[2];
+  p[14] = d.ringbuf[2]; p[15] = d.bud;
 }
 static void fill_peer(PeerPtrs& P, void* const* p, unsigned long long pool_cap) {
   P.top = (Sec32*)p[0]; P.pool = (Sec32*)p[1]; P.ringbuf[0] = (uint32_t*)p[2]; P.ringbuf[1] = (uint32_t*)p[3];
   P.ctl = (RunCtl*)p[4]; P.pa = (float4*)p[5]; P.pb = (double2*)p[6]; P.pc = (uint2*)p[7];
   P.alive = (unsigned char*)p[8]; P.done = (unsigned int*)p[9]; P.head[0] = (unsigned long long*)p[10];
   P.head[1] = (unsigned long long*)p[11]; P.node[0] = (uint2*)p[12]; P.node[1] = (uint2*)p[13];
-  P.ringbuf[2] = (uint32_t*)p[14];
+  P.ringbuf[2] = (uint32_t*)p[14]; P.bud = (double*)p[15];
   P.pool_cap = pool_cap;
 }
 int sm_peer_export(sm_context* ctx, sm_peer_blob* out) {
@@ -1455,6 +1459,7 @@ int sm_peer_export(sm_context* ctx, sm_peer_blob* out) {
   own_ptrs(ctx, p);
   for (int i = 0; i < SM_PEER_ARRAYS; i++) {
     out->ptr[i] = (uint64_t)(uintptr_t)p[i];
+    if (!p[i]) continue;                      // optional array (mass budget) not allocated
     cudaIpcMemHandle_t h;
     CK(cudaIpcGetMemHandle(&h, p[i]));
     static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
@@ -1486,6 +1491,7 @@ int sm_peer_attach(sm_context* ctx, const sm_peer_blob* blobs, int32_t nblobs, i
         cudaGetLastError();
       }
       for (int i = 0; i < SM_PEER_ARRAYS; i++) {
+        if (!b.ptr[i]) continue;
         cudaIpcMemHandle_t h;
         memcpy(&h, b.ipc[i], 64);
         CK(cudaIpcOpenMemHandle(&p[i], h, cudaIpcMemLazyEnablePeerAccess));
@@ -1859,7 +1865,7 @@ static int launch_run(sm_context* ctx, int kind, int n, const float* d_spawn, in
   }
   // default: the warp-per-particle kernel (sm_sweep.cuh).  SM_KERNEL=thread selects the thread-per-particle
   // kernels above (kept for comparison measurements).
-  bool use_coop = SM_DEFAULT_COOP;
+  bool use_coop = SM_DEFAULT_COOP || ctx->d.bud != nullptr;      // the mass budget lives in the warp kernel
   {
     const char* e = getenv("SM_KERNEL");
     if (e && strcmp(e, "thread") == 0) use_coop = false;
@@ -1868,8 +1874,12 @@ static int launch_run(sm_context* ctx, int kind, int n, const float* d_spawn, in
   if (use_coop) {
     const int cthreads = SM_SW_WARPS * 32;
     int occ = 0;
-    void* fn = multi ? (kind == KIND_WATER ? (void*)k_sweep<KIND_WATER, true> : (void*)k_sweep<KIND_WIND, true>)
-                     : (kind == KIND_WATER ? (void*)k_sweep<KIND_WATER, false> : (void*)k_sweep<KIND_WIND, false>);
+    const bool budget = ctx->d.bud != nullptr;
+    void* const fns[8] = {(void*)k_sweep<KIND_WATER, false, false>, (void*)k_sweep<KIND_WIND, false, false>,
+                          (void*)k_sweep<KIND_WATER, true, false>,  (void*)k_sweep<KIND_WIND, true, false>,
+                          (void*)k_sweep<KIND_WATER, false, true>,  (void*)k_sweep<KIND_WIND, false, true>,
+                          (void*)k_sweep<KIND_WATER, true, true>,   (void*)k_sweep<KIND_WIND, true, true>};
+    void* fn = fns[(budget ? 4 : 0) + (multi ? 2 : 0) + (kind == KIND_WATER ? 0 : 1)];
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)fn, cthreads, 0));
     if (occ < 1) return fail(ctx, SM_ERR_CUDA, "sweep kernel does not fit an SM");
     // contexts that share the device must all be resident at once (they meet in the cross-rank barrier)
@@ -1954,6 +1964,29 @@ static int run_host(sm_context* ctx, int kind, int n, const float* spawn_xy, int
   rc = launch_run(ctx, kind, n, ctx->d_spawn, max_sweeps);
   if (rc != SM_OK) return rc;
   return sm_last_stats(ctx, st);
+}
+
+// ---- mass budget --------------------------------------------------------------------------
+int sm_budget_particles(sm_context* ctx, int32_t n, double* out) {
+  if (!ctx->d.bud) return fail(ctx, SM_ERR_INVALID, "context was created without SM_FLAG_BUDGET");
+  if (n < 0 || n > ctx->max_particles || (n && !out)) return fail(ctx, SM_ERR_INVALID, "sm_budget_particles: range");
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (n) CK(cudaMemcpy(out, ctx->d.bud, (size_t)n * SM_BUDGET_SLOTS * sizeof(double), cudaMemcpyDeviceToHost));
+  return SM_OK;
+}
+int sm_last_budget(sm_context* ctx, sm_budget* out) {
+  if (!out) return fail(ctx, SM_ERR_INVALID, "null argument");
+  if (ctx->cur_n < 0) return fail(ctx, SM_ERR_INVALID, "no batch yet");
+  std::vector<double> per((size_t)std::max(ctx->cur_n, 0) * SM_BUDGET_SLOTS);
+  int rc = sm_budget_particles(ctx, std::max(ctx->cur_n, 0), per.data());
+  if (rc != SM_OK) return rc;
+  double s6[SM_BUDGET_SLOTS] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < ctx->cur_n; i++)             // particle order: the same sums on any number of SMs or ranks
+    for (int k = 0; k < SM_BUDGET_SLOTS; k++) s6[k] += per[(size_t)i * SM_BUDGET_SLOTS + k];
+  out->eroded = s6[0]; out->deposited = s6[1]; out->cascade_net = s6[2]; out->discarded = s6[3];
+  out->clamped = s6[4]; out->wind_negative = s6[5]; out->particles = ctx->cur_n;
+  return SM_OK;
 }
 
 int sm_water_run(sm_context* ctx, int32_t n, const float* xy, int32_t max_sweeps, sm_stats* st) {

@@ -49,7 +49,8 @@ struct WarpDev {
 };
 
 // backing store of CoopWin on the device
-template <bool MULTI> struct DevBack {
+template <bool MULTI, bool BUDGET = false> struct DevBack {
+  static constexpr bool kBudget = BUDGET;
   const DevCtx& c;
   const SoilDev* s_soils;   // shared-memory copy of the soil table
   unsigned int phase;       // sweep number mod 3: frees go to ring[phase], allocations pop ring[(phase+1)%3]
@@ -245,7 +246,7 @@ __device__ __forceinline__ unsigned int grid_barrier_x(const DevCtx& c, unsigned
   return *s_total;
 }
 
-template <int KIND, bool MULTI>
+template <int KIND, bool MULTI, bool BUDGET>
 __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(DevCtx c, int n, const float* __restrict__ spawn,
                                                                             int max_sweeps) {
   typedef typename PType<KIND>::T P;
@@ -284,6 +285,7 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
         const int sx = (int)roundf(x), sy = (int)roundf(y);
         if (MULTI && owner_of_x<MULTI>(c, sx) != c.rank) {     // another rank spawns this one
           c.alive[pid] = 0;
+          if (BUDGET) for (int k = 0; k < SM_BUDGET_SLOTS; k++) c.bud[(size_t)pid * SM_BUDGET_SLOTS + k] = 0.0;
           continue;
         }
         const uint32_t contains = s_soils[rec_surface(*cell_ptr<MULTI>(c, sx, sy))].transports;
@@ -301,6 +303,7 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
         }
         c.alive[pid] = alive ? 1 : 0;
         c.done[pid] = alive ? (tag0 - 1u) : 0xFFFFFFFFu;
+        if (BUDGET) for (int k = 0; k < SM_BUDGET_SLOTS; k++) c.bud[(size_t)pid * SM_BUDGET_SLOTS + k] = 0.0;
       } else {
         alive = c.alive[pid] != 0;
         if (MULTI && alive) c.alive[pid] = 1;      // drop the arrival mark of a hand-over (see the sweep loop)
@@ -352,8 +355,8 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
       const uint32_t tgt = coop_scan<KIND, MULTI>(c, ws, lane, tag, pid, ix, iy, myR);
       coop_wait<MULTI>(c, tag, tgt);
 
-      DevBack<MULTI> back(c, s_soils, tag);
-      CoopWin<DevBack<MULTI> > a(back, &ws.cs);
+      DevBack<MULTI, BUDGET> back(c, s_soils, tag);
+      CoopWin<DevBack<MULTI, BUDGET> > a(back, &ws.cs);
       const int r = do_step_coop(w, a, p);
       // hand-off first: the map writes are all the successors of this step wait for
       a.flush(w);
@@ -371,6 +374,18 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
           st_release_u32(&c.done[pid], pub);
         }
         // own state and next sweep's bins are only needed after the grid barrier
+        if (BUDGET) {
+          // the step's six sums join the particle's totals; the totals travel with a particle that changes strips
+          // (exactly one rank holds them), so the final sum per particle is in step order on any number of ranks
+          const int bq = (MULTI && r == SM_ALIVE) ? owner_of_x<MULTI>(c, jx) : c.rank;
+          double* const dst = (MULTI && bq != c.rank) ? c.peer[bq].bud : c.bud;
+          for (int k = 0; k < SM_BUDGET_SLOTS; k++) {
+            const size_t at = (size_t)pid * SM_BUDGET_SLOTS + k;
+            const double tot = c.bud[at] + ws.cs.acc[k];
+            if (MULTI && bq != c.rank) c.bud[at] = 0.0;
+            dst[at] = tot;
+          }
+        }
         if (r == SM_ALIVE) {
           int ddx = jx - ix, ddy = jy - iy;
           ddx = ddx < 0 ? -ddx : ddx; ddy = ddy < 0 ? -ddy : ddy;

@@ -54,10 +54,10 @@ def sum_stats(stats):
 
 
 class VirtualShards:
-    def __init__(self, nranks, dimx, dimy, scale=80, device=0, max_particles=0, pool_capacity=0):
+    def __init__(self, nranks, dimx, dimy, scale=80, device=0, max_particles=0, pool_capacity=0, budget=False):
         self.nranks, self.dimx, self.dimy = nranks, dimx, dimy
         self.ctx = [capi.Context(dimx, dimy, scale, device=device, max_particles=max_particles,
-                                 pool_capacity=pool_capacity, nranks=nranks, rank=r, share=nranks)
+                                 pool_capacity=pool_capacity, nranks=nranks, rank=r, share=nranks, budget=budget)
                     for r in range(nranks)]
         blobs = [c.peer_export() for c in self.ctx]
         for c in self.ctx:

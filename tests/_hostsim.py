@@ -105,6 +105,12 @@ class HostSim:
         self.lib.hs_normal(int(x), int(y), o)
         return np.array(list(o), np.float32)
 
+    def budget(self):
+        """coop mode: per-particle mass-budget accumulators [n, 6] of the current batch"""
+        per = np.zeros((self._n, 6))
+        self.lib.hs_budget(_p(per, C.c_double))
+        return per
+
     def water_begin(self, xy):
         xy = np.ascontiguousarray(xy, np.float32); self._n = len(xy)
         self.lib.hs_water_begin(len(xy), _p(xy, C.c_float))

@@ -92,8 +92,10 @@ struct HostBack {   // backing store of CoopWin on the host
   void set_wtrack(int i, float v) { M.wtrack[i] = v; }
   void set_windfreq(int i, float v) { M.windfreq[i] = v; }
   void note_transfer() {}
+  static constexpr bool kBudget = true;
 };
 int G_coop = 0;   // 1: the sweeps below run the warp-cooperative step
+std::vector<double> BUD;   // coop mode: 6 mass-budget accumulators per particle (sm_coop.cuh)
 
 struct Stats { int64_t steps, sweeps, exit_oob, exit_evap, exit_stall; double seconds; };
 std::vector<WaterP> W; std::vector<int> Wlive;
@@ -167,8 +169,9 @@ void hs_cascade(float x, float y, int loop) { HostAccess a; Cascade<3, HostAcces
 
 void hs_set_mode(int coop, int lane_order) { G_coop = coop; G_lane_order = lane_order; }
 void hs_set_volume_factor(double v) { M.volume_factor = v; }
+void hs_budget(double* per_particle) { memcpy(per_particle, BUD.data(), BUD.size() * sizeof(double)); }
 void hs_water_begin(int n, const float* xy) {
-  HostAccess a; W.clear(); Wlive.clear();
+  HostAccess a; W.clear(); Wlive.clear(); BUD.assign((size_t)n * SM_BUDGET_SLOTS, 0.0);
   for (int i = 0; i < n; i++) {
     WaterP p{xy[2 * i], xy[2 * i + 1], 0.f, 0.f, 1.0, 0.0, 0};
     p.contains = spawn_contains(a, p.px, p.py);
@@ -183,6 +186,7 @@ int hs_water_sweep(Stats* st) {
       WarpHost w; HostBack b; CoopScratch sc; CoopWin<HostBack> cw(b, &sc);
       r = water_step_coop(w, cw, W[i]);
       cw.flush(w);
+      for (int k = 0; k < SM_BUDGET_SLOTS; k++) BUD[(size_t)i * SM_BUDGET_SLOTS + k] += sc.acc[k];
     } else r = water_step(a, W[i]);
     if (r == SM_EXIT_OOB) { st->exit_oob++; continue; }
     if (r == SM_EXIT_STALL) { st->exit_stall++; continue; }
@@ -201,7 +205,7 @@ void hs_water_state(float* pos, float* speed, double* vol, double* sed, int32_t*
   for (int i : Wlive) alive[i] = 1;
 }
 void hs_wind_begin(int n, const float* xy) {
-  HostAccess a; D.clear(); Dlive.clear();
+  HostAccess a; D.clear(); Dlive.clear(); BUD.assign((size_t)n * SM_BUDGET_SLOTS, 0.0);
   for (int i = 0; i < n; i++) {
     WindP p{xy[2 * i], xy[2 * i + 1], -2.f, 0.f, 1.f, 0.0, 0.0, 0};
     p.contains = spawn_contains(a, p.px, p.py);
@@ -216,6 +220,7 @@ int hs_wind_sweep(Stats* st) {
       WarpHost w; HostBack b; CoopScratch sc; CoopWin<HostBack> cw(b, &sc);
       r = wind_step_coop(w, cw, D[i]);
       cw.flush(w);
+      for (int k = 0; k < SM_BUDGET_SLOTS; k++) BUD[(size_t)i * SM_BUDGET_SLOTS + k] += sc.acc[k];
     } else r = wind_step(a, D[i]);
     if (r != SM_ALIVE) { st->exit_oob++; continue; }
     st->steps++;

@@ -519,15 +519,31 @@ def test_config4_config5_shapes_match_reference(ref, soil, dim, nw, nd, sweeps, 
     import soilmachine_b200 as smb
     from soilmachine_b200 import host, presets
     pre = presets.load(soil)
-    ctx = smb.Context(dim, dim, pre["world"]["scale"], max_particles=max(nw, nd))
+    budget = (dim == 8192)        # config 5 carries BASELINE's "mass-conservation check": the budget, vs the oracle port
+    ctx = smb.Context(dim, dim, pre["world"]["scale"], max_particles=max(nw, nd), budget=budget)
     ctx.set_soils(pre["soils"])
     ctx.initialize(42, pre["layers"])
     ref.init(soil, seed=42, dimx=dim, dimy=dim, poolsize=int(dim * dim * poolf) + 2000000)   # layers x cells + headroom
     host.srand(42)
     xw = host.spawn_list(nw, dim, dim)
+    if budget:
+        from oracle import portapi
+        po = portapi.Port().init(dim, dim, pre["world"]["scale"], ref.soils())
+        po.set_columns(ref.columns())
+        hsum0 = ctx.height_sum()
     r, g = ref.water_run(xw, max_sweeps=sweeps), ctx.water_run(xw, max_sweeps=sweeps)
     assert (g.steps, g.sweeps, g.exit_oob, g.exit_evap, g.exit_stall, g.pool_drops) == \
         (r.steps, r.sweeps, r.exit_oob, r.exit_evap, r.exit_stall, 0)
+    if budget:
+        po.water_run(xw, max_sweeps=sweeps)
+        per_p, sums_p = po.budget()
+        _same(ctx.budget_particles(nw), per_p, "mass budget per particle")
+        b = ctx.last_budget()
+        _same(np.array([b.eroded, b.deposited, b.cascade_net, b.discarded, b.clamped, b.wind_negative]), sums_p, "mass budget")
+        dh = ctx.height_sum() - hsum0
+        assert abs(dh - (b.deposited - b.eroded + b.cascade_net)) < 1e-9 * (b.deposited + b.eroded), (dh, b.asdict())
+        assert b.eroded > 0 and b.deposited > 0
+        del po
     s1, s2 = ref.water_state(), ctx.water_state()
     for k in s1:
         _same(s1[k], s2[k], "water particles: " + k)
@@ -602,3 +618,46 @@ def test_facade_per_particle_loop_matches_reference(ref, soil, dim, nw, nd, tmp_
                 "cell %d section %d" % (c, k)
         (h,) = struct.unpack_from("<d", raw, pos); pos += 8
         assert h == hts[c], "cell %d height" % c
+
+
+@pytest.mark.parametrize("nranks", [1, 3])
+def test_mass_budget_matches_port(ref, nranks):
+    """SURVEY.md A.7 on the device: the six per-particle accumulators of a water and a wind batch against the oracle
+    port (itself pinned to the reference), bit for bit - on one context and on a map sharded into three strips,
+    where a particle's sums travel with it - and the identity d(sum of heights) = deposited - eroded + cascade_net."""
+    import soilmachine_b200 as smb
+    from oracle import portapi
+    from soilmachine_b200 import sharded
+    soil, dimx, dimy, nw, nd = "rocksand", 192, 128, 1500, 900
+    ref.init(soil, seed=42, dimx=dimx, dimy=dimy, poolsize=dimx * dimy * 4 + 1000000)
+    cols = ref.columns()
+    po = portapi.Port().init(dimx, dimy, ref.scale, ref.soils())
+    po.set_columns(cols)
+    if nranks == 1:
+        ctxs = [smb.Context(dimx, dimy, ref.scale, max_particles=4096, budget=True)]
+        ctxs[0].set_soils(ref.soils())
+        ctxs[0].upload_columns(cols["offsets"], cols["type"], cols["size"], cols["saturation"])
+        run = {"water": ctxs[0].water_run, "wind": ctxs[0].wind_run}
+        hsum = lambda: ctxs[0].height_sum()
+    else:
+        sh = sharded.VirtualShards(nranks, dimx, dimy, ref.scale, max_particles=4096, budget=True)
+        sh.set_soils(ref.soils())
+        sh.upload_columns(cols)
+        ctxs = sh.ctx
+        run = {"water": sh.water_run, "wind": sh.wind_run}
+        hsum = lambda: float(sh.heights().sum())
+    for kind, n, seed in (("water", nw, 3), ("wind", nd, 4)):
+        xy = ref.spawn_list(n, seed=seed)
+        h0 = hsum()
+        (po.water_run if kind == "water" else po.wind_run)(xy)
+        run[kind](xy)
+        per_p, sums_p = po.budget()
+        per_g = sum(c.budget_particles(n) for c in ctxs)       # exactly one strip holds a particle's sums
+        _same(per_g, per_p, kind + ": mass budget per particle")
+        s = per_g.sum(axis=0)
+        assert abs((hsum() - h0) - (s[1] - s[0] + s[2])) < 1e-9 * max(1.0, s[0] + s[1]), (kind, s)
+        if nranks == 1:
+            b = ctxs[0].last_budget()
+            _same(np.array([b.eroded, b.deposited, b.cascade_net, b.discarded, b.clamped, b.wind_negative]), sums_p, kind)
+    for c in ctxs:
+        c.close()

@@ -80,6 +80,38 @@ def test_warp_cooperative_step_replays_golden_frame(case, lane_order):
         b.hs.lib.hs_set_mode(0, 0)
 
 
+@pytest.mark.parametrize("case", ["frame_rocksand_56", "frame_rgps_64"])
+def test_mass_budget_matches_port_and_closes(case):
+    """the six per-particle accumulators of the cooperative step (eroded, deposited, cascade_net,
+    discarded, clamped, wind_negative) against the oracle port's, bit for bit, on a water and a wind batch; and the
+    identity d(sum of heights) = deposited - eroded + cascade_net, to rounding."""
+    from oracle import portapi
+    g = _golden.load(case)
+    b = Backend(g)
+    b.hs.lib.hs_set_mode(1, 0)
+    try:
+        c0 = _golden.cols(g, "init")
+        b.hs.set_columns(c0)
+        po = portapi.Port().init(int(g["dimx"]), int(g["dimy"]), int(g["scale"]), g["soils"])
+        po.set_columns(c0)
+        for kind in ("water", "wind"):
+            xy = g[kind + "_xy"]
+            h0 = b.hs.heights().sum()
+            (po.water_run if kind == "water" else po.wind_run)(xy)
+            (b.water_run if kind == "water" else b.wind_run)(xy)
+            per_p, sums_p = po.budget()
+            per_h = b.hs.budget()
+            _golden.same(per_h, per_p, kind + " budget per particle")
+            dh = b.hs.heights().sum() - h0
+            s = per_h.sum(axis=0)
+            assert abs(dh - (s[1] - s[0] + s[2])) < 1e-9 * max(1.0, abs(s[0]) + abs(s[1])), (kind, dh, s)
+            assert s[0] > 0 or s[1] > 0
+            if kind == "water":
+                assert s[3] > 0           # evaporating particles take sediment with them
+    finally:
+        b.hs.lib.hs_set_mode(0, 0)
+
+
 @pytest.mark.parametrize("case", _golden.FRAME_CASES)
 def test_product_noise_reproduces_initial_terrain(case):
     """sm_noise.cuh (OpenSimplex2/FBm restatement) == Layermap::initialize of the reference."""
