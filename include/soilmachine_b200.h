@@ -232,6 +232,21 @@ int sm_water_flood(sm_context* ctx, sm_hydro_stats* stats);
  * order, seep(cell) then the water-table cascade with spill 3. */
 int sm_seep(sm_context* ctx, sm_hydro_stats* stats);
 
+/* ---- wind field: D3Q19 lattice Boltzmann, TRT collision (source/include/lbmwind/) ------------------------------
+ * The reference runs this as OpenGL compute shaders and only draws it (WindParticle keeps a constant prevailing
+ * wind, wind.h:29).  sm_lbm_create = lbmw::initialize (lbmwind.h:75-118: buffers + init.cs with an all-zero
+ * boundary); sm_lbm_set_boundary = SoilMachine.cpp:234-239 (NULL: from this context's terrain, else nx*ny*nz
+ * floats, > 0 = obstacle); sm_lbm_step = n x (collide.cs + stream.cs) fused into one kernel per step
+ * (lbmwind.h:170-187); sm_lbm_get: populations in upstream's layout F[cell*19 + q] with cell = (x*ny + y)*nz + z,
+ * density, velocity (x, y, z, w); sm_lbm_advect = move.cs (tracer particles, n x (x, y, z, w), in place).
+ * Arithmetic is defined by oracle/lbm_oracle.c (parity with the GLSL unpinned: no GL here, no reference vectors). */
+int sm_lbm_create(sm_context* ctx, int32_t nx, int32_t ny, int32_t nz);
+int sm_lbm_set_boundary(sm_context* ctx, const float* boundary);
+int sm_lbm_init(sm_context* ctx);                        /* init.cs again, with the current boundary */
+int sm_lbm_step(sm_context* ctx, int32_t nsteps, double* device_ms);
+int sm_lbm_get(sm_context* ctx, float* f, float* rho, float* v4);
+int sm_lbm_advect(sm_context* ctx, int32_t n, float* pos4);
+
 /* CUDA-event stopwatch on the context's stream (the stream every kernel of this context is
  * launched on): start records an event, stop records another, synchronises and returns the elapsed
  * device time between them. */

@@ -36,7 +36,8 @@ SYMBOLS = [
     "sm_wind_sweeps", "sm_wind_state", "sm_launch_count", "sm_device_alloc", "sm_device_free",
     "sm_device_upload", "sm_timer_start", "sm_timer_stop", "sm_set_soil_colors", "sm_mesh_update",
     "sm_mesh_device_ptr", "sm_export_height", "sm_export_color", "sm_create_sharded", "sm_shard_range",
-    "sm_peer_export", "sm_peer_attach", "sm_parse_soil_file", "sm_water_flood", "sm_seep", "sm_last_budget", "sm_budget_particles",
+    "sm_peer_export", "sm_peer_attach", "sm_parse_soil_file", "sm_water_flood", "sm_seep", "sm_last_budget", "sm_budget_particles", "sm_lbm_create", "sm_lbm_set_boundary", "sm_lbm_init",
+    "sm_lbm_step", "sm_lbm_get", "sm_lbm_advect",
 ]
 
 
@@ -337,6 +338,35 @@ class Context:
         b = Budget()
         self._ck(self.lib.sm_last_budget(self.h, C.byref(b)))
         return b
+
+    # ---- wind field (D3Q19 lattice Boltzmann) ----
+    def lbm_create(self, nx, ny, nz):
+        self._lbm = (int(nx), int(ny), int(nz))
+        self._ck(self.lib.sm_lbm_create(self.h, int(nx), int(ny), int(nz)))
+
+    def lbm_set_boundary(self, boundary=None):
+        b = None if boundary is None else np.ascontiguousarray(boundary, np.float32)
+        self._ck(self.lib.sm_lbm_set_boundary(self.h, _p(b, C.c_float)))
+
+    def lbm_init(self):
+        self._ck(self.lib.sm_lbm_init(self.h))
+
+    def lbm_step(self, n=1):
+        ms = C.c_double()
+        self._ck(self.lib.sm_lbm_step(self.h, int(n), C.byref(ms)))
+        return ms.value
+
+    def lbm_get(self):
+        nx, ny, nz = self._lbm
+        n = nx * ny * nz
+        f = np.zeros((n, 19), np.float32); rho = np.zeros(n, np.float32); v = np.zeros((n, 4), np.float32)
+        self._ck(self.lib.sm_lbm_get(self.h, _p(f, C.c_float), _p(rho, C.c_float), _p(v, C.c_float)))
+        return {"f": f, "rho": rho, "v": v}
+
+    def lbm_advect(self, pos4):
+        pos = np.ascontiguousarray(pos4, np.float32).copy()
+        self._ck(self.lib.sm_lbm_advect(self.h, len(pos), _p(pos, C.c_float)))
+        return pos
 
     def water_flood(self):
         """flood() of every finished particle of the last water batch (water.h:123-145), ascending index."""

@@ -19,6 +19,7 @@
 #include "sm_device.cuh"
 #include "sm_noise.cuh"
 #include "sm_hydro.cuh"
+#include "sm_lbm.cuh"
 
 #define KIND_WATER 0
 #define KIND_WIND 1
@@ -1252,6 +1253,8 @@ struct sm_context {
   unsigned long long* d_act = nullptr;   // active-cell index of the seep pass (allocated on first use)
   unsigned long long act_words = 0;
   HydroCount* d_hydro = nullptr;
+  LbmDev lbm = {};                // wind field (sm_lbm_create)
+  int lbm_cur = 0;                // buffer holding the current populations
   RunCtl* h_ctl = nullptr;        // pinned
   int64_t launches = 0;
   int cur_kind = -1, cur_n = 0;
@@ -1299,6 +1302,7 @@ void sm_destroy(sm_context* ctx) {
   for (int i = 0; i < 2; i++) { cudaFree(d.head[i]); cudaFree(d.node[i]); }
   cudaFree(ctx->d_verts); cudaFree(ctx->d_colors); cudaFree(d.dbg);
   cudaFree(ctx->d_act); cudaFree(ctx->d_hydro);
+  cudaFree(ctx->lbm.F[0]); cudaFree(ctx->lbm.F[1]); cudaFree(ctx->lbm.B); cudaFree(ctx->lbm.RHO); cudaFree(ctx->lbm.V);
   cudaFree(ctx->d_spawn); cudaFree(ctx->d_scratch); cudaFree(ctx->d_iscratch); cudaFree(ctx->d_cellres);
   if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -2231,6 +2235,126 @@ int sm_parse_soil_file(const char* path, sm_soil* soils, char* names, float* col
   if (world5) { world5[0] = f.world.sizex; world5[1] = f.world.sizey; world5[2] = f.world.scale; world5[3] = f.world.nwater; world5[4] = f.world.nwind; }
   return SM_OK;
 }
+// ---- wind field: D3Q19 lattice Boltzmann (sm_lbm.cuh) ----------------------------------------------------------
+// boundary from the terrain, SoilMachine.cpp:234-239 with lbmwind.h:119 scale = (SIZEX, SCALE, SIZEY)/(NX, 32, NZ)
+__global__ void k_lbm_boundary_from_map(DevCtx c, LbmDev L) {
+  const size_t n = (size_t)L.nx * L.ny * L.nz;
+  const float sx = (float)c.dimx / (float)L.nx, sy = (float)c.scale / 32.0f, sz = (float)c.dimy / (float)L.nz;
+  for (size_t ind = (size_t)blockIdx.x * blockDim.x + threadIdx.x; ind < n; ind += (size_t)gridDim.x * blockDim.x) {
+    const int z = (int)(ind % L.nz), y = (int)((ind / L.nz) % L.ny), x = (int)(ind / ((size_t)L.nz * L.ny));
+    const int mx = (int)(sx * (float)x), mz = (int)(sz * (float)z);
+    const double h = rec_height(c.top[(size_t)mx * c.dimy + mz]);
+    L.B[ind] = (h > (double)((sy * (float)y) / (float)c.scale)) ? 1.0f : 0.0f;
+  }
+}
+static int lbm_ready(sm_context* ctx) {
+  if (!ctx->lbm.F[0]) return fail(ctx, SM_ERR_INVALID, "no wind field: call sm_lbm_create");
+  CK(cudaSetDevice(ctx->cfg.device));
+  return SM_OK;
+}
+int sm_lbm_init(sm_context* ctx) {
+  int rc = lbm_ready(ctx);
+  if (rc != SM_OK) return rc;
+  ctx->lbm_cur = 0;
+  k_lbm_init<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(ctx->lbm, 0);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return SM_OK;
+}
+int sm_lbm_create(sm_context* ctx, int32_t nx, int32_t ny, int32_t nz) {
+  if (nx < 2 || ny < 2 || nz < 2 || (int64_t)nx * ny * nz > (1ll << 31)) return fail(ctx, SM_ERR_INVALID, "sm_lbm_create: size");
+  CK(cudaSetDevice(ctx->cfg.device));
+  LbmDev& L = ctx->lbm;
+  cudaFree(L.F[0]); cudaFree(L.F[1]); cudaFree(L.B); cudaFree(L.RHO); cudaFree(L.V);
+  L = LbmDev{};
+  L.nx = nx; L.ny = ny; L.nz = nz;
+  const size_t n = (size_t)nx * ny * nz;
+  CK(cudaMalloc(&L.F[0], n * LBM_Q * 4)); CK(cudaMalloc(&L.F[1], n * LBM_Q * 4));
+  CK(cudaMalloc(&L.B, n * 4)); CK(cudaMalloc(&L.RHO, n * 4)); CK(cudaMalloc(&L.V, n * 16));
+  CK(cudaMemsetAsync(L.B, 0, n * 4, ctx->stream));
+  CK(cudaMemsetAsync(L.F[1], 0, n * LBM_Q * 4, ctx->stream));
+  // constants, evaluated as oracle/lbm_oracle.c does (fp32, left to right)
+  LbmConst K;
+  K.w[0] = 1.0f / 3.0f; K.w[1] = 1.0f / 18.0f; K.w[2] = 1.0f / 36.0f;
+  K.force[0] = 0.05f * -2.0f; K.force[1] = 0.05f * 0.0f; K.force[2] = 0.05f * 1.0f;
+  const float cs = 1.0f / sqrtf(3.0f);
+  K.cs2 = 1.0f / cs / cs;
+  K.cs4 = 1.0f / cs / cs / cs / cs;
+  const float zero[3] = {0.0f, 0.0f, 0.0f};
+  LbmEqAll<LBM_Q - 1>::run(K, 1.0f, K.force, K.eq_force);
+  LbmEqAll<LBM_Q - 1>::run(K, 1.0f, zero, K.eq_rest);
+  CK(cudaMemcpyToSymbolAsync(c_lbm, &K, sizeof(K), 0, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return sm_lbm_init(ctx);       // lbmwind.h:101-107: init.cs runs while the boundary is still all zero
+}
+int sm_lbm_set_boundary(sm_context* ctx, const float* boundary) {
+  int rc = lbm_ready(ctx);
+  if (rc != SM_OK) return rc;
+  const size_t n = (size_t)ctx->lbm.nx * ctx->lbm.ny * ctx->lbm.nz;
+  if (boundary) {
+    CK(cudaMemcpyAsync(ctx->lbm.B, boundary, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  } else {                       // from the terrain of this context
+    if (ctx->nranks > 1) return fail(ctx, SM_ERR_INVALID, "sm_lbm_set_boundary: not on a sharded context");
+    k_lbm_boundary_from_map<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(ctx->d, ctx->lbm);
+    ctx->launches++;
+    CK(cudaGetLastError());
+  }
+  return SM_OK;
+}
+int sm_lbm_step(sm_context* ctx, int32_t nsteps, double* device_ms) {
+  int rc = lbm_ready(ctx);
+  if (rc != SM_OK) return rc;
+  if (nsteps < 0) return fail(ctx, SM_ERR_INVALID, "sm_lbm_step: nsteps");
+  const size_t n = (size_t)ctx->lbm.nx * ctx->lbm.ny * ctx->lbm.nz;
+  const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)ctx->num_sms * 16);
+  CK(cudaEventRecord(ctx->evt0, ctx->stream));
+  for (int i = 0; i < nsteps; i++) {
+    k_lbm_step<<<blocks, 256, 0, ctx->stream>>>(ctx->lbm, ctx->lbm_cur);
+    ctx->lbm_cur ^= 1;
+  }
+  CK(cudaEventRecord(ctx->evt1, ctx->stream));
+  ctx->launches += nsteps;
+  CK(cudaGetLastError());
+  CK(cudaEventSynchronize(ctx->evt1));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, ctx->evt0, ctx->evt1));
+  if (device_ms) *device_ms = ms;
+  return SM_OK;
+}
+int sm_lbm_get(sm_context* ctx, float* f, float* rho, float* v4) {
+  int rc = lbm_ready(ctx);
+  if (rc != SM_OK) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  const size_t n = (size_t)ctx->lbm.nx * ctx->lbm.ny * ctx->lbm.nz;
+  if (f) {                       // device: F[q][cell]; caller (as upstream): F[cell*19 + q]
+    std::vector<float> soa(n * LBM_Q);
+    CK(cudaMemcpy(soa.data(), ctx->lbm.F[ctx->lbm_cur], n * LBM_Q * 4, cudaMemcpyDeviceToHost));
+    for (size_t ind = 0; ind < n; ind++) for (int q = 0; q < LBM_Q; q++) f[ind * LBM_Q + q] = soa[(size_t)q * n + ind];
+  }
+  if (rho) CK(cudaMemcpy(rho, ctx->lbm.RHO, n * 4, cudaMemcpyDeviceToHost));
+  if (v4) CK(cudaMemcpy(v4, ctx->lbm.V, n * 16, cudaMemcpyDeviceToHost));
+  return SM_OK;
+}
+int sm_lbm_advect(sm_context* ctx, int32_t n, float* pos4) {
+  int rc = lbm_ready(ctx);
+  if (rc != SM_OK) return rc;
+  if (n < 0 || (n && !pos4)) return fail(ctx, SM_ERR_INVALID, "sm_lbm_advect: arguments");
+  if (!n) return SM_OK;
+  float4* d_pos = nullptr;
+  CK(cudaMalloc(&d_pos, (size_t)n * 16));
+  cudaError_t e = cudaMemcpyAsync(d_pos, pos4, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) {
+    k_lbm_advect<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->lbm, n, d_pos);
+    ctx->launches++;
+    e = cudaMemcpyAsync(pos4, d_pos, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_pos);
+  if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return SM_ERR_CUDA; }
+  return SM_OK;
+}
+
 int sm_timer_start(sm_context* ctx) {
   CK(cudaSetDevice(ctx->cfg.device));
   CK(cudaEventRecord(ctx->evt0, ctx->stream));
