@@ -246,6 +246,10 @@ int sm_lbm_init(sm_context* ctx);                        /* init.cs again, with 
 int sm_lbm_step(sm_context* ctx, int32_t nsteps, double* device_ms);
 int sm_lbm_get(sm_context* ctx, float* f, float* rho, float* v4);
 int sm_lbm_advect(sm_context* ctx, int32_t n, float* pos4);
+/* EXTENSION, off by default (upstream never couples the two: wind.h:29 is a constant): on != 0 makes the prevailing
+ * wind `pspeed` of later wind batches the lattice velocity at the particle (nearest lattice cell, / 0.05, components
+ * clamped to [-2, 2]) instead of (-2, 0, 1).  The oracle port implements the same rule (smo_set_wind_field). */
+int sm_wind_use_lbm(sm_context* ctx, int32_t on);
 
 /* CUDA-event stopwatch on the context's stream (the stream every kernel of this context is
  * launched on): start records an event, stop records another, synchronises and returns the elapsed

@@ -143,6 +143,14 @@ class Port:
         self._nd = len(xy)
         return self._run(self.lib.smo_wind_run, xy, max_sweeps)
 
+    def set_wind_field(self, v4=None, dims=None):
+        """attach a lattice velocity field [nx*ny*nz, 4] for the wind particles' prevailing wind (None: detach)"""
+        if v4 is None:
+            self.lib.smo_set_wind_field(None, 0, 0, 0)
+            return
+        v = np.ascontiguousarray(v4, np.float32)
+        self.lib.smo_set_wind_field(_p(v, C.c_float), int(dims[0]), int(dims[1]), int(dims[2]))
+
     def budget(self):
         """mass budget of the last lockstep batch: (per-particle accumulators [n, 6], their sums in particle order
         [6]) - eroded, deposited, cascade_net, discarded, clamped, wind_negative (sm_coop.cuh)"""

@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstring>
 #include <vector>
+#include <algorithm>
 #include <chrono>
 
 namespace {
@@ -365,6 +366,21 @@ void wind_spawn(Wind& p, float x, float y) {                 // ctor, wind.h:13-
   p.param = W.soils[p.surf];
   p.contains = p.param.transports;
 }
+// Prevailing wind.  Upstream: the constant (-2, 0, 1) (wind.h:29).  Extension (off unless a field is attached): the
+// nearest cell of a lattice velocity field, lattice <-> world as SoilMachine.cpp:234-239 maps them, velocity / 0.05,
+// components clamped to [-2, 2]; the product's rule is soilmachine_b200/csrc/sm_coop.cuh wind_field_pspeed.
+std::vector<float> FIELD; int FNX = 0, FNY = 0, FNZ = 0;
+V3 pspeed_at(const V2& pos, double height) {
+  if (FIELD.empty()) return {-2, 0, 1};
+  const float sx = (float)W.dimx / (float)FNX, sy = (float)W.SCALE / 32.0f, sz = (float)W.dimy / (float)FNZ;
+  int lx = (int)(pos.x / sx), lz = (int)(pos.y / sz);
+  int ly = (int)((float)(height * 80.0 / (double)W.SCALE) * (float)W.SCALE / sy);
+  lx = std::min(std::max(lx, 0), FNX - 1); ly = std::min(std::max(ly, 0), FNY - 1); lz = std::min(std::max(lz, 0), FNZ - 1);
+  const float* v = &FIELD[(((size_t)lx * FNY + ly) * FNZ + lz) * 4];
+  float c[3];
+  for (int k = 0; k < 3; k++) { c[k] = v[k] / 0.05f; c[k] = c[k] < -2.0f ? -2.0f : (c[k] > 2.0f ? 2.0f : c[k]); }
+  return {c[0], c[1], c[2]};
+}
 V3 mixd(V3 x, V3 y, double a) {                              // glm::mix with a double weight
   return {(float)((double)x.x * (1.0 - a) + (double)y.x * a), (float)((double)x.y * (1.0 - a) + (double)y.y * a),
           (float)((double)x.z * (1.0 - a) + (double)y.z * a)};
@@ -381,7 +397,7 @@ bool wind_move(Wind& p) {                                    // wind.h:54-92
   if (p.height < p.sheight) p.height = p.sheight;
   if (p.height > p.sheight) p.speed.y -= 0.25;
   else p.speed = mixd(p.speed, cross(cross(p.speed, n), n), 0.8);
-  p.speed = mixd(p.speed, {-2, 0, 1}, 0.2);
+  p.speed = mixd(p.speed, pspeed_at(p.pos, p.height), 0.2);
   p.pos.x += p.speed.x; p.pos.y += p.speed.z;
   p.height += p.speed.y;
   if (!(p.pos.x >= 0.0f && p.pos.y >= 0.0f) || !((int)p.pos.x < W.dimx - 1 && (int)p.pos.y < W.dimy - 1) ||
@@ -500,6 +516,10 @@ int smo_water_sweep(smo_stats* st) {
   }
   Wlive.swap(next); st->sweeps++;
   return (int)Wlive.size();
+}
+void smo_set_wind_field(const float* v4, int nx, int ny, int nz) {
+  if (!v4) { FIELD.clear(); return; }
+  FIELD.assign(v4, v4 + (size_t)nx * ny * nz * 4); FNX = nx; FNY = ny; FNZ = nz;
 }
 // mass budget of the current lockstep batch: per-particle accumulators (n x 6) and their sums in particle order
 int64_t smo_budget(double* per_particle, double* sums6) {

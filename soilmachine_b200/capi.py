@@ -37,7 +37,7 @@ SYMBOLS = [
     "sm_device_upload", "sm_timer_start", "sm_timer_stop", "sm_set_soil_colors", "sm_mesh_update",
     "sm_mesh_device_ptr", "sm_export_height", "sm_export_color", "sm_create_sharded", "sm_shard_range",
     "sm_peer_export", "sm_peer_attach", "sm_parse_soil_file", "sm_water_flood", "sm_seep", "sm_last_budget", "sm_budget_particles", "sm_lbm_create", "sm_lbm_set_boundary", "sm_lbm_init",
-    "sm_lbm_step", "sm_lbm_get", "sm_lbm_advect",
+    "sm_lbm_step", "sm_lbm_get", "sm_lbm_advect", "sm_wind_use_lbm",
 ]
 
 
@@ -362,6 +362,9 @@ class Context:
         f = np.zeros((n, 19), np.float32); rho = np.zeros(n, np.float32); v = np.zeros((n, 4), np.float32)
         self._ck(self.lib.sm_lbm_get(self.h, _p(f, C.c_float), _p(rho, C.c_float), _p(v, C.c_float)))
         return {"f": f, "rho": rho, "v": v}
+
+    def wind_use_lbm(self, on=True):
+        self._ck(self.lib.sm_wind_use_lbm(self.h, 1 if on else 0))
 
     def lbm_advect(self, pos4):
         pos = np.ascontiguousarray(pos4, np.float32).copy()

@@ -66,12 +66,39 @@ struct
   double pad2_[2];
 };
 
+// Prevailing wind of a WindParticle from a lattice velocity field (extension; upstream: the constant (-2, 0, 1),
+// wind.h:29).  The lattice maps to the world as upstream's boundary construction does (SoilMachine.cpp:234-239 with
+// lbmwind.h:119): lattice (x, y, z) <-> map cell (x*SIZEX/NX, z*SIZEY/NZ) at map height y*(SCALE/32)/SCALE.  A
+// particle's `height` is in units of map height * SCALE/80 (wind.h:67).  Nearest lattice cell, clamped to the
+// lattice; velocity / 0.05 (the lattice is driven with 0.05 * pspeed, lbm.cs:35) and each component clamped to
+// the reference's magnitude (|x| <= 2, |y| <= 2, |z| <= 2), which keeps the conflict reach of a step valid.
+struct WindField {
+  const float* v4;          // 4 floats per lattice cell, cell = (x*ny + y)*nz + z; null = no field
+  int nx, ny, nz;
+  int dimx, dimy, scale;    // of the map
+};
+SM_HD void wind_field_pspeed(const WindField& f, float px, float py, double height, float* ps) {
+  if (!f.v4) { ps[0] = -2.0f; ps[1] = 0.0f; ps[2] = 1.0f; return; }
+  const float sx = (float)f.dimx / (float)f.nx, sy = (float)f.scale / 32.0f, sz = (float)f.dimy / (float)f.nz;
+  int lx = (int)(px / sx), lz = (int)(py / sz);
+  int ly = (int)((float)(height * 80.0 / (double)f.scale) * (float)f.scale / sy);
+  lx = lx < 0 ? 0 : (lx > f.nx - 1 ? f.nx - 1 : lx);
+  ly = ly < 0 ? 0 : (ly > f.ny - 1 ? f.ny - 1 : ly);
+  lz = lz < 0 ? 0 : (lz > f.nz - 1 ? f.nz - 1 : lz);
+  const float* v = f.v4 + (((size_t)lx * f.ny + ly) * f.nz + lz) * 4;
+  for (int k = 0; k < 3; k++) {
+    float c = v[k] / 0.05f;
+    c = c < -2.0f ? -2.0f : (c > 2.0f ? 2.0f : c);
+    ps[k] = c;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // the window accessor
 // ------------------------------------------------------------------------------------------------
 // B provides: dimx() dimy() scale(), soilp(t) -> const SoilDev*, cell_ptr(x, y) -> Sec32* (global record),
 // focus(x, y), pool_load/pool_store/pool_alloc/pool_free, wfreq(ind) wtrack(ind) windfreq(ind),
-// set_wtrack(ind, v) set_windfreq(ind, v), note_transfer().
+// set_wtrack(ind, v) set_windfreq(ind, v), note_transfer(), pspeed(px, py, height, out3), kBudget.
 // ax..f_track are warp-uniform: every lane holds the same values and updates them identically.
 template <class B> struct CoopWin {
   B& b;
@@ -386,10 +413,14 @@ template <class W, class A> SM_HD int wind_step_coop(W& w, A& a, WindP& p) {
     p.sz = (float)((double)s.z * (1.0 - wt) + (double)v.z * wt);
   }
   {                                                                 // :78 mix(speed, pspeed, 0.2)
+    // pspeed is the constant (-2, 0, 1) upstream (wind.h:29); with a wind field attached (sm_wind_use_lbm,
+    // a modelling extension that is off by default) it is sampled from the lattice Boltzmann velocity
+    float ps[3];
+    a.b.pspeed(p.px, p.py, p.height, ps);
     const double wt = 0.2;
-    p.sx = (float)((double)p.sx * (1.0 - wt) + (double)(-2.0f) * wt);
-    p.sy = (float)((double)p.sy * (1.0 - wt) + (double)(0.0f) * wt);
-    p.sz = (float)((double)p.sz * (1.0 - wt) + (double)(1.0f) * wt);
+    p.sx = (float)((double)p.sx * (1.0 - wt) + (double)(ps[0]) * wt);
+    p.sy = (float)((double)p.sy * (1.0 - wt) + (double)(ps[1]) * wt);
+    p.sz = (float)((double)p.sz * (1.0 - wt) + (double)(ps[2]) * wt);
   }
   p.px += p.sx;                                                     // :79
   p.py += p.sz;

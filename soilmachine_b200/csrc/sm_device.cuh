@@ -81,6 +81,8 @@ struct DevCtx {
   int nsoils;
   int dimx, dimy, scale;
   double volume_factor;          // WaterParticle::volumeFactor (water.h:368), default 0.015
+  const float* wind_v4;          // lattice velocity field coupled to the wind particles (null: constant pspeed)
+  int wind_nx, wind_ny, wind_nz;
   RunCtl* ctl;
   // particle batch
   float4* pa;        // water: px,py,sx,sy        | wind: px,py,sx,sy

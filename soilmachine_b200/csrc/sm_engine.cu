@@ -1869,7 +1869,8 @@ static int launch_run(sm_context* ctx, int kind, int n, const float* d_spawn, in
   }
   // default: the warp-per-particle kernel (sm_sweep.cuh).  SM_KERNEL=thread selects the thread-per-particle
   // kernels above (kept for comparison measurements).
-  bool use_coop = SM_DEFAULT_COOP || ctx->d.bud != nullptr;      // the mass budget lives in the warp kernel
+  // the mass budget and the wind-field coupling live in the warp kernel
+  bool use_coop = SM_DEFAULT_COOP || ctx->d.bud != nullptr || ctx->d.wind_v4 != nullptr;
   {
     const char* e = getenv("SM_KERNEL");
     if (e && strcmp(e, "thread") == 0) use_coop = false;
@@ -2267,6 +2268,7 @@ int sm_lbm_create(sm_context* ctx, int32_t nx, int32_t ny, int32_t nz) {
   LbmDev& L = ctx->lbm;
   cudaFree(L.F[0]); cudaFree(L.F[1]); cudaFree(L.B); cudaFree(L.RHO); cudaFree(L.V);
   L = LbmDev{};
+  ctx->d.wind_v4 = nullptr;
   L.nx = nx; L.ny = ny; L.nz = nz;
   const size_t n = (size_t)nx * ny * nz;
   CK(cudaMalloc(&L.F[0], n * LBM_Q * 4)); CK(cudaMalloc(&L.F[1], n * LBM_Q * 4));
@@ -2334,6 +2336,14 @@ int sm_lbm_get(sm_context* ctx, float* f, float* rho, float* v4) {
   }
   if (rho) CK(cudaMemcpy(rho, ctx->lbm.RHO, n * 4, cudaMemcpyDeviceToHost));
   if (v4) CK(cudaMemcpy(v4, ctx->lbm.V, n * 16, cudaMemcpyDeviceToHost));
+  return SM_OK;
+}
+int sm_wind_use_lbm(sm_context* ctx, int32_t on) {
+  if (!on) { ctx->d.wind_v4 = nullptr; return SM_OK; }
+  int rc = lbm_ready(ctx);
+  if (rc != SM_OK) return rc;
+  ctx->d.wind_v4 = (const float*)ctx->lbm.V;
+  ctx->d.wind_nx = ctx->lbm.nx; ctx->d.wind_ny = ctx->lbm.ny; ctx->d.wind_nz = ctx->lbm.nz;
   return SM_OK;
 }
 int sm_lbm_advect(sm_context* ctx, int32_t n, float* pos4) {

@@ -104,6 +104,10 @@ template <bool MULTI, bool BUDGET = false> struct DevBack {
   __device__ __forceinline__ void set_wtrack(int i, float v) { c.wtrack[i] = v; }
   __device__ __forceinline__ void set_windfreq(int i, float v) { c.windfreq[i] = v; }
   __device__ __forceinline__ void note_transfer() {}
+  __device__ __forceinline__ void pspeed(float px, float py, double height, float* ps) const {
+    const WindField f{c.wind_v4, c.wind_nx, c.wind_ny, c.wind_nz, c.dimx, c.dimy, c.scale};
+    wind_field_pspeed(f, px, py, height, ps);
+  }
 };
 
 struct __align__(32) WarpSmem {

@@ -105,6 +105,13 @@ class HostSim:
         self.lib.hs_normal(int(x), int(y), o)
         return np.array(list(o), np.float32)
 
+    def set_wind_field(self, v4=None, dims=None):
+        if v4 is None:
+            self.lib.hs_set_wind_field(None, 0, 0, 0)
+            return
+        v = np.ascontiguousarray(v4, np.float32)
+        self.lib.hs_set_wind_field(_p(v, C.c_float), int(dims[0]), int(dims[1]), int(dims[2]))
+
     def budget(self):
         """coop mode: per-particle mass-budget accumulators [n, 6] of the current batch"""
         per = np.zeros((self._n, 6))

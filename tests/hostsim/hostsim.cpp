@@ -74,6 +74,8 @@ struct WarpHost {
   template <class F> void one(F f) { f(); }
   bool lead() const { return true; }
 };
+std::vector<float> G_field_store;
+WindField G_field = {nullptr, 0, 0, 0, 0, 0, 0};
 struct HostBack {   // backing store of CoopWin on the host
   HostAccess h;
   int dimx() const { return M.dimx; }
@@ -93,6 +95,7 @@ struct HostBack {   // backing store of CoopWin on the host
   void set_windfreq(int i, float v) { M.windfreq[i] = v; }
   void note_transfer() {}
   static constexpr bool kBudget = true;
+  void pspeed(float px, float py, double height, float* ps) const { wind_field_pspeed(G_field, px, py, height, ps); }
 };
 int G_coop = 0;   // 1: the sweeps below run the warp-cooperative step
 std::vector<double> BUD;   // coop mode: 6 mass-budget accumulators per particle (sm_coop.cuh)
@@ -169,6 +172,12 @@ void hs_cascade(float x, float y, int loop) { HostAccess a; Cascade<3, HostAcces
 
 void hs_set_mode(int coop, int lane_order) { G_coop = coop; G_lane_order = lane_order; }
 void hs_set_volume_factor(double v) { M.volume_factor = v; }
+// attach (v4 != null) or detach a lattice velocity field for the wind particles' prevailing wind
+void hs_set_wind_field(const float* v4, int nx, int ny, int nz) {
+  if (!v4) { G_field = WindField{nullptr, 0, 0, 0, 0, 0, 0}; return; }
+  G_field_store.assign(v4, v4 + (size_t)nx * ny * nz * 4);
+  G_field = WindField{G_field_store.data(), nx, ny, nz, M.dimx, M.dimy, M.scale};
+}
 void hs_budget(double* per_particle) { memcpy(per_particle, BUD.data(), BUD.size() * sizeof(double)); }
 void hs_water_begin(int n, const float* xy) {
   HostAccess a; W.clear(); Wlive.clear(); BUD.assign((size_t)n * SM_BUDGET_SLOTS, 0.0);

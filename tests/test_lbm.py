@@ -119,3 +119,82 @@ def test_gpu_lbm_boundary_from_terrain(ref):
     for k in ("f", "rho", "v"):
         assert np.array_equal(g[k], r[k]), k
     ctx.close()
+
+
+def _field_with_obstacle(nx, ny, nz, steps=15):
+    from oracle import lbmapi
+    o = lbmapi.Lbm(nx, ny, nz)
+    b = np.zeros((nx, ny, nz), np.float32)
+    b[nx // 3:nx // 2, 0:ny // 2, nz // 4:3 * nz // 4] = 1.0
+    o.set_boundary(b)
+    o.step(steps)
+    return o.get()["v"]
+
+
+def test_wind_particles_follow_the_lattice_field_cpu():
+    """EXTENSION (off by default): WindParticle's prevailing wind sampled from the lattice Boltzmann velocity.  The
+    product's step (host build of sm_coop.cuh) against the oracle port's restatement of the same rule, bit for bit;
+    and without a field the constant of wind.h:29 - the golden frames - is untouched."""
+    import _golden
+    import _hostsim
+    from oracle import portapi
+    g = _golden.load("frame_rocksand_56")
+    dims = (16, 10, 16)
+    v4 = _field_with_obstacle(*dims)
+    hs = _hostsim.HostSim()
+    hs.init(int(g["dimx"]), int(g["dimy"]), int(g["scale"]), g["soils"])
+    hs.set_columns(_golden.cols(g, "init"))
+    hs.lib.hs_set_mode(1, 0)
+    po = portapi.Port().init(int(g["dimx"]), int(g["dimy"]), int(g["scale"]), g["soils"])
+    po.set_columns(_golden.cols(g, "init"))
+    try:
+        hs.set_wind_field(v4, dims); po.set_wind_field(v4, dims)
+        xy = g["wind_xy"]
+        po.wind_run(xy)
+        st = _hostsim.Stats()
+        hs.wind_begin(xy)
+        while hs.wind_sweep(st):
+            pass
+        a, b = hs.wind_state(), po.wind_state()
+        for k in a:
+            _golden.same(a[k], b[k], "wind state " + k)
+        _golden.same_cols(hs.columns(), po.columns(), "columns")
+        assert not np.array_equal(a["pos"], g["wind_state_pos"])     # the field does change the trajectories
+    finally:
+        hs.set_wind_field(None); po.set_wind_field(None)
+        hs.lib.hs_set_mode(0, 0)
+
+
+@pytest.mark.gpu
+def test_gpu_wind_particles_follow_the_lattice_field(ref):
+    """the coupled wind batch on the device (field = this context's own lattice after some steps around the terrain)
+    against the oracle port fed with the downloaded velocity field"""
+    import soilmachine_b200 as smb
+    from oracle import portapi
+    dim, n = 128, 600
+    ref.init("rocksand", seed=42, dimx=dim, dimy=dim, poolsize=dim * dim * 4 + 1000000)
+    cols = ref.columns()
+    ctx = smb.Context(dim, dim, ref.scale, max_particles=4096)
+    ctx.set_soils(ref.soils())
+    ctx.upload_columns(cols["offsets"], cols["type"], cols["size"], cols["saturation"])
+    dims = (32, 20, 32)
+    ctx.lbm_create(*dims)
+    ctx.lbm_set_boundary(None)
+    ctx.lbm_step(25)
+    ctx.wind_use_lbm(True)
+    v4 = ctx.lbm_get()["v"]
+    po = portapi.Port().init(dim, dim, ref.scale, ref.soils())
+    po.set_columns(cols)
+    po.set_wind_field(v4, dims)
+    xy = ref.spawn_list(n, seed=9)
+    r, g = po.wind_run(xy), ctx.wind_run(xy)
+    po.set_wind_field(None)
+    assert (g.steps, g.exit_oob) == (r.steps, r.exit_oob) and g.steps > 0
+    a, b = ctx.wind_state(), po.wind_state()
+    for k in b:
+        assert np.array_equal(np.ascontiguousarray(a[k]).view(np.uint8), np.ascontiguousarray(b[k]).view(np.uint8)), k
+    c1, c2 = po.columns(), ctx.download_columns()
+    for k in ("offsets", "type", "size", "floor", "saturation"):
+        assert np.array_equal(c1[k], c2[k]), k
+    ctx.wind_use_lbm(False)
+    ctx.close()
