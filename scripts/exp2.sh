@@ -6,7 +6,7 @@ L=$PWD/soilmachine_b200/lib
 O=gpurun_out/r02_exp2
 mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > $O/gpu.txt
-export SM_KERNEL=warp
+export SM_KERNEL=warp SM_HYDRO=warp
 Q='not config3 and not config4 and not ipc and not facade_per_particle and not lbm'
 ( timeout 900 python -m pytest tests -m gpu -x -q -k "$Q" 2>&1 | tail -15 ) > $O/tests_warp.log 2>&1
 ( timeout 300 python tests/gpu_probe.py cfg3:both 2
@@ -15,8 +15,10 @@ Q='not config3 and not config4 and not ipc and not facade_per_particle and not l
   SM_KERNEL=thread timeout 300 python tests/gpu_probe.py cfg3:both 2
   timeout 300 python tests/gpu_probe.py single
   SM_KERNEL=thread timeout 300 python tests/gpu_probe.py single
-  timeout 300 python tests/gpu_probe.py big ) > $O/timing.log 2>&1
-( SM_KERNEL=thread timeout 900 python -m pytest tests -m gpu -x -q -k "$Q" 2>&1 | tail -5 ) > $O/tests_thread.log 2>&1
+  timeout 300 python tests/gpu_probe.py big
+  timeout 300 python tests/gpu_probe.py hydro:cfg3
+  SM_HYDRO=thread timeout 300 python tests/gpu_probe.py hydro:cfg3 ) > $O/timing.log 2>&1
+( SM_KERNEL=thread SM_HYDRO=thread timeout 900 python -m pytest tests -m gpu -x -q -k "$Q" 2>&1 | tail -5 ) > $O/tests_thread.log 2>&1
 ( timeout 600 python -m pytest tests -m gpu -q -k "lbm or facade_per_particle or budget" 2>&1 | tail -25 ) > $O/tests_new.log 2>&1
 ( timeout 600 python -m pytest tests -m gpu -x -q -k "ipc" 2>&1 | tail -15 ) > $O/tests_ipc.log 2>&1
 ( timeout 900 python -m pytest tests -m gpu -x -q -k "config3" 2>&1 | tail -15 ) > $O/tests_cfg3.log 2>&1

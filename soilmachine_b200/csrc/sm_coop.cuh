@@ -98,7 +98,8 @@ SM_HD void wind_field_pspeed(const WindField& f, float px, float py, double heig
 // ------------------------------------------------------------------------------------------------
 // B provides: dimx() dimy() scale(), soilp(t) -> const SoilDev*, cell_ptr(x, y) -> Sec32* (global record),
 // focus(x, y), pool_load/pool_store/pool_alloc/pool_free, wfreq(ind) wtrack(ind) windfreq(ind),
-// set_wtrack(ind, v) set_windfreq(ind, v), note_transfer(), pspeed(px, py, height, out3), kBudget.
+// set_wtrack(ind, v) set_windfreq(ind, v), note_transfer(), pspeed(px, py, height, out3), kBudget, kHydroHooks
+// (+ air_mark(rec, x, y), wet_mark(x, y), volume_factor() when kHydroHooks).
 // ax..f_track are warp-uniform: every lane holds the same values and updates them identically.
 template <class B> struct CoopWin {
   B& b;
@@ -165,6 +166,18 @@ template <class B> struct CoopWin {
     const long off = (long)(r - s->win);
     if (off >= 0 && off < SM_CW_SLOTS) dirtym |= 1u << (int)off;
   }
+  // a record was modified: window bookkeeping (every lane) + the backing's hook for Air-topped cells (one lane;
+  // only the pooling-hydrology executor has one: it keeps the active-cell index of the seep pass up to date)
+  template <class W> SM_HD void touched(W& w, Sec32* r, int x, int y) {
+    dirty_rec(r);
+    if (B::kHydroHooks && w.lead()) b.air_mark(r, x, y);
+  }
+  // no staged patches: rec() hands out the records in place (the hydrology frames work that way)
+  SM_HD void detach() { ax = ay = bx = by = -(1 << 28); has_b = false; valid = 0; dirtym = 0; }
+  // single-lane services of sm_hydro.cuh's sequential pieces (hydro_seep_cell)
+  SM_HD void dirty_rec(Sec32* r, int x, int y) { dirty_rec(r); if (B::kHydroHooks) b.air_mark(r, x, y); }
+  SM_HD void wet_mark(int x, int y) { if (B::kHydroHooks) b.wet_mark(x, y); }
+  SM_HD double volume_factor() const { return b.volume_factor(); }
   // write the modified records back: one record per lane
   template <class W> SM_HD void flush(W& w) {
     const uint32_t m = dirtym;
@@ -270,8 +283,8 @@ template <int DEPTH, class W, class A> struct CascadeCoop {
         if (A::kBudget) a.s->acc[2] += (rec_height(*tr) - ht0) + (rec_height(*br) - hb0);
         a.s->u = re ? 1u : 0u;
       });
-      a.dirty_rec(pc);
-      a.dirty_rec(pn);
+      a.touched(w, pc, cx, cy);
+      a.touched(w, pn, nx, ny);
       if constexpr (DEPTH > 0) {
         const bool recascade = a.s->u != 0;
         if (recascade && transferloop > 0) {                                // :96-97

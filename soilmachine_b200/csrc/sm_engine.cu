@@ -205,6 +205,7 @@ template <class A> __device__ __forceinline__ int do_step(A& a, WaterP& p) { ret
 template <class A> __device__ __forceinline__ int do_step(A& a, WindP& p) { return wind_step(a, p); }
 
 #include "sm_sweep.cuh"
+#include "sm_hydro_coop.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // the persistent sweep kernel
@@ -1226,6 +1227,74 @@ __global__ void __launch_bounds__(32) k_hydro_seep(DevCtx c, ActiveMap am, Hydro
   hydro_count_out(out, hc);
 }
 
+// ---- the same two phases executed by one WARP (sm_hydro_coop.cuh): frames evaluated eight neighbours at a time,
+// nested particles on the cooperative step.  Records are accessed in place through L2 (a frame's nine records are
+// fetched by nine lanes at once, which is what the one-thread executor needs its shared-memory cache for).
+struct HydroBack : DevBack<false, false> {
+  static constexpr bool kHydroHooks = true;
+  ActiveMap act;
+  bool marking;
+  __device__ __forceinline__ HydroBack(const DevCtx& ctx, const SoilDev* ss, const ActiveMap& am, bool mk)
+      : DevBack<false, false>(ctx, ss, 0u), act(am), marking(mk) {}
+  // single writer: only the lane that mutates columns calls these
+  __device__ __forceinline__ void air_mark(Sec32* r, int x, int y) {
+    if (marking && r->type == SM_AIR) active_mark_block(act, x, y, c.dimx, c.dimy);
+  }
+  __device__ __forceinline__ void wet_mark(int x, int y) {
+    if (marking) active_set(act, (unsigned long long)x * c.dimy + y);
+  }
+};
+__global__ void __launch_bounds__(32) k_hydro_flood_w(DevCtx c, int n, HydroCount* out) {
+  __shared__ SoilDev s_soils[SM_MAX_SOILS];
+  __shared__ CoopScratch sc;
+  __shared__ HydroScratch hx;
+  const int lane = threadIdx.x;
+  for (int i = lane; i < c.nsoils; i += 32) s_soils[i] = c.soils[i];
+  __syncwarp();
+  WarpDev w{lane};
+  ActiveMap none{};
+  HydroBack back(c, s_soils, none, false);
+  CoopWin<HydroBack> a(back, &sc);
+  HydroCount hc{};
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    bool cand = false;
+    if (i < n) cand = (c.alive[i] == 0) && !(c.pb[i].x < SM_MINVOL) && c.done[i] != SM_DONE_FLOODED;
+    unsigned int m = __ballot_sync(0xFFFFFFFFu, cand);
+    while (m) {                                   // warp-uniform
+      const int j = base + __ffs((int)m) - 1;
+      m &= m - 1u;
+      const float4 pa = c.pa[j];
+      const double2 pb = c.pb[j];
+      WaterP p;
+      p.px = pa.x; p.py = pa.y; p.sx = pa.z; p.sy = pa.w;
+      p.volume = pb.x; p.sediment = pb.y; p.contains = c.pc[j].x;
+      hydro_flood_particle_coop(w, a, &hx, p, hc);
+      if (lane == 0) c.done[j] = SM_DONE_FLOODED;
+      __syncwarp();
+    }
+  }
+  if (lane == 0) hydro_count_out(out, hc);
+}
+__global__ void __launch_bounds__(32) k_hydro_seep_w(DevCtx c, ActiveMap am, HydroCount* out) {
+  __shared__ SoilDev s_soils[SM_MAX_SOILS];
+  __shared__ CoopScratch sc;
+  __shared__ HydroScratch hx;
+  const int lane = threadIdx.x;
+  for (int i = lane; i < c.nsoils; i += 32) s_soils[i] = c.soils[i];
+  __syncwarp();
+  WarpDev w{lane};
+  HydroBack back(c, s_soils, am, true);
+  CoopWin<HydroBack> a(back, &sc);
+  HydroCount hc{};
+  const unsigned long long cells = am.ncells;
+  for (unsigned long long cell = active_next(am, 0); cell < cells; cell = active_next(am, cell + 1)) {
+    hydro_seep_visit_coop(w, a, &hx, (int)(cell / (unsigned long long)c.dimy), (int)(cell % (unsigned long long)c.dimy), hc);
+    __syncwarp();
+  }
+  if (lane == 0) hydro_count_out(out, hc);
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -2014,6 +2083,13 @@ int sm_wind_run_device(sm_context* ctx, int32_t n, const float* d_xy, int32_t ma
 }
 
 // ---- pooling hydrology ----------------------------------------------------------------------------
+// SM_HYDRO=warp | thread selects the executor of the flood phase and the seep pass
+static bool hydro_warp() {
+  const char* e = getenv("SM_HYDRO");
+  if (e && strcmp(e, "warp") == 0) return true;
+  if (e && strcmp(e, "thread") == 0) return false;
+  return SM_DEFAULT_COOP;
+}
 static int hydro_ready(sm_context* ctx) {
   if (ctx->nsoils < 1) return fail(ctx, SM_ERR_INVALID, "soil table not set");
   if (ctx->nranks > 1) return fail(ctx, SM_ERR_INVALID, "pooling hydrology is not available on a sharded context");
@@ -2052,7 +2128,8 @@ int sm_water_flood(sm_context* ctx, sm_hydro_stats* st) {
   if (rc != SM_OK) return rc;
   if (ctx->cur_kind != KIND_WATER) return fail(ctx, SM_ERR_INVALID, "sm_water_flood: the last batch was not a water batch");
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
-  k_hydro_flood<<<1, 32, SM_HC_BYTES, ctx->stream>>>(ctx->d, ctx->cur_n, ctx->d_hydro);
+  if (hydro_warp()) k_hydro_flood_w<<<1, 32, 0, ctx->stream>>>(ctx->d, ctx->cur_n, ctx->d_hydro);
+  else k_hydro_flood<<<1, 32, SM_HC_BYTES, ctx->stream>>>(ctx->d, ctx->cur_n, ctx->d_hydro);
   ctx->launches++;
   CK(cudaGetLastError());
   return hydro_finish(ctx, st);
@@ -2075,7 +2152,8 @@ int sm_seep(sm_context* ctx, sm_hydro_stats* st) {
   CK(cudaEventRecord(ctx->evt0, ctx->stream));
   k_hydro_classify<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(ctx->d, am);
   CK(cudaEventRecord(ctx->evt1, ctx->stream));
-  k_hydro_seep<<<1, 32, SM_HC_BYTES, ctx->stream>>>(ctx->d, am, ctx->d_hydro);
+  if (hydro_warp()) k_hydro_seep_w<<<1, 32, 0, ctx->stream>>>(ctx->d, am, ctx->d_hydro);
+  else k_hydro_seep<<<1, 32, SM_HC_BYTES, ctx->stream>>>(ctx->d, am, ctx->d_hydro);
   ctx->launches += 2;
   CK(cudaGetLastError());
   int rc2 = hydro_finish(ctx, st);

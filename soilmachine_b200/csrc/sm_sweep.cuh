@@ -51,6 +51,10 @@ struct WarpDev {
 // backing store of CoopWin on the device
 template <bool MULTI, bool BUDGET = false> struct DevBack {
   static constexpr bool kBudget = BUDGET;
+  static constexpr bool kHydroHooks = false;
+  __device__ __forceinline__ void air_mark(Sec32*, int, int) {}
+  __device__ __forceinline__ void wet_mark(int, int) {}
+  __device__ __forceinline__ double volume_factor() const { return c.volume_factor; }
   const DevCtx& c;
   const SoilDev* s_soils;   // shared-memory copy of the soil table
   unsigned int phase;       // sweep number mod 3: frees go to ring[phase], allocations pop ring[(phase+1)%3]

@@ -12,6 +12,7 @@ CORE = os.path.join(HERE, "..", "soilmachine_b200", "csrc", "sm_core.cuh")
 NOISE = os.path.join(HERE, "..", "soilmachine_b200", "csrc", "sm_noise.cuh")
 HYDRO = os.path.join(HERE, "..", "soilmachine_b200", "csrc", "sm_hydro.cuh")
 COOP = os.path.join(HERE, "..", "soilmachine_b200", "csrc", "sm_coop.cuh")
+HCOOP = os.path.join(HERE, "..", "soilmachine_b200", "csrc", "sm_hydro_coop.cuh")
 
 SOILDEV = np.dtype([("friction", "<f4"), ("solubility", "<f4"), ("equrate", "<f4"), ("erosionrate", "<f4"),
                     ("maxdiff", "<f4"), ("settling", "<f4"), ("suspension", "<f4"), ("porosity", "<f4"),
@@ -32,7 +33,7 @@ class HydroCount(C.Structure):
 
 
 def build():
-    if (not os.path.exists(LIB)) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(CORE), os.path.getmtime(NOISE), os.path.getmtime(HYDRO), os.path.getmtime(COOP)):
+    if (not os.path.exists(LIB)) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(CORE), os.path.getmtime(NOISE), os.path.getmtime(HYDRO), os.path.getmtime(COOP), os.path.getmtime(HCOOP)):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", SRC, "-o", LIB])
     return LIB
 

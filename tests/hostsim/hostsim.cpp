@@ -10,6 +10,7 @@
 #include "../../soilmachine_b200/csrc/sm_noise.cuh"
 #include "../../soilmachine_b200/csrc/sm_hydro.cuh"
 #include "../../soilmachine_b200/csrc/sm_coop.cuh"
+#include "../../soilmachine_b200/csrc/sm_hydro_coop.cuh"
 
 namespace {
 struct HostMap {
@@ -95,6 +96,10 @@ struct HostBack {   // backing store of CoopWin on the host
   void set_windfreq(int i, float v) { M.windfreq[i] = v; }
   void note_transfer() {}
   static constexpr bool kBudget = true;
+  static constexpr bool kHydroHooks = true;     // the hooks HostAccess has (active-cell index of the seep pass)
+  void air_mark(Sec32* r, int x, int y) { h.dirty_rec(r, x, y); }
+  void wet_mark(int x, int y) { h.wet_mark(x, y); }
+  double volume_factor() const { return M.volume_factor; }
   void pspeed(float px, float py, double height, float* ps) const { wind_field_pspeed(G_field, px, py, height, ps); }
 };
 int G_coop = 0;   // 1: the sweeps below run the warp-cooperative step
@@ -252,15 +257,25 @@ void hs_water_flood(HydroCount* out) {
   HostAccess a; HydroCount hc{};
   std::vector<char> live(W.size(), 0);
   for (int i : Wlive) live[i] = 1;
-  for (size_t i = 0; i < W.size(); i++) if (!live[i]) hydro_flood_particle(a, W[i], hc);
+  if (G_coop) {            // the warp-cooperative executor (sm_hydro_coop.cuh), lanes as loops
+    WarpHost w; HostBack b; CoopScratch sc; HydroScratch hx; CoopWin<HostBack> cw(b, &sc);
+    for (size_t i = 0; i < W.size(); i++) if (!live[i]) hydro_flood_particle_coop(w, cw, &hx, W[i], hc);
+  } else {
+    for (size_t i = 0; i < W.size(); i++) if (!live[i]) hydro_flood_particle(a, W[i], hc);
+  }
   if (out) *out = hc;
 }
 // mode 0: visit every cell in x-major order, as upstream; mode 1: classify + visit the flagged cells only,
 // the way the device pass does
 void hs_seep(int mode, HydroCount* out) {
   HostAccess a; HydroCount hc{};
+  WarpHost w; HostBack b; CoopScratch sc; HydroScratch hx; CoopWin<HostBack> cw(b, &sc);
+  auto visit = [&](int x, int y) {
+    if (G_coop) hydro_seep_visit_coop(w, cw, &hx, x, y, hc);
+    else hydro_seep_visit(a, x, y, hc);
+  };
   if (mode == 0) {
-    for (int x = 0; x < M.dimx; x++) for (int y = 0; y < M.dimy; y++) hydro_seep_visit(a, x, y, hc);
+    for (int x = 0; x < M.dimx; x++) for (int y = 0; y < M.dimy; y++) visit(x, y);
   } else {
     ActiveMap am{};
     const unsigned long long cells = (unsigned long long)M.dimx * M.dimy;
@@ -277,7 +292,7 @@ void hs_seep(int mode, HydroCount* out) {
     }
     G_act = &am;
     for (unsigned long long c = active_next(am, 0); c < cells; c = active_next(am, c + 1))
-      hydro_seep_visit(a, (int)(c / M.dimy), (int)(c % M.dimy), hc);
+      visit((int)(c / M.dimy), (int)(c % M.dimy));
     G_act = nullptr;
   }
   if (out) *out = hc;

@@ -168,12 +168,34 @@ def test_product_hydrology_replays_golden(case, seep_mode):
     assert all(c.floods >= f for c, f in zip(counters, g["floods"]))
 
 
-def test_product_hydrology_counters_match_port():
+@pytest.mark.parametrize("case", _golden.HYDRO_CASES)
+@pytest.mark.parametrize("seep_mode", [0, 1], ids=["every_cell", "active_index"])
+@pytest.mark.parametrize("lane_order", [0, 1], ids=["lanes_up", "lanes_down"])
+def test_warp_cooperative_hydrology_replays_golden(case, seep_mode, lane_order):
+    """sm_hydro_coop.cuh - floods, water-table cascade frames evaluated eight neighbours at a time, nested
+    particles on the cooperative step, the seep pass - with the lanes run as loops on the host, against the vectors
+    generated from the reference's recursive code; the water batches themselves run the cooperative step too."""
+    g = _golden.load(case)
+    b = HydroBackend(g, seep_mode)
+    b.hs.lib.hs_set_mode(1, lane_order)
+    try:
+        b.hs.set_columns(_golden.cols(g, "init"))
+        counters = _golden.replay_hydro(g, b)
+        assert all(c.overflow == 0 for c in counters)
+        assert all(c.floods >= f for c, f in zip(counters, g["floods"]))
+    finally:
+        b.hs.lib.hs_set_mode(0, 0)
+
+
+@pytest.mark.parametrize("coop", [0, 1], ids=["thread", "warp"])
+def test_product_hydrology_counters_match_port(coop):
     """nested particles, their steps and the transfers are invisible to the verbatim reference; the oracle
-    port (recursive, pinned to the reference) and the product's frame machine must agree on them."""
+    port (recursive, pinned to the reference) and the product's frame machine - one thread (sm_hydro.cuh) or one
+    warp (sm_hydro_coop.cuh) - must agree on them."""
     from oracle import portapi
     g = _golden.load("hydro_bigbutte_40")
     b = HydroBackend(g, 1)
+    b.hs.lib.hs_set_mode(coop, 0)
     b.hs.set_columns(_golden.cols(g, "init"))
     po = portapi.Port().init(int(g["dimx"]), int(g["dimy"]), int(g["scale"]), g["soils"])
     po.set_columns(_golden.cols(g, "init"))
@@ -187,6 +209,7 @@ def test_product_hydrology_counters_match_port():
         assert (x.floods, x.nested, x.nested_steps, x.transfers) == (y.floods, y.nested, y.nested_steps, y.transfers)
         assert x.cells == cells and y.cells < cells
         po.frequency_update(); b.frequency_update()
+    b.hs.lib.hs_set_mode(0, 0)
 
 
 def test_active_index_next_and_set():
