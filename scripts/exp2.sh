@@ -12,6 +12,8 @@ Q='not config3 and not config4 and not ipc and not facade_per_particle and not l
 ( timeout 300 python tests/gpu_probe.py cfg3:both 2
   SM_LIB_PATH=$L/libsm_mb2.so timeout 300 python tests/gpu_probe.py cfg3:both 2
   SM_LIB_PATH=$L/libsm_mb4.so timeout 300 python tests/gpu_probe.py cfg3:both 2
+  SM_LIB_PATH=$L/libsm_w24.so timeout 300 python tests/gpu_probe.py cfg3:both 2
+  SM_LIB_PATH=$L/libsm_w4.so timeout 300 python tests/gpu_probe.py cfg3:both 2
   SM_KERNEL=thread timeout 300 python tests/gpu_probe.py cfg3:both 2
   timeout 300 python tests/gpu_probe.py single
   SM_KERNEL=thread timeout 300 python tests/gpu_probe.py single
