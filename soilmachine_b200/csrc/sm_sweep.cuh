@@ -348,13 +348,22 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
     if (gtid == 0) st_volatile_u32(&ctl->alive_slot[(s + 2) % 3], 0u);
 
     unsigned int my_alive = 0;
-    for (int pid = slot; pid < n; pid += nslots) {      // ascending index within a warp: no wait can cycle
-      const unsigned int av = c.alive[pid];
-      if (av == 0) continue;
-      // sharded map: a particle handed over during this very sweep carries the arrival mark 2 + parity of the
-      // sweep it arrived in; it has completed this sweep already and becomes runnable with the next one
-      // (the rank that handed it over counted it among the survivors of this sweep)
-      if (MULTI && av >= 2u && (av - 2u) == (tag & 1u)) continue;
+    // This warp's particles are slot, slot + nslots, slot + 2 nslots, ... (ascending index within a warp: no wait
+    // can cycle).  Their alive flags are fetched 32 at a time, one per lane, so a warp whose particles are mostly
+    // dead pays one round trip per 32 of them instead of one each.
+    for (int base = 0; slot + (long long)base * nslots < n; base += 32) {
+    const long long lpid = slot + (long long)(base + lane) * nslots;
+    const unsigned int av_l = (lpid < n) ? (unsigned int)c.alive[lpid] : 0u;
+    // sharded map: a particle handed over during this very sweep carries the arrival mark 2 + parity of the
+    // sweep it arrived in; it has completed this sweep already and becomes runnable with the next one
+    // (the rank that handed it over counted it among the survivors of this sweep)
+    const bool run_l = av_l != 0u && !(MULTI && av_l >= 2u && (av_l - 2u) == (tag & 1u));
+    unsigned int todo = __ballot_sync(0xffffffffu, run_l);
+    while (todo) {
+      const int t = __ffs((int)todo) - 1;
+      todo &= todo - 1u;
+      const int pid = slot + (base + t) * nslots;
+      const unsigned int av = __shfl_sync(0xffffffffu, av_l, t);
       last_active = s;
       P p;
       load_particle(c, pid, p);
@@ -423,6 +432,7 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
       else if (r == SM_EXIT_STALL) n_stall++;
       else { n_steps++; n_evap++; }
       __syncwarp();
+    }
     }
     if (lane == 0 && my_alive) atomicAdd(&s_alive, my_alive);
     __syncthreads();
