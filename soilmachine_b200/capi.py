@@ -179,6 +179,17 @@ class Context:
             pass
 
     def _ck(self, rc):
+        if rc == SM_ERR_POOL and getattr(self, "pool_warn", True):
+            # as upstream (layermap.h:92-95: print and drop the section, keep running): a warning, not an error;
+            # the call's stats count the drops.  Calls that cannot proceed (a pool too small for the terrain)
+            # turn the warning off around themselves and raise.
+            import warnings
+            warnings.warn("soilmachine_b200: " + self.lib.sm_last_error(self.h).decode(), RuntimeWarning)
+            return
+        if rc != SM_OK:
+            raise SoilMachineError(rc, self.lib.sm_last_error(self.h).decode())
+
+    def _ck_strict(self, rc):
         if rc != SM_OK:
             raise SoilMachineError(rc, self.lib.sm_last_error(self.h).decode())
 
@@ -191,7 +202,7 @@ class Context:
         lay = np.zeros(len(layers), LAYER_DTYPE)
         for k in LAYER_DTYPE.names:
             lay[k] = layers[k]
-        self._ck(self.lib.sm_initialize(self.h, int(seed), lay.ctypes.data_as(C.c_void_p), len(lay)))
+        self._ck_strict(self.lib.sm_initialize(self.h, int(seed), lay.ctypes.data_as(C.c_void_p), len(lay)))
 
     def upload_columns(self, offsets, typ, size, saturation=None):
         offsets = np.ascontiguousarray(offsets, np.int64)
@@ -199,8 +210,8 @@ class Context:
         size = np.ascontiguousarray(size, np.float64)
         sat = None if saturation is None else np.ascontiguousarray(saturation, np.float64)
         assert len(offsets) == self.cells + 1
-        self._ck(self.lib.sm_upload_columns(self.h, _p(offsets, C.c_int64), _p(typ, C.c_int32),
-                                            _p(size, C.c_double), _p(sat, C.c_double)))
+        self._ck_strict(self.lib.sm_upload_columns(self.h, _p(offsets, C.c_int64), _p(typ, C.c_int32),
+                                                   _p(size, C.c_double), _p(sat, C.c_double)))
 
     def section_count(self):
         n = C.c_int64()

@@ -204,6 +204,50 @@ def test_gpu_edge_cases():
         ctx.water_run(np.zeros((70001, 2), np.float32))   # larger than max_particles
 
 
+def test_pool_exhaustion_is_counted_reported_and_not_sticky():
+    """layermap.h:92-95: when the section pool runs dry upstream prints, drops the section and keeps running.
+    Here the drops are counted per call and reported as a warning (SM_ERR_POOL from the C ABI); a pool too small
+    for the terrain itself is an error; a later call that drops nothing is clean again."""
+    import warnings
+    import soilmachine_b200 as smb
+    from soilmachine_b200 import presets
+    pre = presets.load("rocksand")               # soil 1 = Rock, soil 2 = Red Sand
+    dim = 64
+    cells = dim * dim
+    # a chequerboard: bare rock next to rock under a thin sand cover -> sand picked up on one cell lands as a NEW
+    # section on the next one, and every new section needs a pool slot
+    x, y = np.meshgrid(np.arange(dim), np.arange(dim), indexing="ij")
+    sandy = ((x + y) % 2 == 0).reshape(-1)
+    tilt = (0.2 + 0.6 * x / dim + 0.1 * y / dim).reshape(-1)
+    counts = np.where(sandy, 2, 1)
+    offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    typ = np.ones(offsets[-1], np.int32); size = np.zeros(offsets[-1])
+    size[offsets[:-1]] = tilt
+    typ[offsets[:-1][sandy] + 1] = 2; size[offsets[:-1][sandy] + 1] = 0.02
+    need = int(sandy.sum())                      # buried sections of the initial terrain
+    with pytest.raises(smb.SoilMachineError) as e:
+        small = smb.Context(dim, dim, 80, max_particles=4096, pool_capacity=need - 1)
+        small.set_soils(pre["soils"])
+        small.upload_columns(offsets, typ, size)
+    assert e.value.code == smb.capi.SM_ERR_POOL
+    ctx = smb.Context(dim, dim, 80, max_particles=4096, pool_capacity=need + 3)
+    ctx.set_soils(pre["soils"])
+    ctx.upload_columns(offsets, typ, size)
+    rng = np.random.RandomState(0)
+    xy = (rng.rand(2000, 2) * (dim - 2) + 0.5).astype(np.float32)
+    with warnings.catch_warnings(record=True) as wlist:
+        warnings.simplefilter("always")
+        st = ctx.water_run(xy)
+    assert st.pool_drops > 0 and any("pool" in str(w.message) for w in wlist)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")           # a call that drops nothing must not warn: the status is per call
+        st2 = ctx.water_run(np.zeros((0, 2), np.float32))
+        assert st2.pool_drops == 0
+        h = ctx.heights()
+    assert np.isfinite(h).all()
+    ctx.close()
+
+
 def test_cpp_facade_frame_loop_runs():
     import os, subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
