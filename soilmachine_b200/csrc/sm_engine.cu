@@ -2341,7 +2341,8 @@ int sm_lbm_init(sm_context* ctx) {
   return SM_OK;
 }
 int sm_lbm_create(sm_context* ctx, int32_t nx, int32_t ny, int32_t nz) {
-  if (nx < 2 || ny < 2 || nz < 2 || (int64_t)nx * ny * nz > (1ll << 31)) return fail(ctx, SM_ERR_INVALID, "sm_lbm_create: size");
+  if (nx < 3 || ny < 3 || nz < 3 || (int64_t)nx * ny * nz * LBM_Q >= (1ll << 31))
+    return fail(ctx, SM_ERR_INVALID, "sm_lbm_create: 3 <= nx, ny, nz and nx*ny*nz*19 < 2^31");
   CK(cudaSetDevice(ctx->cfg.device));
   LbmDev& L = ctx->lbm;
   cudaFree(L.F[0]); cudaFree(L.F[1]); cudaFree(L.B); cudaFree(L.RHO); cudaFree(L.V);

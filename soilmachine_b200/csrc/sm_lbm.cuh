@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(256) k_lbm_step(LbmDev L, int src) {
     const int z = (int)(ind % L.nz), y = (int)((ind / L.nz) % L.ny), x = (int)(ind / ((size_t)L.nz * L.ny));
     float f[LBM_Q];
 #pragma unroll
-    for (int q = 0; q < LBM_Q; q++) f[q] = Fa[(size_t)q * n + ind];
+    for (int q = 0; q < LBM_Q; q++) f[q] = Fa[(unsigned int)q * (unsigned int)n + (unsigned int)ind];   // 19 n < 2^31 (sm_lbm_create)
     const bool solid = L.B[ind] > 0.0f;
     // ---- collide ----
     float rho = 0.0f;                                           // getRho, lbm.cs:101-108
@@ -160,22 +160,34 @@ __global__ void __launch_bounds__(256) k_lbm_step(LbmDev L, int src) {
       if (solid) post[q] = c_lbm.eq_rest[q];
     });
     // ---- stream (push) ----
-    const bool driven = (y == L.ny - 1 || x == 0 || x == L.nx - 1 || z == 0 || z == L.nz - 1);
+    // Where a population goes / comes from is decided per axis by compile-time offsets and nine per-cell flags,
+    // so each of the 19 slots costs a couple of predicate operations instead of a dozen comparisons.
+    const bool x0 = (x == 0), x1 = (x == 1), xl = (x == L.nx - 1), xl1 = (x == L.nx - 2);
+    const bool y0 = (y == 0), yl = (y == L.ny - 1), yl1 = (y == L.ny - 2);
+    const bool z0 = (z == 0), z1 = (z == 1), zl = (z == L.nz - 1), zl1 = (z == L.nz - 2);
+    const bool driven = (yl || x0 || xl || z0 || zl);
+    const unsigned int cell = (unsigned int)ind;
+    const unsigned int un = (unsigned int)n;
+    const int sxy = L.ny * L.nz;
     lbm_for_q([&](auto qc) {
       constexpr int q = LBM_QC(qc);
       constexpr int cx = LbmSet::c[q][0], cy = LbmSet::c[q][1], cz = LbmSet::c[q][2];
-      const int ax = x + cx, ay = y + cy, az = z + cz;           // destination of population q
-      if (ax >= 0 && ax < L.nx && ay >= 0 && ay < L.ny && az >= 0 && az < L.nz) {
-        const bool dst_driven = (ay == L.ny - 1 || ax == 0 || ax == L.nx - 1 || az == 0 || az == L.nz - 1);
-        if (!dst_driven) Fb[(size_t)q * n + (((size_t)ax * L.ny + ay) * L.nz + az)] = post[q];
-      }
+      // destination (x + cx, y + cy, z + cz) inside the lattice?
+      const bool dst_in = (cx < 0 ? !x0 : (cx > 0 ? !xl : true)) && (cy < 0 ? !y0 : (cy > 0 ? !yl : true)) &&
+                          (cz < 0 ? !z0 : (cz > 0 ? !zl : true));
+      // destination on a driven face (x' = 0, x' = NX-1, y' = NY-1, z' = 0, z' = NZ-1)?
+      const bool dst_driven = (cx < 0 ? x1 : (cx == 0 ? x0 : false)) || (cx > 0 ? xl1 : (cx == 0 ? xl : false)) ||
+                              (cy > 0 ? yl1 : (cy == 0 ? yl : false)) ||
+                              (cz < 0 ? z1 : (cz == 0 ? z0 : false)) || (cz > 0 ? zl1 : (cz == 0 ? zl : false));
+      if (dst_in && !dst_driven) Fb[(unsigned int)q * un + (unsigned int)((int)cell + cx * sxy + cy * L.nz + cz)] = post[q];
       // this cell's own slot q
       if (driven) {
-        Fb[(size_t)q * n + ind] = c_lbm.eq_force[q];            // stream.cs:25-35, after every push
+        Fb[(unsigned int)q * un + cell] = c_lbm.eq_force[q];     // stream.cs:25-35, after every push
       } else {
-        const int sx = x - cx, sy = y - cy, sz = z - cz;         // where slot q is fed from
-        if (!(sx >= 0 && sx < L.nx && sy >= 0 && sy < L.ny && sz >= 0 && sz < L.nz))
-          Fb[(size_t)q * n + ind] = f[q];                        // nobody pushes into it: it keeps its value
+        // slot q is fed from (x - cx, y - cy, z - cz); outside the lattice nobody pushes into it: it keeps its value
+        const bool src_in = (cx > 0 ? !x0 : (cx < 0 ? !xl : true)) && (cy > 0 ? !y0 : (cy < 0 ? !yl : true)) &&
+                            (cz > 0 ? !z0 : (cz < 0 ? !zl : true));
+        if (!src_in) Fb[(unsigned int)q * un + cell] = f[q];
       }
     });
   }
