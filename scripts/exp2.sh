@@ -9,7 +9,9 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > $O/gpu.txt
 export SM_KERNEL=warp SM_HYDRO=warp
 Q='not config3 and not config4 and not ipc and not facade_per_particle and not lbm'
 ( timeout 900 python -m pytest tests -m gpu -x -q -k "$Q" 2>&1 | tail -15 ) > $O/tests_warp.log 2>&1
+( SM_EXACT=1 timeout 900 python -m pytest tests -m gpu -x -q -k "$Q" 2>&1 | tail -15 ) > $O/tests_warp_exact.log 2>&1
 ( timeout 300 python tests/gpu_probe.py cfg3:both 2
+  SM_EXACT=1 timeout 300 python tests/gpu_probe.py cfg3:water 2
   SM_LIB_PATH=$L/libsm_mb2.so timeout 300 python tests/gpu_probe.py cfg3:both 2
   SM_LIB_PATH=$L/libsm_mb4.so timeout 300 python tests/gpu_probe.py cfg3:both 2
   SM_LIB_PATH=$L/libsm_w24.so timeout 300 python tests/gpu_probe.py cfg3:both 2

@@ -129,7 +129,7 @@ def soils_from(table):
 
 
 class PeerBlob(C.Structure):
-    _fields_ = [("ptr", C.c_uint64 * 16), ("ipc", (C.c_ubyte * 64) * 16), ("pool_cap", C.c_uint64),
+    _fields_ = [("ptr", C.c_uint64 * 24), ("ipc", (C.c_ubyte * 64) * 24), ("pool_cap", C.c_uint64),
                 ("rank", C.c_int32), ("device", C.c_int32)]
 
 

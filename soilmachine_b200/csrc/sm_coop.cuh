@@ -33,6 +33,7 @@
 #endif
 
 #define SM_CW_SLOTS 18   // patch A = 3x3 around ipos (slots 0-8), patch B = 3x3 around npos (slots 9-17)
+#define SM_CW_PLUS 186u   // (1<<1)|(1<<3)|(1<<4)|(1<<5)|(1<<7): the 5-point stencil inside a 3x3 block
 
 // Mass budget (the reference is not conservative, so "mass conservation" is a budget): six f64
 // accumulators per particle, summed in step order, identical in the oracle port (oracle/sm_oracle.cpp).  Heights
@@ -125,34 +126,54 @@ template <class B> struct CoopWin {
     }
     return -1;
   }
-  // stage the in-bounds cells of one 3x3 patch: one record per lane
-  template <class W> SM_HD void fetch(W& w, int ox, int oy, int base) {
+  // stage the in-bounds cells of patch A that `want` names (bit k = cell k of the 3x3 block): one record per lane
+  template <class W> SM_HD void fetch_a(W& w, uint32_t want) {
     const int nx_ = b.dimx(), ny_ = b.dimy();
+    const uint32_t have = valid;
     const uint32_t got = w.ballot(9, [&](int k) {
-      const int x = ox + k / 3 - 1, y = oy + k % 3 - 1;
-      bool need = x >= 0 && y >= 0 && x < nx_ && y < ny_;
-      if (base == 9 && need) {
-        const int dx = x - ax + 1, dy = y - ay + 1;
-        if ((unsigned)dx < 3u && (unsigned)dy < 3u) need = false;   // resolves to patch A
-      }
-      if (need) s->win[base + k] = *b.cell_ptr(x, y);
+      const int x = ax + k / 3 - 1, y = ay + k % 3 - 1;
+      const bool need = ((want >> k) & 1u) && !((have >> k) & 1u) && x >= 0 && y >= 0 && x < nx_ && y < ny_;
+      if (need) s->win[k] = *b.cell_ptr(x, y);
       return need;
     });
-    valid |= got << base;
+    valid |= got;
   }
-  template <class W> SM_HD void begin(W& w, int ix, int iy, int kind) {
+  // `mask`: which cells of the 3x3 block around ipos to stage now.  The default stages all nine.  The exact-footprint
+  // schedule stages only the plus-shaped stencil move() reads (SM_CW_PLUS): the corners may still be written by a
+  // lower-index particle this one has not had to wait for yet, and are staged by target() after the second wait.
+  template <class W> SM_HD void begin(W& w, int ix, int iy, int kind, uint32_t mask = 0x1FFu) {
     ax = ix; ay = iy; has_b = false; valid = 0; dirtym = 0;
     const int ind = iy * b.dimx() + ix;
     if (kind == 0) { f_freq = b.wfreq(ind); f_track = b.wtrack(ind); }
     else f_freq = b.windfreq(ind);
-    fetch(w, ix, iy, 0);
+    fetch_a(w, mask);
   }
+  // patch B = the 3x3 block around the new position: lanes 0-8 stage its cells that do not resolve to patch A,
+  // lanes 9-17 the cells of patch A inside that block that are not staged yet
   template <class W> SM_HD void target(W& w, int nx, int ny) {
     bx = nx; by = ny; has_b = true;
-    fetch(w, nx, ny, 9);
+    const int nx_ = b.dimx(), ny_ = b.dimy();
+    const uint32_t have = valid;
+    const uint32_t got = w.ballot(18, [&](int l) {
+      if (l < 9) {
+        const int x = nx + l / 3 - 1, y = ny + l % 3 - 1;
+        bool need = x >= 0 && y >= 0 && x < nx_ && y < ny_;
+        const int dx = x - ax + 1, dy = y - ay + 1;
+        if ((unsigned)dx < 3u && (unsigned)dy < 3u) need = false;     // resolves to patch A
+        if (need) s->win[9 + l] = *b.cell_ptr(x, y);
+        return need;
+      }
+      const int k = l - 9;
+      const int x = ax + k / 3 - 1, y = ay + k % 3 - 1;
+      const int dx = x - nx + 1, dy = y - ny + 1;
+      const bool need = !((have >> k) & 1u) && (unsigned)dx < 3u && (unsigned)dy < 3u && x >= 0 && y >= 0 && x < nx_ && y < ny_;
+      if (need) s->win[k] = *b.cell_ptr(x, y);
+      return need;
+    });
+    valid |= ((got & 0x1FFu) << 9) | (got >> 9);
   }
-  // every in-bounds cell of a staged patch is in the window; anything else (only the nested re-cascade of a
-  // wind step reaches it) is accessed in place
+  // every cell a step touches inside the two blocks is staged before it is touched; anything else (only the nested
+  // re-cascade of a wind step reaches it) is accessed in place
   SM_HD Sec32* rec(int x, int y) {
     const int sl = slot_of(x, y);
     return sl >= 0 ? &s->win[sl] : b.cell_ptr(x, y);
@@ -311,13 +332,19 @@ template <int DEPTH, class W, class A> struct CascadeCoop {
 // ------------------------------------------------------------------------------------------------
 // WaterParticle::move && interact, water.h:43-121
 // ------------------------------------------------------------------------------------------------
-template <class W, class A> SM_HD int water_step_coop(W& w, A& a, WaterP& p) {
+// What move() hands to interact() of the same step (the friction-modified `param` copy of water.h:48-54 is only
+// read for solubility and equrate afterwards).
+struct WaterMidCoop {
+  float freq, solubility, equrate;
+  double evaprate;
+  int ix, iy;
+};
+// WaterParticle::move, water.h:43-73.  `amask`: cells of the 3x3 block around ipos staged now (see CoopWin::begin).
+template <class W, class A> SM_HD int water_move_coop(W& w, A& a, WaterP& p, WaterMidCoop& m, uint32_t amask = 0x1FFu) {
   const int dimx = a.dimx(), dimy = a.dimy();
-  const int SCALE = a.scale();
   if (A::kBudget && w.lead()) { for (int k = 0; k < SM_BUDGET_SLOTS; k++) a.s->acc[k] = 0.0; }
-  // ---- move ----
   const int ix = (int)roundf(p.px), iy = (int)roundf(p.py);        // :45
-  a.begin(w, ix, iy, 0);
+  a.begin(w, ix, iy, 0, amask);
   const sm_f3 n = map_normal(a, ix, iy);                            // :46
   Sec32* const ir = a.rec(ix, iy);
   SoilDev param = a.soil(rec_surface(*ir));                         // :47-48
@@ -327,6 +354,8 @@ template <class W, class A> SM_HD int water_step_coop(W& w, A& a, WaterP& p) {
   const float freq = a.f_freq;
   param.friction = param.friction * (1.0f - freq);                  // :53
   evaprate = evaprate * (1.0f - 0.2f * freq);                       // :54
+  m.freq = freq; m.solubility = param.solubility; m.equrate = param.equrate; m.evaprate = evaprate;
+  m.ix = ix; m.iy = iy;
   {
     const float vx = n.x * param.friction, vz = n.z * param.friction;   // :56
     if (sqrtf(vx * vx + vz * vz) < 1E-5) return SM_EXIT_STALL;
@@ -347,10 +376,18 @@ template <class W, class A> SM_HD int water_step_coop(W& w, A& a, WaterP& p) {
     p.volume = 0.0;
     return SM_EXIT_OOB;
   }
-  // ---- interact ----
+  return SM_ALIVE;
+}
+// WaterParticle::interact, water.h:75-121
+template <class W, class A> SM_HD int water_interact_coop(W& w, A& a, WaterP& p, const WaterMidCoop& m) {
+  const int SCALE = a.scale();
+  const int ix = m.ix, iy = m.iy;
+  const float freq = m.freq;
+  const double evaprate = m.evaprate;
+  Sec32* const ir = a.rec(ix, iy);
   const int nx = (int)roundf(p.px), ny = (int)roundf(p.py);
   a.target(w, nx, ny);
-  double c_eq = param.solubility * (rec_height(*ir) - map_height_bilinear(a, p.px, p.py)) *
+  double c_eq = m.solubility * (rec_height(*ir) - map_height_bilinear(a, p.px, p.py)) *
                 (double)SCALE / 80.0;                               // :78
   if (c_eq < 0.0) c_eq = 0.0;
   if (c_eq > 1.0) c_eq = 1.0;
@@ -358,9 +395,9 @@ template <class W, class A> SM_HD int water_step_coop(W& w, A& a, WaterP& p) {
     p.contains = a.soil(p.contains).erodes;
   const double cdiff = c_eq - p.sediment;                           // :87
   if (cdiff > 0) {                                                  // :91-101
-    p.sediment += param.equrate * cdiff;
+    p.sediment += m.equrate * cdiff;
     p.contains = a.soil(rec_surface(*ir)).transports;
-    const double amount = param.equrate * cdiff * p.volume;
+    const double amount = m.equrate * cdiff * p.volume;
     w.one([&]() {
       const double h0 = A::kBudget ? rec_height(*ir) : 0.0;
       a.focus(ix, iy);
@@ -394,6 +431,13 @@ template <class W, class A> SM_HD int water_step_coop(W& w, A& a, WaterP& p) {
     if (!lives) a.s->acc[3] += p.sediment * p.volume;
   }
   return lives ? SM_ALIVE : SM_EXIT_EVAP;
+}
+// one move() && interact()
+template <class W, class A> SM_HD int water_step_coop(W& w, A& a, WaterP& p, uint32_t amask = 0x1FFu) {
+  WaterMidCoop m;
+  const int r = water_move_coop(w, a, p, m, amask);
+  if (r != SM_ALIVE) return r;
+  return water_interact_coop(w, a, p, m);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -67,6 +67,7 @@ struct PeerPtrs {
   unsigned long long* head[2];
   uint2* node[2];
   double* bud;
+  unsigned int* fin;
 };
 
 struct DevCtx {

@@ -56,6 +56,9 @@ __device__ __forceinline__ int particle_reach(const WindP& p) {
 #define SM_MINBLOCKS 3  // resident blocks per SM the sweep kernels are compiled for (register cap)
 #endif
 #define SM_SWEEPS_NONE 0x40000000   // internal: run the prologue only
+#ifndef SM_DEFAULT_EXACT
+#define SM_DEFAULT_EXACT 0             // warp kernel: exact footprints for water batches (flipped once measured)
+#endif
 #ifndef SM_DEFAULT_COOP
 #define SM_DEFAULT_COOP false          // flipped once k_sweep has passed the GPU parity suite
 #endif
@@ -203,9 +206,6 @@ template <> struct PType<KIND_WIND> { typedef WindP T; };
 
 template <class A> __device__ __forceinline__ int do_step(A& a, WaterP& p) { return water_step(a, p); }
 template <class A> __device__ __forceinline__ int do_step(A& a, WindP& p) { return wind_step(a, p); }
-
-#include "sm_sweep.cuh"
-#include "sm_hydro_coop.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // the persistent sweep kernel
@@ -513,6 +513,9 @@ template <class A> __device__ __forceinline__ int do_move(A& a, WaterP& p, Water
 template <class A> __device__ __forceinline__ int do_move(A& a, WindP& p, WindMid& m) { return wind_move(a, p, m); }
 template <class A> __device__ __forceinline__ int do_interact(A& a, WaterP& p, const WaterMid& m) { return water_interact(a, p, m); }
 template <class A> __device__ __forceinline__ int do_interact(A& a, WindP& p, const WindMid& m) { return wind_interact(a, p, m); }
+
+#include "sm_sweep.cuh"
+#include "sm_hydro_coop.cuh"
 
 template <int KIND>
 __global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run_exact(DevCtx c, int n, const float* __restrict__ spawn,
@@ -1308,7 +1311,7 @@ struct sm_context {
   size_t lcells = 0;       // cells of this rank's x-strip (top records); == cells when not sharded
   int nranks = 1, rank = 0, x0 = 0, x1 = 0, share = 1;
   bool peers_attached = false;
-  void* ipc_opened[SM_MAX_RANKS][16] = {};
+  void* ipc_opened[SM_MAX_RANKS][SM_PEER_SLOTS] = {};
   int max_particles = 0;
   int nsoils = 0;
   SoilDev* d_soils = nullptr;
@@ -1363,7 +1366,7 @@ void sm_destroy(sm_context* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
   cudaDeviceSynchronize();
-  for (int q = 0; q < SM_MAX_RANKS; q++) for (int i = 0; i < 16; i++) if (ctx->ipc_opened[q][i]) cudaIpcCloseMemHandle(ctx->ipc_opened[q][i]);
+  for (int q = 0; q < SM_MAX_RANKS; q++) for (int i = 0; i < SM_PEER_SLOTS; i++) if (ctx->ipc_opened[q][i]) cudaIpcCloseMemHandle(ctx->ipc_opened[q][i]);
   DevCtx& d = ctx->d;
   cudaFree(d.top); cudaFree(d.pool); cudaFree(d.ringbuf[0]); cudaFree(d.ringbuf[1]); cudaFree(d.ringbuf[2]);
   cudaFree(d.wfreq); cudaFree(d.wtrack); cudaFree(d.windfreq); cudaFree(ctx->d_soils);
@@ -1514,21 +1517,21 @@ static void own_ptrs(sm_context* ctx, void** p) {
   DevCtx& d = ctx->d;
   p[0] = d.top; p[1] = d.pool; p[2] = d.ringbuf[0]; p[3] = d.ringbuf[1]; p[4] = d.ctl; p[5] = d.pa; p[6] = d.pb;
   p[7] = d.pc; p[8] = d.alive; p[9] = d.done; p[10] = d.head[0]; p[11] = d.head[1]; p[12] = d.node[0]; p[13] = d.node[1];
-  p[14] = d.ringbuf[2]; p[15] = d.bud;
+  p[14] = d.ringbuf[2]; p[15] = d.bud; p[16] = d.fin;
 }
 static void fill_peer(PeerPtrs& P, void* const* p, unsigned long long pool_cap) {
   P.top = (Sec32*)p[0]; P.pool = (Sec32*)p[1]; P.ringbuf[0] = (uint32_t*)p[2]; P.ringbuf[1] = (uint32_t*)p[3];
   P.ctl = (RunCtl*)p[4]; P.pa = (float4*)p[5]; P.pb = (double2*)p[6]; P.pc = (uint2*)p[7];
   P.alive = (unsigned char*)p[8]; P.done = (unsigned int*)p[9]; P.head[0] = (unsigned long long*)p[10];
   P.head[1] = (unsigned long long*)p[11]; P.node[0] = (uint2*)p[12]; P.node[1] = (uint2*)p[13];
-  P.ringbuf[2] = (uint32_t*)p[14]; P.bud = (double*)p[15];
+  P.ringbuf[2] = (uint32_t*)p[14]; P.bud = (double*)p[15]; P.fin = (unsigned int*)p[16];
   P.pool_cap = pool_cap;
 }
 int sm_peer_export(sm_context* ctx, sm_peer_blob* out) {
   if (!out) return fail(ctx, SM_ERR_INVALID, "null blob");
   CK(cudaSetDevice(ctx->cfg.device));
   memset(out, 0, sizeof(*out));
-  void* p[16] = {};
+  void* p[SM_PEER_SLOTS] = {};
   own_ptrs(ctx, p);
   for (int i = 0; i < SM_PEER_ARRAYS; i++) {
     out->ptr[i] = (uint64_t)(uintptr_t)p[i];
@@ -1549,7 +1552,7 @@ int sm_peer_attach(sm_context* ctx, const sm_peer_blob* blobs, int32_t nblobs, i
   for (int q = 0; q < ctx->nranks; q++) {
     const sm_peer_blob& b = blobs[q];
     if (b.rank != q) return fail(ctx, SM_ERR_INVALID, "sm_peer_attach: blobs must be ordered by rank");
-    void* p[16] = {};
+    void* p[SM_PEER_SLOTS] = {};
     if (q == ctx->rank) {
       own_ptrs(ctx, p);
     } else if (!use_ipc) {
@@ -1949,11 +1952,20 @@ static int launch_run(sm_context* ctx, int kind, int n, const float* d_spawn, in
     const int cthreads = SM_SW_WARPS * 32;
     int occ = 0;
     const bool budget = ctx->d.bud != nullptr;
-    void* const fns[8] = {(void*)k_sweep<KIND_WATER, false, false>, (void*)k_sweep<KIND_WIND, false, false>,
-                          (void*)k_sweep<KIND_WATER, true, false>,  (void*)k_sweep<KIND_WIND, true, false>,
-                          (void*)k_sweep<KIND_WATER, false, true>,  (void*)k_sweep<KIND_WIND, false, true>,
-                          (void*)k_sweep<KIND_WATER, true, true>,   (void*)k_sweep<KIND_WIND, true, true>};
-    void* fn = fns[(budget ? 4 : 0) + (multi ? 2 : 0) + (kind == KIND_WATER ? 0 : 1)];
+    // SM_EXACT: bit 0 = water batches use exact footprints (sweep_water_exact); wind keeps the conservative rule
+    bool exact = false;
+    {
+      const char* e = getenv("SM_EXACT");
+      exact = (kind == KIND_WATER) && ((e ? atoi(e) : SM_DEFAULT_EXACT) & 1);
+    }
+    void* const fns[12] = {(void*)k_sweep<KIND_WATER, false, false, false>, (void*)k_sweep<KIND_WIND, false, false, false>,
+                           (void*)k_sweep<KIND_WATER, true, false, false>,  (void*)k_sweep<KIND_WIND, true, false, false>,
+                           (void*)k_sweep<KIND_WATER, false, true, false>,  (void*)k_sweep<KIND_WIND, false, true, false>,
+                           (void*)k_sweep<KIND_WATER, true, true, false>,   (void*)k_sweep<KIND_WIND, true, true, false>,
+                           (void*)k_sweep<KIND_WATER, false, false, true>,  (void*)k_sweep<KIND_WATER, true, false, true>,
+                           (void*)k_sweep<KIND_WATER, false, true, true>,   (void*)k_sweep<KIND_WATER, true, true, true>};
+    void* fn = exact ? fns[8 + (budget ? 2 : 0) + (multi ? 1 : 0)]
+                     : fns[(budget ? 4 : 0) + (multi ? 2 : 0) + (kind == KIND_WATER ? 0 : 1)];
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)fn, cthreads, 0));
     if (occ < 1) return fail(ctx, SM_ERR_CUDA, "sweep kernel does not fit an SM");
     // contexts that share the device must all be resident at once (they meet in the cross-rank barrier)

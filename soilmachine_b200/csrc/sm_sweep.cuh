@@ -119,7 +119,10 @@ struct __align__(32) WarpSmem {
   uint32_t blk[32];      // in-range lower-index particles of this sweep (rank in bits 28-31 on a sharded map)
   uint32_t pred[12];     // per-bin predecessors (largest lower index in each of the 3x3 bins)
   uint32_t cnt;
-  uint32_t pad_[3];
+  uint32_t m0;           // exact schedule: bit l = entry l can delay move() (its box can meet plus(ipos))
+  uint32_t remote;       // exact schedule: some in-range lower-index particle is executed by another rank
+  uint32_t pad_;
+  uint32_t blkxy[32];    // exact schedule: packed (ipos, reach) of entry l, as in the bin node
 };
 
 template <class W, class A> __device__ __forceinline__ int do_step_coop(W& w, A& a, WaterP& p) { return water_step_coop(w, a, p); }
@@ -131,13 +134,13 @@ template <class W, class A> __device__ __forceinline__ int do_step_coop(W& w, A&
 // range): the nine per-bin predecessors.  Every particle always waits for its own-bin predecessor, hence
 // "X done => every lower index in X's bin done", which makes the per-bin predecessors a complete (conservative)
 // blocker set however large the cluster is.  Returns this lane's wait target (SM_NIL = none).
-template <int KIND, bool MULTI>
+template <int KIND, bool MULTI, bool EXACT = false>
 __device__ __forceinline__ uint32_t coop_scan(const DevCtx& c, WarpSmem& ws, int lane, unsigned int tag, int pid, int ix,
                                               int iy, int R) {
   const unsigned int par = tag & 1u;
   const int G = Reach<KIND>::G;
   const int nbx = (c.dimx + G - 1) / G, nby = (c.dimy + G - 1) / G;
-  if (lane == 0) ws.cnt = 0;
+  if (lane == 0) { ws.cnt = 0; if (EXACT) { ws.m0 = 0; ws.remote = 0; } }
   __syncwarp();
   if (lane < 9) {
     const int cx = ix / G + lane / 3 - 1, cy = iy / G + lane % 3 - 1;
@@ -160,7 +163,16 @@ __device__ __forceinline__ uint32_t coop_scan(const DevCtx& c, WarpSmem& ws, int
             dy = dy < 0 ? -dy : dy;
             if (dx <= D && dy <= D) {
               const unsigned int at = atomicAdd(&ws.cnt, 1u);
-              if (at < SM_SW_NEAR) ws.blk[at] = j | qtag;
+              if (at < SM_SW_NEAR) {
+                ws.blk[at] = j | qtag;
+                if (EXACT) {
+                  ws.blkxy[at] = nd.y;
+                  // static pruning: a neighbour whose box cannot meet plus(ipos) never delays the move
+                  if (Foot<KIND>::box_hits_M((int)(nd.y >> 18) - ix, (int)((nd.y >> 4) & 0x3FFFu) - iy, (int)(nd.y & 0xFu)))
+                    atomicOr(&ws.m0, 1u << at);
+                  if (MULTI && bq != c.rank) ws.remote = 1u;
+                }
+              }
             }
           }
           j = nd.x;
@@ -254,7 +266,95 @@ __device__ __forceinline__ unsigned int grid_barrier_x(const DevCtx& c, unsigned
   return *s_total;
 }
 
-template <int KIND, bool MULTI, bool BUDGET>
+// ---- exact footprints (water) ----------------------------------------------------------------------------------
+// The conservative rule orders two steps whenever their boxes (ipos +- 3) overlap, but a water step really touches
+// F = plus(ipos) U 3x3(npos) - about 14 of the 49 cells - and npos is only known after move().  With EXACT a
+// particle publishes three words per sweep: mv (= npos, right after move(); it only lets others SKIP a wait, so it
+// needs no fence), fin (its map writes are complete; release) and done (published in own-bin index order, which
+// keeps "X done => every lower index in X's bin done" and with it the crowded fallback sound).  A lower-index
+// particle B in range holds A back
+//   before A.move()     only while B's writes {ipos_B} U 3x3(npos_B) can meet plus(ipos_A)
+//                       (B not moved yet: while B's box can),
+//   before A.interact() only while F_B can meet F_A (B not moved yet: while B's box can meet F_A).
+// The oracle emulation of this rule halves the longest chain per sweep at config-3 density.  Particles with more
+// than SM_SW_NEAR neighbours in range, or (sharded maps) with a neighbour executed by another rank, take the
+// conservative path for that sweep - waiting for `done` is always sufficient.
+// Returns the step's result; fin and done are published inside.
+template <bool MULTI, bool BUDGET>
+__device__ __forceinline__ int sweep_water_exact(const DevCtx& c, WarpSmem& ws, WarpDev& w, const SoilDev* s_soils,
+                                                 unsigned int tag, int pid, int ix, int iy, int myR, WaterP& p,
+                                                 bool edge) {
+  const int lane = w.lane;
+  const unsigned int par = tag & 1u;
+  const unsigned int cnt = ws.cnt;
+  const uint32_t ownpred = ws.pred[4];
+  // this lane's neighbour
+  const bool mine = lane < (int)cnt;
+  const uint32_t j = mine ? (ws.blk[lane] & 0x0FFFFFFFu) : 0u;   // executed by this rank (else the caller goes conservative)
+  const uint32_t jxy = mine ? ws.blkxy[lane] : 0u;
+  const int jx = (int)(jxy >> 18), jy = (int)((jxy >> 4) & 0x3FFFu), jR = (int)(jxy & 0xFu);
+  bool need1 = mine;                                   // still to be resolved before interact()
+  bool need0 = mine && ((ws.m0 >> lane) & 1u);         // ... before move()
+  int mx = 0, my = 0;
+  bool moved = false;                                  // neighbour's npos known
+  // ---- wait to move ----
+  for (;;) {
+    if (need0) {
+      if (ld_acquire_u32(&c.fin[j]) >= tag) { need0 = false; need1 = false; }
+      else {
+        const unsigned long long v = *((volatile unsigned long long*)&c.mv[j]);
+        if ((unsigned int)(v >> 32) == tag) {
+          mx = (int)((v >> 16) & 0xFFFFu); my = (int)(v & 0xFFFFu); moved = true;
+          if (!Foot<KIND_WATER>::W_hits_M(jx, jy, mx, my, ix, iy)) need0 = false;
+        }
+      }
+    }
+    if (!__any_sync(0xffffffffu, need0)) break;
+  }
+  DevBack<MULTI, BUDGET> back(c, s_soils, tag);
+  CoopWin<DevBack<MULTI, BUDGET> > a(back, &ws.cs);
+  WaterMidCoop mid;
+  int r = water_move_coop(w, a, p, mid, SM_CW_PLUS);
+  if (r == SM_ALIVE) {
+    const int nx = (int)roundf(p.px), ny = (int)roundf(p.py);
+    if (lane == 0)
+      *((volatile unsigned long long*)&c.mv[pid]) = ((unsigned long long)tag << 32) | ((unsigned long long)nx << 16) | (unsigned long long)ny;
+    // ---- wait to interact ----
+    for (;;) {
+      if (need1) {
+        if (ld_acquire_u32(&c.fin[j]) >= tag) need1 = false;
+        else {
+          if (!moved) {
+            const unsigned long long v = *((volatile unsigned long long*)&c.mv[j]);
+            if ((unsigned int)(v >> 32) == tag) { mx = (int)((v >> 16) & 0xFFFFu); my = (int)(v & 0xFFFFu); moved = true; }
+          }
+          const bool hit = moved ? Foot<KIND_WATER>::F_hits_F(ix, iy, nx, ny, jx, jy, mx, my)
+                                 : Foot<KIND_WATER>::box_hits_F(ix, iy, nx, ny, jx, jy, jR);
+          if (!hit) need1 = false;
+        }
+      }
+      if (!__any_sync(0xffffffffu, need1)) break;
+    }
+    r = water_interact_coop(w, a, p, mid);
+    a.flush(w);
+  }
+  // stalled or left the map in move(): only track[] was written
+  if (lane == 0) {
+    st_release_u32(&c.fin[pid], r == SM_ALIVE ? tag : 0xFFFFFFFFu);
+    // `done` in own-bin index order
+    if (ownpred != SM_NIL) {
+      const unsigned int* dp = MULTI ? &c.peer[ownpred >> 28].done[ownpred & 0x0FFFFFFFu] : &c.done[ownpred];
+      while (ld_acquire_u32(dp) < tag) { }
+    }
+    const unsigned int pub = (r == SM_ALIVE) ? tag : 0xFFFFFFFFu;
+    if (MULTI && edge) st_release_sys_u32(&c.done[pid], pub);
+    else st_release_u32(&c.done[pid], pub);
+  }
+  __syncwarp();
+  return r;
+}
+
+template <int KIND, bool MULTI, bool BUDGET, bool EXACT>
 __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(DevCtx c, int n, const float* __restrict__ spawn,
                                                                             int max_sweeps) {
   typedef typename PType<KIND>::T P;
@@ -311,6 +411,7 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
         }
         c.alive[pid] = alive ? 1 : 0;
         c.done[pid] = alive ? (tag0 - 1u) : 0xFFFFFFFFu;
+        if (EXACT) c.fin[pid] = alive ? (tag0 - 1u) : 0xFFFFFFFFu;
         if (BUDGET) for (int k = 0; k < SM_BUDGET_SLOTS; k++) c.bud[(size_t)pid * SM_BUDGET_SLOTS + k] = 0.0;
       } else {
         alive = c.alive[pid] != 0;
@@ -369,27 +470,36 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
       load_particle(c, pid, p);
       const int ix = (int)roundf(p.px), iy = (int)roundf(p.py);
       const int myR = particle_reach(p);
-      const uint32_t tgt = coop_scan<KIND, MULTI>(c, ws, lane, tag, pid, ix, iy, myR);
-      coop_wait<MULTI>(c, tag, tgt);
-
-      DevBack<MULTI, BUDGET> back(c, s_soils, tag);
-      CoopWin<DevBack<MULTI, BUDGET> > a(back, &ws.cs);
-      const int r = do_step_coop(w, a, p);
-      // hand-off first: the map writes are all the successors of this step wait for
-      a.flush(w);
+      const uint32_t tgt = coop_scan<KIND, MULTI, EXACT>(c, ws, lane, tag, pid, ix, iy, myR);
+      // sharded map: only particles within two bins of a strip edge can have touched a peer's records or be polled
+      // from another rank: they release at system scope, the interior ones at gpu scope
+      bool edge = false;
+      if (MULTI) {
+        const int xlo = c.rank * c.strip_w, xhi = xlo + c.strip_w;
+        edge = (ix < xlo + 32 && c.rank > 0) || (ix >= xhi - 32 && c.rank < c.nranks - 1);
+      }
+      int r = SM_ALIVE;
+      bool exact_now = false;
+      if constexpr (EXACT && KIND == KIND_WATER) {
+        exact_now = ws.cnt <= SM_SW_NEAR && !(MULTI && ws.remote);
+        if (exact_now) r = sweep_water_exact<MULTI, BUDGET>(c, ws, w, s_soils, tag, pid, ix, iy, myR, p, edge);
+      }
+      if (!exact_now) {
+        coop_wait<MULTI>(c, tag, tgt);
+        DevBack<MULTI, BUDGET> back(c, s_soils, tag);
+        CoopWin<DevBack<MULTI, BUDGET> > a(back, &ws.cs);
+        r = do_step_coop(w, a, p);
+        // hand-off first: the map writes are all the successors of this step wait for
+        a.flush(w);
+        if (lane == 0) {
+          const unsigned int pub = (r == SM_ALIVE) ? tag : 0xFFFFFFFFu;
+          if (EXACT) st_release_u32(&c.fin[pid], pub);
+          if (MULTI && edge) st_release_sys_u32(&c.done[pid], pub);
+          else st_release_u32(&c.done[pid], pub);
+        }
+      }
       const int jx = (int)roundf(p.px), jy = (int)roundf(p.py);
       if (lane == 0) {
-        const unsigned int pub = (r == SM_ALIVE) ? tag : 0xFFFFFFFFu;
-        if (MULTI) {
-          // only particles within two bins of a strip edge can have touched a peer's records or be polled
-          // from another rank: they release at system scope, the interior ones at gpu scope
-          const int xlo = c.rank * c.strip_w, xhi = xlo + c.strip_w;
-          const bool edge = (ix < xlo + 32 && c.rank > 0) || (ix >= xhi - 32 && c.rank < c.nranks - 1);
-          if (edge) st_release_sys_u32(&c.done[pid], pub);
-          else st_release_u32(&c.done[pid], pub);
-        } else {
-          st_release_u32(&c.done[pid], pub);
-        }
         // own state and next sweep's bins are only needed after the grid barrier
         if (BUDGET) {
           // the step's six sums join the particle's totals; the totals travel with a particle that changes strips
@@ -415,6 +525,7 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
             o.pa = c.peer[nq].pa; o.pb = c.peer[nq].pb; o.pc = c.peer[nq].pc;
             store_particle(o, pid, p);
             c.peer[nq].done[pid] = tag;            // it has completed this sweep, wherever it is asked
+            if (EXACT) c.peer[nq].fin[pid] = tag;
             c.peer[nq].alive[pid] = (unsigned char)(2u + (tag & 1u));
             c.alive[pid] = 0;
           } else {

@@ -198,7 +198,7 @@ int hs_water_sweep(Stats* st) {
     int r;
     if (G_coop) {
       WarpHost w; HostBack b; CoopScratch sc; CoopWin<HostBack> cw(b, &sc);
-      r = water_step_coop(w, cw, W[i]);
+      r = water_step_coop(w, cw, W[i], G_coop == 2 ? SM_CW_PLUS : 0x1FFu);   // 2: staged as the exact-footprint schedule does
       cw.flush(w);
       for (int k = 0; k < SM_BUDGET_SLOTS; k++) BUD[(size_t)i * SM_BUDGET_SLOTS + k] += sc.acc[k];
     } else r = water_step(a, W[i]);

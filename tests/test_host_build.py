@@ -65,6 +65,20 @@ def test_product_arithmetic_replays_golden_frame(case):
 
 
 @pytest.mark.parametrize("case", _golden.FRAME_CASES)
+def test_warp_cooperative_step_with_late_corner_staging(case):
+    """the water step with only the plus-shaped stencil staged before move() and the corners of the first block staged
+    with the second block (what the exact-footprint schedule needs, CoopWin::begin / target)"""
+    g = _golden.load(case)
+    b = Backend(g)
+    b.hs.lib.hs_set_mode(2, 0)
+    try:
+        b.hs.set_columns(_golden.cols(g, "init"))
+        _golden.replay_frame(g, b, stats5)
+    finally:
+        b.hs.lib.hs_set_mode(0, 0)
+
+
+@pytest.mark.parametrize("case", _golden.FRAME_CASES)
 @pytest.mark.parametrize("lane_order", [0, 1], ids=["lanes_up", "lanes_down"])
 def test_warp_cooperative_step_replays_golden_frame(case, lane_order):
     """sm_coop.cuh - the step as the sweep kernel's warps execute it (lane-parallel gathers and cascade
