@@ -285,7 +285,6 @@ __device__ __forceinline__ int sweep_water_exact(const DevCtx& c, WarpSmem& ws, 
                                                  unsigned int tag, int pid, int ix, int iy, int myR, WaterP& p,
                                                  bool edge) {
   const int lane = w.lane;
-  const unsigned int par = tag & 1u;
   const unsigned int cnt = ws.cnt;
   const uint32_t ownpred = ws.pred[4];
   // this lane's neighbour
