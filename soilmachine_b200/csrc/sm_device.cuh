@@ -132,6 +132,29 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
 __device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// relaxed polls: a spin loop reads with relaxed loads (an acquire load drags an L1 invalidation along on every
+// iteration - CCTL.IVALL was 12 % of all stall samples of the first warp-kernel profile, and the poll traffic slows
+// every other L2 access down) and acquires ONCE when the value it waited for has arrived
+__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned int ld_relaxed_sys_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#ifndef SM_POLL_NS
+#define SM_POLL_NS 0          // back-off between two polls of a spin loop, ns (0 = none)
+#endif
+__device__ __forceinline__ void poll_backoff() { if (SM_POLL_NS > 0) __nanosleep(SM_POLL_NS); }
 // system scope: the other end may be a different GPU
 __device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int* p) {
   unsigned int v;
@@ -160,7 +183,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
     __threadfence();
     atomicAdd(counter, 1u);
     const unsigned int target = epoch * gridDim.x;
-    while ((int)(ld_volatile_u32(counter) - target) < 0) { }
+    while ((int)(ld_relaxed_u32(counter) - target) < 0) poll_backoff();
     __threadfence();
   }
   __syncthreads();

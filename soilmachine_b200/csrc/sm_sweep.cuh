@@ -125,6 +125,11 @@ struct __align__(32) WarpSmem {
   uint32_t blkxy[32];    // exact schedule: packed (ipos, reach) of entry l, as in the bin node
 };
 
+#ifndef SM_PREFETCH
+#define SM_PREFETCH 1
+#endif
+__device__ __forceinline__ float next_dy(const WaterP& p) { return p.sy; }   // speed component along map y
+__device__ __forceinline__ float next_dy(const WindP& p) { return p.sz; }
 template <class W, class A> __device__ __forceinline__ int do_step_coop(W& w, A& a, WaterP& p) { return water_step_coop(w, a, p); }
 template <class W, class A> __device__ __forceinline__ int do_step_coop(W& w, A& a, WindP& p) { return wind_step_coop(w, a, p); }
 
@@ -204,13 +209,17 @@ __device__ __forceinline__ void coop_wait(const DevCtx& c, unsigned int tag, uin
       remote = (bq != c.rank);      // polled over NVLink: system scope
     } else dp = &c.done[tgt];
   }
+  const bool had = !ok;
   for (;;) {
     if (!ok) {
-      const unsigned int v = remote ? ld_acquire_sys_u32(dp) : ld_acquire_u32(dp);
+      const unsigned int v = remote ? ld_relaxed_sys_u32(dp) : ld_relaxed_u32(dp);
       ok = v >= tag;
     }
     if (__all_sync(0xffffffffu, ok)) break;
+    poll_backoff();
   }
+  // acquire once: the word only grows, so this load reads a value >= tag and synchronises with its release
+  if (had) { if (remote) (void)ld_acquire_sys_u32(dp); else (void)ld_acquire_u32(dp); }
 }
 
 // ---- barrier across the blocks of every rank of a sharded map ---------------------------------------------
@@ -253,11 +262,13 @@ __device__ __forceinline__ unsigned int grid_barrier_x(const DevCtx& c, unsigned
     bool ok = !involved;
     for (;;) {
       if (!ok) {
-        const unsigned long long wv = ld_acquire_sys_u64(&ctl->xw[ge & 1u][lane]);
+        const unsigned long long wv = ld_relaxed_sys_u64(&ctl->xw[ge & 1u][lane]);
         if ((int)((unsigned int)(wv >> 32) - ge) >= 0) { ok = true; cnt = (unsigned int)wv; }
       }
       if (__all_sync(0xffffffffu, ok)) break;
+      poll_backoff();
     }
+    if (involved) (void)ld_acquire_sys_u64(&ctl->xw[ge & 1u][lane]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if (lane == 0) *s_total = cnt;
@@ -297,9 +308,10 @@ __device__ __forceinline__ int sweep_water_exact(const DevCtx& c, WarpSmem& ws, 
   int mx = 0, my = 0;
   bool moved = false;                                  // neighbour's npos known
   // ---- wait to move ----
+  bool acq = false;            // this lane's neighbour was resolved by its fin word: acquire it once after the loop
   for (;;) {
     if (need0) {
-      if (ld_acquire_u32(&c.fin[j]) >= tag) { need0 = false; need1 = false; }
+      if (ld_relaxed_u32(&c.fin[j]) >= tag) { need0 = false; need1 = false; acq = true; }
       else {
         const unsigned long long v = *((volatile unsigned long long*)&c.mv[j]);
         if ((unsigned int)(v >> 32) == tag) {
@@ -309,7 +321,9 @@ __device__ __forceinline__ int sweep_water_exact(const DevCtx& c, WarpSmem& ws, 
       }
     }
     if (!__any_sync(0xffffffffu, need0)) break;
+    poll_backoff();
   }
+  if (acq) { (void)ld_acquire_u32(&c.fin[j]); acq = false; }
   DevBack<MULTI, BUDGET> back(c, s_soils, tag);
   CoopWin<DevBack<MULTI, BUDGET> > a(back, &ws.cs);
   WaterMidCoop mid;
@@ -321,7 +335,7 @@ __device__ __forceinline__ int sweep_water_exact(const DevCtx& c, WarpSmem& ws, 
     // ---- wait to interact ----
     for (;;) {
       if (need1) {
-        if (ld_acquire_u32(&c.fin[j]) >= tag) need1 = false;
+        if (ld_relaxed_u32(&c.fin[j]) >= tag) { need1 = false; acq = true; }
         else {
           if (!moved) {
             const unsigned long long v = *((volatile unsigned long long*)&c.mv[j]);
@@ -333,7 +347,9 @@ __device__ __forceinline__ int sweep_water_exact(const DevCtx& c, WarpSmem& ws, 
         }
       }
       if (!__any_sync(0xffffffffu, need1)) break;
+      poll_backoff();
     }
+    if (acq) (void)ld_acquire_u32(&c.fin[j]);
     r = water_interact_coop(w, a, p, mid);
     a.flush(w);
   }
@@ -343,7 +359,8 @@ __device__ __forceinline__ int sweep_water_exact(const DevCtx& c, WarpSmem& ws, 
     // `done` in own-bin index order
     if (ownpred != SM_NIL) {
       const unsigned int* dp = MULTI ? &c.peer[ownpred >> 28].done[ownpred & 0x0FFFFFFFu] : &c.done[ownpred];
-      while (ld_acquire_u32(dp) < tag) { }
+      while (ld_relaxed_u32(dp) < tag) poll_backoff();
+      (void)ld_acquire_u32(dp);
     }
     const unsigned int pub = (r == SM_ALIVE) ? tag : 0xFFFFFFFFu;
     if (MULTI && edge) st_release_sys_u32(&c.done[pid], pub);
@@ -537,6 +554,19 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
           c.alive[pid] = 0;
         }
       }
+#if SM_PREFETCH
+      // next sweep's records towards L2 while this sweep finishes: the 3x3 blocks around the next ipos and around
+      // the position the current speed predicts after it (a wind particle covers fresh terrain every sweep; the
+      // map is 4x the L2)
+      if (r == SM_ALIVE && lane < 18) {
+        const int ox = lane < 9 ? jx : (int)roundf(p.px + p.sx);
+        const int oy = lane < 9 ? jy : (int)roundf(p.py + next_dy(p));
+        const int k = lane < 9 ? lane : lane - 9;
+        const int x = ox + k / 3 - 1, y = oy + k % 3 - 1;
+        if (x >= 0 && y >= 0 && x < c.dimx && y < c.dimy && (!MULTI || owner_of_x<MULTI>(c, x) == c.rank))
+          prefetch_l2(cell_ptr<MULTI>(c, x, y));
+      }
+#endif
       if (r == SM_ALIVE) { n_steps++; my_alive++; }
       else if (r == SM_EXIT_OOB) n_oob++;
       else if (r == SM_EXIT_STALL) n_stall++;
