@@ -85,7 +85,7 @@ int sm_sync(sm_context* ctx);
  * (x - x0)*dimy + y) and sm_*_run_device must be called on EVERY rank (the kernels meet in a cross-rank
  * barrier every sweep); results are bit-identical to the unsharded run.  share = number of contexts
  * that run their kernels concurrently on this device. */
-#define SM_PEER_ARRAYS 17
+#define SM_PEER_ARRAYS 20
 #define SM_PEER_SLOTS 24
 typedef struct sm_peer_blob {
   uint64_t ptr[SM_PEER_SLOTS];

@@ -68,6 +68,7 @@ struct PeerPtrs {
   uint2* node[2];
   double* bud;
   unsigned int* fin;
+  unsigned int* lmask[3];
 };
 
 struct DevCtx {
@@ -93,6 +94,7 @@ struct DevCtx {
   unsigned int* done;            // tag of the last sweep this particle completed (0xFFFFFFFF = dead)
   unsigned int* fin;             // exact kernel: tag of the last sweep whose map writes are complete
   unsigned long long* mv;        // exact kernel: tag<<32 | npos.x<<16 | npos.y, published right after move()
+  unsigned int* lmask[3];        // k_sweep: live-particle bit masks (bit pid), rotated by sweep number mod 3
   double* bud;                   // mass budget: SM_BUDGET_SLOTS f64 accumulators per particle (contexts created with SM_FLAG_BUDGET)
   unsigned long long* head[2];   // bin heads per sweep parity
   uint2* node[2];                // per particle: .x = next particle in the bin list, .y = ipos x<<16|y

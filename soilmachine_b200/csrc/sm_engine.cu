@@ -1371,6 +1371,7 @@ void sm_destroy(sm_context* ctx) {
   cudaFree(d.top); cudaFree(d.pool); cudaFree(d.ringbuf[0]); cudaFree(d.ringbuf[1]); cudaFree(d.ringbuf[2]);
   cudaFree(d.wfreq); cudaFree(d.wtrack); cudaFree(d.windfreq); cudaFree(ctx->d_soils);
   cudaFree(d.ctl); cudaFree(d.pa); cudaFree(d.pb); cudaFree(d.pc); cudaFree(d.alive); cudaFree(d.done); cudaFree(d.fin); cudaFree(d.mv); cudaFree(d.bud);
+  for (int i = 0; i < 3; i++) cudaFree(d.lmask[i]);
   for (int i = 0; i < 2; i++) { cudaFree(d.head[i]); cudaFree(d.node[i]); }
   cudaFree(ctx->d_verts); cudaFree(ctx->d_colors); cudaFree(d.dbg);
   cudaFree(ctx->d_act); cudaFree(ctx->d_hydro);
@@ -1452,6 +1453,10 @@ static int create_impl(const sm_config* cfg, int nranks, int rank, int share, sm
     CK(cudaMalloc(&d.pa, N * sizeof(float4))); CK(cudaMalloc(&d.pb, N * sizeof(double2)));
     CK(cudaMalloc(&d.pc, N * sizeof(uint2))); CK(cudaMalloc(&d.alive, N)); CK(cudaMalloc(&d.done, N * 4));
     CK(cudaMalloc(&d.fin, N * 4)); CK(cudaMalloc(&d.mv, N * 8));
+    for (int i = 0; i < 3; i++) {
+      CK(cudaMalloc(&d.lmask[i], (N / 32 + 2) * sizeof(unsigned int)));
+      CK(cudaMemsetAsync(d.lmask[i], 0, (N / 32 + 2) * sizeof(unsigned int), ctx->stream));
+    }
     if (cfg->flags & SM_FLAG_BUDGET) {
       CK(cudaMalloc(&d.bud, N * SM_BUDGET_SLOTS * sizeof(double)));
       CK(cudaMemsetAsync(d.bud, 0, N * SM_BUDGET_SLOTS * sizeof(double), ctx->stream));
@@ -1517,7 +1522,7 @@ static void own_ptrs(sm_context* ctx, void** p) {
   DevCtx& d = ctx->d;
   p[0] = d.top; p[1] = d.pool; p[2] = d.ringbuf[0]; p[3] = d.ringbuf[1]; p[4] = d.ctl; p[5] = d.pa; p[6] = d.pb;
   p[7] = d.pc; p[8] = d.alive; p[9] = d.done; p[10] = d.head[0]; p[11] = d.head[1]; p[12] = d.node[0]; p[13] = d.node[1];
-  p[14] = d.ringbuf[2]; p[15] = d.bud; p[16] = d.fin;
+  p[14] = d.ringbuf[2]; p[15] = d.bud; p[16] = d.fin; p[17] = d.lmask[0]; p[18] = d.lmask[1]; p[19] = d.lmask[2];
 }
 static void fill_peer(PeerPtrs& P, void* const* p, unsigned long long pool_cap) {
   P.top = (Sec32*)p[0]; P.pool = (Sec32*)p[1]; P.ringbuf[0] = (uint32_t*)p[2]; P.ringbuf[1] = (uint32_t*)p[3];
@@ -1525,6 +1530,7 @@ static void fill_peer(PeerPtrs& P, void* const* p, unsigned long long pool_cap) 
   P.alive = (unsigned char*)p[8]; P.done = (unsigned int*)p[9]; P.head[0] = (unsigned long long*)p[10];
   P.head[1] = (unsigned long long*)p[11]; P.node[0] = (uint2*)p[12]; P.node[1] = (uint2*)p[13];
   P.ringbuf[2] = (uint32_t*)p[14]; P.bud = (double*)p[15]; P.fin = (unsigned int*)p[16];
+  P.lmask[0] = (unsigned int*)p[17]; P.lmask[1] = (unsigned int*)p[18]; P.lmask[2] = (unsigned int*)p[19];
   P.pool_cap = pool_cap;
 }
 int sm_peer_export(sm_context* ctx, sm_peer_blob* out) {
@@ -1966,7 +1972,10 @@ static int launch_run(sm_context* ctx, int kind, int n, const float* d_spawn, in
                            (void*)k_sweep<KIND_WATER, false, true, true>,   (void*)k_sweep<KIND_WATER, true, true, true>};
     void* fn = exact ? fns[8 + (budget ? 2 : 0) + (multi ? 1 : 0)]
                      : fns[(budget ? 4 : 0) + (multi ? 2 : 0) + (kind == KIND_WATER ? 0 : 1)];
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)fn, cthreads, 0));
+    // dynamic shared memory: the live mask of the batch and its popcount prefix (2 x n/32 words per block)
+    const size_t csmem = (size_t)2 * (((size_t)std::max(n, 1) + 31) / 32) * sizeof(unsigned int);
+    if (csmem > 40 * 1024) CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)fn, cthreads, csmem));
     if (occ < 1) return fail(ctx, SM_ERR_CUDA, "sweep kernel does not fit an SM");
     // contexts that share the device must all be resident at once (they meet in the cross-rank barrier)
     const long long maxblocks = std::max<long long>(1, (long long)ctx->num_sms * occ / ctx->share);
@@ -1978,8 +1987,10 @@ static int launch_run(sm_context* ctx, int kind, int n, const float* d_spawn, in
     if (max_sweeps == SM_SWEEPS_NONE) ms = 0;
     void* cargs[] = {&dd, &n, (void*)&d_spawn, &ms};
     CK(cudaMemsetAsync(ctx->d.ctl, 0, 4 * sizeof(unsigned int), ctx->stream));  // barrier + alive_slot[3]
+    for (int i = 0; i < 3; i++)      // the kernel's prologue sets the bits of the live particles
+      CK(cudaMemsetAsync(ctx->d.lmask[i], 0, ((size_t)ctx->max_particles / 32 + 2) * sizeof(unsigned int), ctx->stream));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    CK(cudaLaunchCooperativeKernel(fn, dim3(cblocks), dim3(cthreads), cargs, 0, ctx->stream));
+    CK(cudaLaunchCooperativeKernel(fn, dim3(cblocks), dim3(cthreads), cargs, csmem, ctx->stream));
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->launches++;
     ctx->timing_pending = true;

@@ -370,13 +370,53 @@ __device__ __forceinline__ int sweep_water_exact(const DevCtx& c, WarpSmem& ws, 
   return r;
 }
 
+// Load the live mask (W words) into shared memory, build its exclusive popcount prefix, return the number of live
+// particles.  Called by every thread of the block; ends with a block barrier.
+template <int NWARPS>
+__device__ __forceinline__ unsigned int live_total(const unsigned int* __restrict__ mask, int W, unsigned int* s_word,
+                                                   unsigned int* s_pref, unsigned int* s_wsum) {
+  const int T = NWARPS * 32;
+  const int cw = (W + T - 1) / T;                       // contiguous words per thread
+  const int lo = threadIdx.x * cw, hi = (lo + cw < W) ? lo + cw : W;
+  unsigned int local = 0;
+  for (int i = lo; i < hi; i++) {
+    const unsigned int wd = ld_relaxed_u32(&mask[i]);
+    s_word[i] = wd;
+    local += (unsigned int)__popc(wd);
+  }
+  unsigned int incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((int)(threadIdx.x & 31) >= o) incl += v;
+  }
+  __syncthreads();                                      // previous users of s_wsum / s_pref are done
+  if ((threadIdx.x & 31) == 31) s_wsum[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  unsigned int base = 0, total = 0;
+#pragma unroll
+  for (int k = 0; k < NWARPS; k++) {
+    const unsigned int v = s_wsum[k];
+    if (k < (int)(threadIdx.x >> 5)) base += v;
+    total += v;
+  }
+  unsigned int run = base + incl - local;
+  for (int i = lo; i < hi; i++) { s_pref[i] = run; run += (unsigned int)__popc(s_word[i]); }
+  __syncthreads();
+  return total;
+}
+
 template <int KIND, bool MULTI, bool BUDGET, bool EXACT>
 __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(DevCtx c, int n, const float* __restrict__ spawn,
                                                                             int max_sweeps) {
   typedef typename PType<KIND>::T P;
   __shared__ SoilDev s_soils[SM_MAX_SOILS];
-  __shared__ unsigned int s_alive, s_total;
+  __shared__ unsigned int s_alive, s_total, s_wsum[SM_SW_WARPS];
   __shared__ WarpSmem s_w[SM_SW_WARPS];
+  extern __shared__ unsigned int s_live[];          // [0, W): this sweep's live mask, [W, 2W): exclusive popcount prefix
+  const int W = (n + 31) >> 5;
+  unsigned int* const s_word = s_live;
+  unsigned int* const s_pref = s_live + W;
   for (int i = threadIdx.x; i < c.nsoils; i += blockDim.x) s_soils[i] = c.soils[i];
   if (threadIdx.x == 0) s_alive = 0;
   __syncthreads();
@@ -431,12 +471,12 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
         if (BUDGET) for (int k = 0; k < SM_BUDGET_SLOTS; k++) c.bud[(size_t)pid * SM_BUDGET_SLOTS + k] = 0.0;
       } else {
         alive = c.alive[pid] != 0;
-        if (MULTI && alive) c.alive[pid] = 1;      // drop the arrival mark of a hand-over (see the sweep loop)
       }
       if (alive) {
         P q;
         load_particle(c, pid, q);
         bin_insert<KIND, MULTI>(c, tag0, pid, (int)roundf(q.px), (int)roundf(q.py), particle_reach(q), c.rank);
+        atomicOr(&c.lmask[tag0 % 3u][pid >> 5], 1u << (pid & 31));     // the masks were zeroed by the host
         my_alive++;
       }
     }
@@ -459,28 +499,36 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
   int s = 0;
   for (;; s++) {
     const unsigned int tag = tag0 + (unsigned int)s;
-    if (!MULTI) total_alive = ld_volatile_u32(&ctl->alive_slot[s % 3]);
-    if (max_sweeps >= 0 && s >= max_sweeps) break;
+    if (max_sweeps >= 0 && s >= max_sweeps) {
+      if (!MULTI) total_alive = live_total<SM_SW_WARPS>(c.lmask[tag % 3u], W, s_word, s_pref, s_wsum);
+      break;
+    }
+    // ---- who is alive, in index order ------------------------------------------------------------------------
+    // The live particles of this rank are the set bits of lmask[tag % 3] (written during the previous sweep,
+    // complete since the barrier).  Every block loads the mask and its exclusive popcount prefix into shared
+    // memory; the warp with grid-wide index g then runs the live particles of RANK g, g + nslots, g + 2 nslots, ...
+    // - ascending index within a warp (no wait can cycle), and every warp gets the same share whatever the pattern
+    // of deaths is.  (With a fixed particle -> warp map the warp holding the most survivors set the pace of the
+    // sweep: 5-6 of its 7 particles where the average is under 2.)
+    const unsigned int live = live_total<SM_SW_WARPS>(c.lmask[tag % 3u], W, s_word, s_pref, s_wsum);
+    if (!MULTI) total_alive = live;
     if ((!MULTI || xglobal) && total_alive == 0) break;
-    if (gtid == 0) st_volatile_u32(&ctl->alive_slot[(s + 2) % 3], 0u);
+    {   // the mask two sweeps ahead becomes the survivors' mask of the next sweep: clear it now
+      unsigned int* const z = c.lmask[(tag + 2u) % 3u];
+      for (int i = gtid; i < W; i += gridDim.x * blockDim.x) z[i] = 0u;
+    }
+    if (MULTI && gtid == 0) st_volatile_u32(&ctl->alive_slot[(s + 2) % 3], 0u);
 
     unsigned int my_alive = 0;
-    // This warp's particles are slot, slot + nslots, slot + 2 nslots, ... (ascending index within a warp: no wait
-    // can cycle).  Their alive flags are fetched 32 at a time, one per lane, so a warp whose particles are mostly
-    // dead pays one round trip per 32 of them instead of one each.
-    for (int base = 0; slot + (long long)base * nslots < n; base += 32) {
-    const long long lpid = slot + (long long)(base + lane) * nslots;
-    const unsigned int av_l = (lpid < n) ? (unsigned int)c.alive[lpid] : 0u;
-    // sharded map: a particle handed over during this very sweep carries the arrival mark 2 + parity of the
-    // sweep it arrived in; it has completed this sweep already and becomes runnable with the next one
-    // (the rank that handed it over counted it among the survivors of this sweep)
-    const bool run_l = av_l != 0u && !(MULTI && av_l >= 2u && (av_l - 2u) == (tag & 1u));
-    unsigned int todo = __ballot_sync(0xffffffffu, run_l);
-    while (todo) {
-      const int t = __ffs((int)todo) - 1;
-      todo &= todo - 1u;
-      const int pid = slot + (base + t) * nslots;
-      const unsigned int av = __shfl_sync(0xffffffffu, av_l, t);
+    {
+    for (unsigned int rank = (unsigned int)slot; rank < live; rank += (unsigned int)nslots) {
+      // rank -> particle: the word whose prefix range holds it, then the (rank - prefix)-th set bit of that word
+      int lo = 0, hi = W - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_pref[mid] <= rank) lo = mid; else hi = mid - 1;
+      }
+      const int pid = (lo << 5) + (int)__fns(s_word[lo], 0u, (int)(rank - s_pref[lo]) + 1);
       last_active = s;
       P p;
       load_particle(c, pid, p);
@@ -542,11 +590,12 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
             store_particle(o, pid, p);
             c.peer[nq].done[pid] = tag;            // it has completed this sweep, wherever it is asked
             if (EXACT) c.peer[nq].fin[pid] = tag;
-            c.peer[nq].alive[pid] = (unsigned char)(2u + (tag & 1u));
+            c.peer[nq].alive[pid] = 1;
             c.alive[pid] = 0;
+            atomicOr_system(&c.peer[nq].lmask[(tag + 1u) % 3u][pid >> 5], 1u << (pid & 31));   // runnable there next sweep
           } else {
             store_particle(c, pid, p);
-            if (MULTI && av != 1u) c.alive[pid] = 1;
+            atomicOr(&c.lmask[(tag + 1u) % 3u][pid >> 5], 1u << (pid & 31));
           }
           bin_insert<KIND, MULTI>(c, tag + 1u, pid, jx, jy, particle_reach(p), nq);
         } else {
@@ -574,11 +623,13 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
       __syncwarp();
     }
     }
-    if (lane == 0 && my_alive) atomicAdd(&s_alive, my_alive);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      if (s_alive) atomicAdd(&ctl->alive_slot[(s + 1) % 3], s_alive);
-      s_alive = 0;
+    if (MULTI) {     // the cross-rank barrier carries this rank's survivor count
+      if (lane == 0 && my_alive) atomicAdd(&s_alive, my_alive);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        if (s_alive) atomicAdd(&ctl->alive_slot[(s + 1) % 3], s_alive);
+        s_alive = 0;
+      }
     }
     if (MULTI) {
       xglobal = !xnb || ((s + 1) % SM_XSYNC_K == 0) || (max_sweeps >= 0 && s + 1 >= max_sweeps);
