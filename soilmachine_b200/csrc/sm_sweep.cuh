@@ -121,7 +121,7 @@ struct __align__(32) WarpSmem {
   uint32_t cnt;
   uint32_t m0;           // exact schedule: bit l = entry l can delay move() (its box can meet plus(ipos))
   uint32_t remote;       // exact schedule: some in-range lower-index particle is executed by another rank
-  uint32_t pad_;
+  uint32_t succ;         // a higher-index particle lives in the 3x3 bins: somebody may wait for this particle's hand-off
   uint32_t blkxy[32];    // exact schedule: packed (ipos, reach) of entry l, as in the bin node
 };
 
@@ -145,7 +145,7 @@ __device__ __forceinline__ uint32_t coop_scan(const DevCtx& c, WarpSmem& ws, int
   const unsigned int par = tag & 1u;
   const int G = Reach<KIND>::G;
   const int nbx = (c.dimx + G - 1) / G, nby = (c.dimy + G - 1) / G;
-  if (lane == 0) { ws.cnt = 0; if (EXACT) { ws.m0 = 0; ws.remote = 0; } }
+  if (lane == 0) { ws.cnt = 0; ws.succ = 0; if (EXACT) { ws.m0 = 0; ws.remote = 0; } }
   __syncwarp();
   if (lane < 9) {
     const int cx = ix / G + lane / 3 - 1, cy = iy / G + lane % 3 - 1;
@@ -160,6 +160,7 @@ __device__ __forceinline__ uint32_t coop_scan(const DevCtx& c, WarpSmem& ws, int
         uint32_t j = (uint32_t)h;
         while (j != SM_NIL) {
           const uint2 nd = nodes[j];
+          if (j > (uint32_t)pid) ws.succ = 1u;        // (same value from every lane that sees one)
           if (j < (uint32_t)pid) {
             if (best == SM_NIL || (j | qtag) > best) best = j | qtag;
             int dx = (int)(nd.y >> 18) - ix, dy = (int)((nd.y >> 4) & 0x3FFFu) - iy;
@@ -355,16 +356,21 @@ __device__ __forceinline__ int sweep_water_exact(const DevCtx& c, WarpSmem& ws, 
   }
   // stalled or left the map in move(): only track[] was written
   if (lane == 0) {
-    st_release_u32(&c.fin[pid], r == SM_ALIVE ? tag : 0xFFFFFFFFu);
-    // `done` in own-bin index order
-    if (ownpred != SM_NIL) {
-      const unsigned int* dp = MULTI ? &c.peer[ownpred >> 28].done[ownpred & 0x0FFFFFFFu] : &c.done[ownpred];
-      while (ld_relaxed_u32(dp) < tag) poll_backoff();
-      (void)ld_acquire_u32(dp);
-    }
     const unsigned int pub = (r == SM_ALIVE) ? tag : 0xFFFFFFFFu;
-    if (MULTI && edge) st_release_sys_u32(&c.done[pid], pub);
-    else st_release_u32(&c.done[pid], pub);
+    if (ws.succ) {
+      st_release_u32(&c.fin[pid], pub);
+      // `done` in own-bin index order
+      if (ownpred != SM_NIL) {
+        const unsigned int* dp = MULTI ? &c.peer[ownpred >> 28].done[ownpred & 0x0FFFFFFFu] : &c.done[ownpred];
+        while (ld_relaxed_u32(dp) < tag) poll_backoff();
+        (void)ld_acquire_u32(dp);
+      }
+      if (MULTI && edge) st_release_sys_u32(&c.done[pid], pub);
+      else st_release_u32(&c.done[pid], pub);
+    } else {             // no higher index in the 3x3 bins: nobody waits for fin or done (see the conservative path)
+      st_volatile_u32(&c.fin[pid], pub);
+      st_volatile_u32(&c.done[pid], pub);
+    }
   }
   __syncwarp();
   return r;
@@ -557,9 +563,17 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
         a.flush(w);
         if (lane == 0) {
           const unsigned int pub = (r == SM_ALIVE) ? tag : 0xFFFFFFFFu;
-          if (EXACT) st_release_u32(&c.fin[pid], pub);
-          if (MULTI && edge) st_release_sys_u32(&c.done[pid], pub);
-          else st_release_u32(&c.done[pid], pub);
+          if (ws.succ) {
+            if (EXACT) st_release_u32(&c.fin[pid], pub);
+            if (MULTI && edge) st_release_sys_u32(&c.done[pid], pub);
+            else st_release_u32(&c.done[pid], pub);
+          } else {
+            // Nobody can be waiting for this hand-off: a waiter lists particles of its own 3x3 bins, so it would
+            // sit in ours, and no higher index does.  The release fence (the single most expensive instruction of
+            // a step: it waits for every write-back to be acknowledged) is left to the sweep barrier.
+            if (EXACT) st_volatile_u32(&c.fin[pid], pub);
+            st_volatile_u32(&c.done[pid], pub);
+          }
         }
       }
       const int jx = (int)roundf(p.px), jy = (int)roundf(p.py);
