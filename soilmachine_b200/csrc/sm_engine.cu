@@ -60,7 +60,7 @@ __device__ __forceinline__ int particle_reach(const WindP& p) {
 #define SM_DEFAULT_EXACT 0             // warp kernel: exact footprints for water batches (flipped once measured)
 #endif
 #ifndef SM_DEFAULT_COOP
-#define SM_DEFAULT_COOP false          // flipped once k_sweep has passed the GPU parity suite
+#define SM_DEFAULT_COOP true           // k_sweep (warp per particle); SM_KERNEL=thread selects the round-1 kernels
 #endif
 #define SM_DONE_FLOODED 0xFFFFFFFEu  // done[] of a dead particle whose flood() has run (0xFFFFFFFF = dead)
 
@@ -2111,7 +2111,8 @@ static bool hydro_warp() {
   const char* e = getenv("SM_HYDRO");
   if (e && strcmp(e, "warp") == 0) return true;
   if (e && strcmp(e, "thread") == 0) return false;
-  return SM_DEFAULT_COOP;
+  return false;     // measured (profiles/r02_exp2_timing.log): without a record cache the warp executor's seep pass is
+                    // 2-4x slower than the one-thread executor with its shared-memory cache; flood 0.7-1.5x
 }
 static int hydro_ready(sm_context* ctx) {
   if (ctx->nsoils < 1) return fail(ctx, SM_ERR_INVALID, "soil table not set");
