@@ -50,6 +50,7 @@ struct RunCtl {
   // k_sweep's cross-rank barrier: xw[ge & 1][r] = (global epoch ge << 32) | live particles of rank r, written by
   // rank r into the copy of every rank it synchronises with at that epoch (its own included)
   unsigned long long xw[2][8];
+  unsigned int ticket[3];       // k_sweep: next unclaimed live-particle rank beyond the first nslots, by sweep number mod 3
 };
 
 // Pointers of one rank's arrays, as seen from this rank (own arrays, same-process contexts, or CUDA-IPC

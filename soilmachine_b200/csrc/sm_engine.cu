@@ -1987,6 +1987,7 @@ static int launch_run(sm_context* ctx, int kind, int n, const float* d_spawn, in
     if (max_sweeps == SM_SWEEPS_NONE) ms = 0;
     void* cargs[] = {&dd, &n, (void*)&d_spawn, &ms};
     CK(cudaMemsetAsync(ctx->d.ctl, 0, 4 * sizeof(unsigned int), ctx->stream));  // barrier + alive_slot[3]
+    CK(cudaMemsetAsync(&ctx->d.ctl->ticket[0], 0, 3 * sizeof(unsigned int), ctx->stream));
     for (int i = 0; i < 3; i++)      // the kernel's prologue sets the bits of the live particles
       CK(cudaMemsetAsync(ctx->d.lmask[i], 0, ((size_t)ctx->max_particles / 32 + 2) * sizeof(unsigned int), ctx->stream));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));

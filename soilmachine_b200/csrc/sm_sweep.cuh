@@ -523,11 +523,18 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
       unsigned int* const z = c.lmask[(tag + 2u) % 3u];
       for (int i = gtid; i < W; i += gridDim.x * blockDim.x) z[i] = 0u;
     }
-    if (MULTI && gtid == 0) st_volatile_u32(&ctl->alive_slot[(s + 2) % 3], 0u);
+    if (gtid == 0) {
+      if (MULTI) st_volatile_u32(&ctl->alive_slot[(s + 2) % 3], 0u);
+      st_volatile_u32(&ctl->ticket[(tag + 2u) % 3u], 0u);
+    }
 
     unsigned int my_alive = 0;
     {
-    for (unsigned int rank = (unsigned int)slot; rank < live; rank += (unsigned int)nslots) {
+    // Rank g belongs to warp g; the ranks beyond the first nslots are claimed one at a time, in order, by whichever
+    // warp is free (a warp stuck in a long step does not hold up the particles a fixed map would queue behind it).
+    // Ranks are handed out in ascending order and a holder only ever waits for lower ranks, which are done or held
+    // by a running warp: no wait can cycle.
+    for (unsigned int rank = (unsigned int)slot; rank < live;) {
       // rank -> particle: the word whose prefix range holds it, then the (rank - prefix)-th set bit of that word
       int lo = 0, hi = W - 1;
       while (lo < hi) {
@@ -635,6 +642,11 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
       else if (r == SM_EXIT_STALL) n_stall++;
       else { n_steps++; n_evap++; }
       __syncwarp();
+      // next rank: only when there are more live particles than warps
+      if (live <= (unsigned int)nslots) break;
+      unsigned int nr = 0;
+      if (lane == 0) nr = (unsigned int)nslots + atomicAdd(&ctl->ticket[tag % 3u], 1u);
+      rank = __shfl_sync(0xffffffffu, nr, 0);
     }
     }
     if (MULTI) {     // the cross-rank barrier carries this rank's survivor count
