@@ -1472,8 +1472,8 @@ static int create_impl(const sm_config* cfg, int nranks, int rank, int share, sm
     CK(cudaMalloc(&ctx->d_scratch, std::max(C, (size_t)SUM_BLOCKS + 8) * 8));
     CK(cudaMalloc(&ctx->d_iscratch, C * 4));
     CK(cudaMalloc(&ctx->d_cellres, sizeof(CellRes)));
-    CK(cudaMalloc(&d.dbg, 2 * 16384 * sizeof(unsigned long long)));
-    CK(cudaMemsetAsync(d.dbg, 0, 2 * 16384 * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMalloc(&d.dbg, 8 * 16384 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(d.dbg, 0, 8 * 16384 * sizeof(unsigned long long), ctx->stream));
     CK(cudaMallocHost(&ctx->h_ctl, sizeof(RunCtl)));
     // tags start at 1 so that zero-initialised bin heads never match
     RunCtl init; memset(&init, 0, sizeof(init)); init.tag_base = 2;
@@ -2485,6 +2485,15 @@ int sm_timer_stop(sm_context* ctx, double* elapsed_ms) {
 }
 int sm_launch_count(sm_context* ctx, int64_t* n) { *n = ctx->launches; return SM_OK; }
 // debug (only meaningful in a -DSM_PROFILE build): clock64() totals per phase, summed over particles
+// -DSM_PROFILE builds of k_sweep: 8 words per sweep - live particles, max step cycles, max wait cycles, max cycles a
+// warp spent on its particles, sum of step cycles, steps, globaltimer at the first warp's start, at the last warp's end
+int sm_debug_sweeps8(sm_context* ctx, uint64_t* out, int nsweeps) {
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(out, ctx->d.dbg, (size_t)std::min(nsweeps, 16384) * 64, cudaMemcpyDeviceToHost));
+  CK(cudaMemset(ctx->d.dbg, 0, 8 * 16384 * sizeof(unsigned long long)));
+  return SM_OK;
+}
 int sm_debug_sweeps(sm_context* ctx, uint64_t* out, int nsweeps) {   // -DSM_PROFILE builds: (clock64, alive) per sweep
   CK(cudaSetDevice(ctx->cfg.device));
   CK(cudaStreamSynchronize(ctx->stream));

@@ -529,6 +529,10 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
     }
 
     unsigned int my_alive = 0;
+#ifdef SM_PROFILE
+    unsigned long long prof_warp = 0;
+    if (gtid == 0 && s < 16384) c.dbg[8 * s + 0] = live;
+#endif
     {
     // Rank g belongs to warp g; the ranks beyond the first nslots are claimed one at a time, in order, by whichever
     // warp is free (a warp stuck in a long step does not hold up the particles a fixed map would queue behind it).
@@ -543,11 +547,22 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
       }
       const int pid = (lo << 5) + (int)__fns(s_word[lo], 0u, (int)(rank - s_pref[lo]) + 1);
       last_active = s;
+#ifdef SM_PROFILE
+      const long long pc0 = clock64();
+      if (lane == 0 && s < 16384) {
+        unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        atomicMax(&c.dbg[8 * s + 6], ~gt);             // max of the complement = earliest start
+      }
+#endif
       P p;
       load_particle(c, pid, p);
       const int ix = (int)roundf(p.px), iy = (int)roundf(p.py);
       const int myR = particle_reach(p);
       const uint32_t tgt = coop_scan<KIND, MULTI, EXACT>(c, ws, lane, tag, pid, ix, iy, myR);
+#ifdef SM_PROFILE
+      const long long pc1 = clock64();
+      long long pc2 = pc1;
+#endif
       // sharded map: only particles within two bins of a strip edge can have touched a peer's records or be polled
       // from another rank: they release at system scope, the interior ones at gpu scope
       bool edge = false;
@@ -563,6 +578,9 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
       }
       if (!exact_now) {
         coop_wait<MULTI>(c, tag, tgt);
+#ifdef SM_PROFILE
+        pc2 = clock64();
+#endif
         DevBack<MULTI, BUDGET> back(c, s_soils, tag);
         CoopWin<DevBack<MULTI, BUDGET> > a(back, &ws.cs);
         r = do_step_coop(w, a, p);
@@ -637,6 +655,18 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
           prefetch_l2(cell_ptr<MULTI>(c, x, y));
       }
 #endif
+#ifdef SM_PROFILE
+      {
+        const long long pc3 = clock64();
+        prof_warp += (unsigned long long)(pc3 - pc0);
+        if (lane == 0 && s < 16384) {
+          atomicMax(&c.dbg[8 * s + 1], (unsigned long long)(pc3 - pc2));
+          atomicMax(&c.dbg[8 * s + 2], (unsigned long long)(pc2 - pc1));
+          atomicAdd(&c.dbg[8 * s + 4], (unsigned long long)(pc3 - pc2));
+          atomicAdd(&c.dbg[8 * s + 5], 1ull);
+        }
+      }
+#endif
       if (r == SM_ALIVE) { n_steps++; my_alive++; }
       else if (r == SM_EXIT_OOB) n_oob++;
       else if (r == SM_EXIT_STALL) n_stall++;
@@ -649,6 +679,13 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
       rank = __shfl_sync(0xffffffffu, nr, 0);
     }
     }
+#ifdef SM_PROFILE
+    if (lane == 0 && s < 16384 && prof_warp) {
+      atomicMax(&c.dbg[8 * s + 3], prof_warp);
+      unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      atomicMax(&c.dbg[8 * s + 7], gt);
+    }
+#endif
     if (MULTI) {     // the cross-rank barrier carries this rank's survivor count
       if (lane == 0 && my_alive) atomicAdd(&s_alive, my_alive);
       __syncthreads();

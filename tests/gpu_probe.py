@@ -26,7 +26,7 @@ def run(soil, dim, nw, nd, lanes=None, iters=1, label=""):
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
-    if which in ("profile", "one", "mesh", "big", "tail", "poolrate", "sweepcurve") or which.startswith("cfg3:"): which = "none"
+    if which in ("profile", "one", "mesh", "big", "tail", "poolrate", "sweepcurve", "sweepstat") or which.startswith("cfg3:"): which = "none"
     if which in ("all", "single"):
         # single particles: sweep time = step latency (+ trivial barrier)
         run("rocksand", 1024, 1, 0, label="single")
@@ -202,3 +202,32 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1].startswith("hydr
     hydro()
     if sys.argv[1] == "hydro":
         hydro("default", 1024, 10000, 4)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "sweepstat":
+    # needs a -DSM_PROFILE build (SM_LIB_PATH): per-sweep statistics of the warp kernel's wind batch at config 3
+    import ctypes as C
+    from soilmachine_b200 import host
+    sim = host.Simulation("rockgravelpebblessand", seed=42, dimx=4096, dimy=4096, max_particles=25000)
+    xw = host.spawn_list(25000, 4096, 4096); xd = host.spawn_list(25000, 4096, 4096)
+    for kind, xy in (("water", xw), ("wind", xd)):
+        buf = np.zeros((16384, 8), np.uint64)
+        sim.ctx.lib.sm_debug_sweeps8(sim.ctx.h, buf.ctypes.data_as(C.c_void_p), 16384)      # clear
+        g = sim.ctx.water_run(xy) if kind == "water" else sim.ctx.wind_run(xy)
+        n = min(int(g.sweeps), 16384)
+        sim.ctx.lib.sm_debug_sweeps8(sim.ctx.h, buf.ctypes.data_as(C.c_void_p), n)
+        b = buf[:n].astype(np.float64)
+        live, mxstep, mxwait, mxwarp, sumstep, nstep = b[:, 0], b[:, 1], b[:, 2], b[:, 3], b[:, 4], b[:, 5]
+        t0 = (~buf[:n, 6]).astype(np.float64); t1 = b[:, 7]
+        span = (t1 - t0) / 1e3                                  # us between the first warp's start and the last warp's end
+        period = np.diff(t0) / 1e3                              # us from sweep to sweep
+        cyc = 1.965e3
+        print("%s: sweeps=%d ms=%.1f  us/sweep=%.2f" % (kind, g.sweeps, g.device_ms, g.device_ms * 1e3 / g.sweeps))
+        print("  avg step %.2f us, avg of per-sweep max step %.2f us, avg max wait %.2f us, avg max warp busy %.2f us, avg span %.2f us, avg period %.2f us"
+              % (sumstep.sum() / nstep.sum() / cyc, mxstep.mean() / cyc, mxwait.mean() / cyc, mxwarp.mean() / cyc, span.mean(), period.mean()))
+        for lo in range(0, n - 1, max(n // 14, 1)):
+            hi = min(lo + max(n // 14, 1), n - 1)
+            sl = slice(lo, hi)
+            print("  sweeps %5d-%5d live %6d: period %.1f us | span %.1f | max warp busy %.1f | max step %.1f | avg step %.2f | max wait %.1f | trips %.2f"
+                  % (lo, hi, live[sl].mean(), period[sl].mean(), span[sl].mean(), mxwarp[sl].mean() / cyc, mxstep[sl].mean() / cyc,
+                     sumstep[sl].sum() / max(nstep[sl].sum(), 1) / cyc, mxwait[sl].mean() / cyc, np.ceil(live[sl] / 3552).mean()), flush=True)
