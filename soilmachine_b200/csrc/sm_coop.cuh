@@ -443,19 +443,25 @@ template <class W, class A> SM_HD int water_step_coop(W& w, A& a, WaterP& p, uin
 // ------------------------------------------------------------------------------------------------
 // WindParticle::move && interact, wind.h:54-136
 // ------------------------------------------------------------------------------------------------
-template <class W, class A> SM_HD int wind_step_coop(W& w, A& a, WindP& p) {
+// What WindParticle::move hands to interact() of the same step.
+struct WindMidCoop {
+  float suspension;      // param.suspension of the surface at ipos
+  uint32_t transports;   // param.transports
+  int ix, iy;
+};
+// WindParticle::move, wind.h:54-92.  `amask`: cells of the 3x3 block around ipos staged now (see CoopWin::begin).
+template <class W, class A> SM_HD int wind_move_coop(W& w, A& a, WindP& p, WindMidCoop& m, uint32_t amask = 0x1FFu) {
   const int dimx = a.dimx(), dimy = a.dimy();
   const int SCALE = a.scale();
   if (A::kBudget && w.lead()) { for (int k = 0; k < SM_BUDGET_SLOTS; k++) a.s->acc[k] = 0.0; }
   // ---- move ----
   if (a.soil(p.contains).suspension == 0.0) return SM_EXIT_OOB;     // :56-57
   const int ix = (int)roundf(p.px), iy = (int)roundf(p.py);         // :60
-  a.begin(w, ix, iy, 1);
+  a.begin(w, ix, iy, 1, amask);
   const sm_f3 n = map_normal(a, ix, iy);                            // :61
   Sec32* const ir = a.rec(ix, iy);
   const SoilDev& param = a.soil(rec_surface(*ir));                  // :62-63
-  const float suspension = param.suspension;
-  const uint32_t transports = param.transports;
+  m.suspension = param.suspension; m.transports = param.transports; m.ix = ix; m.iy = iy;
   if (w.lead()) a.b.set_windfreq(iy * dimx + ix, (float)(0.5 * a.f_freq + 0.5f));   // :64, 49-52
   const double sheight = rec_height(*ir) * (float)SCALE / 80.0f;    // :67
   if (p.height < sheight) p.height = sheight;                       // :68-70
@@ -488,7 +494,16 @@ template <class W, class A> SM_HD int wind_step_coop(W& w, A& a, WindP& p) {
     if (A::kBudget && w.lead()) a.s->acc[3] += p.sediment;
     return SM_EXIT_OOB;
   }
-  // ---- interact (always returns true upstream) ----
+  return SM_ALIVE;
+}
+// WindParticle::interact, wind.h:94-136 (always returns true upstream)
+template <class W, class A> SM_HD int wind_interact_coop(W& w, A& a, WindP& p, const WindMidCoop& m) {
+  const int SCALE = a.scale();
+  const int ix = m.ix, iy = m.iy;
+  const float suspension = m.suspension;
+  const uint32_t transports = m.transports;
+  a.fetch_a(w, 0x1FFu);                                             // the cascade around ipos needs the whole block
+  Sec32* const ir = a.rec(ix, iy);
   const int nx = (int)roundf(p.px), ny = (int)roundf(p.py);         // :99
   a.target(w, nx, ny);
   int ncascade = 0;
@@ -531,4 +546,11 @@ template <class W, class A> SM_HD int wind_step_coop(W& w, A& a, WindP& p) {
   for (int q = 0; q < ncascade; q++)                                // one call site for both
     CascadeCoop<1, W, A>::run(w, a, q == 0 ? ix : nx, q == 0 ? iy : ny, 1);
   return SM_ALIVE;
+}
+// one move() && interact()
+template <class W, class A> SM_HD int wind_step_coop(W& w, A& a, WindP& p, uint32_t amask = 0x1FFu) {
+  WindMidCoop m;
+  const int r = wind_move_coop(w, a, p, m, amask);
+  if (r != SM_ALIVE) return r;
+  return wind_interact_coop(w, a, p, m);
 }

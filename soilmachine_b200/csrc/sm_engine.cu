@@ -1958,20 +1958,21 @@ static int launch_run(sm_context* ctx, int kind, int n, const float* d_spawn, in
     const int cthreads = SM_SW_WARPS * 32;
     int occ = 0;
     const bool budget = ctx->d.bud != nullptr;
-    // SM_EXACT: bit 0 = water batches use exact footprints (sweep_water_exact); wind keeps the conservative rule
+    // SM_EXACT: bit mask of the kinds that use exact footprints (sweep_exact): 1 = water, 2 = wind
     bool exact = false;
     {
       const char* e = getenv("SM_EXACT");
-      exact = (kind == KIND_WATER) && ((e ? atoi(e) : SM_DEFAULT_EXACT) & 1);
+      exact = (((e ? atoi(e) : SM_DEFAULT_EXACT) >> kind) & 1) != 0;
     }
-    void* const fns[12] = {(void*)k_sweep<KIND_WATER, false, false, false>, (void*)k_sweep<KIND_WIND, false, false, false>,
+    void* const fns[16] = {(void*)k_sweep<KIND_WATER, false, false, false>, (void*)k_sweep<KIND_WIND, false, false, false>,
                            (void*)k_sweep<KIND_WATER, true, false, false>,  (void*)k_sweep<KIND_WIND, true, false, false>,
                            (void*)k_sweep<KIND_WATER, false, true, false>,  (void*)k_sweep<KIND_WIND, false, true, false>,
                            (void*)k_sweep<KIND_WATER, true, true, false>,   (void*)k_sweep<KIND_WIND, true, true, false>,
-                           (void*)k_sweep<KIND_WATER, false, false, true>,  (void*)k_sweep<KIND_WATER, true, false, true>,
-                           (void*)k_sweep<KIND_WATER, false, true, true>,   (void*)k_sweep<KIND_WATER, true, true, true>};
-    void* fn = exact ? fns[8 + (budget ? 2 : 0) + (multi ? 1 : 0)]
-                     : fns[(budget ? 4 : 0) + (multi ? 2 : 0) + (kind == KIND_WATER ? 0 : 1)];
+                           (void*)k_sweep<KIND_WATER, false, false, true>,  (void*)k_sweep<KIND_WIND, false, false, true>,
+                           (void*)k_sweep<KIND_WATER, true, false, true>,   (void*)k_sweep<KIND_WIND, true, false, true>,
+                           (void*)k_sweep<KIND_WATER, false, true, true>,   (void*)k_sweep<KIND_WIND, false, true, true>,
+                           (void*)k_sweep<KIND_WATER, true, true, true>,    (void*)k_sweep<KIND_WIND, true, true, true>};
+    void* fn = fns[(exact ? 8 : 0) + (budget ? 4 : 0) + (multi ? 2 : 0) + (kind == KIND_WATER ? 0 : 1)];
     // dynamic shared memory: the live mask of the batch and its popcount prefix (2 x n/32 words per block)
     const size_t csmem = (size_t)2 * (((size_t)std::max(n, 1) + 31) / 32) * sizeof(unsigned int);
     if (csmem > 40 * 1024) CK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));

@@ -278,9 +278,12 @@ __device__ __forceinline__ unsigned int grid_barrier_x(const DevCtx& c, unsigned
   return *s_total;
 }
 
-// ---- exact footprints (water) ----------------------------------------------------------------------------------
-// The conservative rule orders two steps whenever their boxes (ipos +- 3) overlap, but a water step really touches
-// F = plus(ipos) U 3x3(npos) - about 14 of the 49 cells - and npos is only known after move().  With EXACT a
+// ---- exact footprints ------------------------------------------------------------------------------------------
+// The conservative rule orders two steps whenever their boxes (ipos +- R, R = 3 water, 3..5 wind) overlap, but a
+// water step really touches F = plus(ipos) U 3x3(npos) - about 14 of the 49 cells - and a wind step
+// plus(ipos) U 5x5(ipos) U 5x5(npos) (cascades around both cells with one nested re-cascade) out of up to 121; npos
+// is only known after move().  The per-sweep statistics (profiles/r02_sweepstat.log) show what that costs: in every
+// wind sweep some particle waits ~17 us for a chain of 2-3 boxes that overlap while the footprints do not.  With EXACT a
 // particle publishes three words per sweep: mv (= npos, right after move(); it only lets others SKIP a wait, so it
 // needs no fence), fin (its map writes are complete; release) and done (published in own-bin index order, which
 // keeps "X done => every lower index in X's bin done" and with it the crowded fallback sound).  A lower-index
@@ -292,10 +295,17 @@ __device__ __forceinline__ unsigned int grid_barrier_x(const DevCtx& c, unsigned
 // than SM_SW_NEAR neighbours in range, or (sharded maps) with a neighbour executed by another rank, take the
 // conservative path for that sweep - waiting for `done` is always sufficient.
 // Returns the step's result; fin and done are published inside.
-template <bool MULTI, bool BUDGET>
-__device__ __forceinline__ int sweep_water_exact(const DevCtx& c, WarpSmem& ws, WarpDev& w, const SoilDev* s_soils,
-                                                 unsigned int tag, int pid, int ix, int iy, int myR, WaterP& p,
-                                                 bool edge) {
+template <class W, class A> __device__ __forceinline__ int do_move_coop(W& w, A& a, WaterP& p, WaterMidCoop& m) { return water_move_coop(w, a, p, m, SM_CW_PLUS); }
+template <class W, class A> __device__ __forceinline__ int do_move_coop(W& w, A& a, WindP& p, WindMidCoop& m) { return wind_move_coop(w, a, p, m, SM_CW_PLUS); }
+template <class W, class A> __device__ __forceinline__ int do_interact_coop(W& w, A& a, WaterP& p, const WaterMidCoop& m) { return water_interact_coop(w, a, p, m); }
+template <class W, class A> __device__ __forceinline__ int do_interact_coop(W& w, A& a, WindP& p, const WindMidCoop& m) { return wind_interact_coop(w, a, p, m); }
+template <int KIND> struct MidCoopType { typedef WaterMidCoop T; };
+template <> struct MidCoopType<KIND_WIND> { typedef WindMidCoop T; };
+
+template <int KIND, bool MULTI, bool BUDGET>
+__device__ __forceinline__ int sweep_exact(const DevCtx& c, WarpSmem& ws, WarpDev& w, const SoilDev* s_soils,
+                                           unsigned int tag, int pid, int ix, int iy, int myR,
+                                           typename PType<KIND>::T& p, bool edge) {
   const int lane = w.lane;
   const unsigned int cnt = ws.cnt;
   const uint32_t ownpred = ws.pred[4];
@@ -317,7 +327,7 @@ __device__ __forceinline__ int sweep_water_exact(const DevCtx& c, WarpSmem& ws, 
         const unsigned long long v = *((volatile unsigned long long*)&c.mv[j]);
         if ((unsigned int)(v >> 32) == tag) {
           mx = (int)((v >> 16) & 0xFFFFu); my = (int)(v & 0xFFFFu); moved = true;
-          if (!Foot<KIND_WATER>::W_hits_M(jx, jy, mx, my, ix, iy)) need0 = false;
+          if (!Foot<KIND>::W_hits_M(jx, jy, mx, my, ix, iy)) need0 = false;
         }
       }
     }
@@ -327,8 +337,8 @@ __device__ __forceinline__ int sweep_water_exact(const DevCtx& c, WarpSmem& ws, 
   if (acq) { (void)ld_acquire_u32(&c.fin[j]); acq = false; }
   DevBack<MULTI, BUDGET> back(c, s_soils, tag);
   CoopWin<DevBack<MULTI, BUDGET> > a(back, &ws.cs);
-  WaterMidCoop mid;
-  int r = water_move_coop(w, a, p, mid, SM_CW_PLUS);
+  typename MidCoopType<KIND>::T mid;
+  int r = do_move_coop(w, a, p, mid);
   if (r == SM_ALIVE) {
     const int nx = (int)roundf(p.px), ny = (int)roundf(p.py);
     if (lane == 0)
@@ -342,8 +352,8 @@ __device__ __forceinline__ int sweep_water_exact(const DevCtx& c, WarpSmem& ws, 
             const unsigned long long v = *((volatile unsigned long long*)&c.mv[j]);
             if ((unsigned int)(v >> 32) == tag) { mx = (int)((v >> 16) & 0xFFFFu); my = (int)(v & 0xFFFFu); moved = true; }
           }
-          const bool hit = moved ? Foot<KIND_WATER>::F_hits_F(ix, iy, nx, ny, jx, jy, mx, my)
-                                 : Foot<KIND_WATER>::box_hits_F(ix, iy, nx, ny, jx, jy, jR);
+          const bool hit = moved ? Foot<KIND>::F_hits_F(ix, iy, nx, ny, jx, jy, mx, my)
+                                 : Foot<KIND>::box_hits_F(ix, iy, nx, ny, jx, jy, jR);
           if (!hit) need1 = false;
         }
       }
@@ -351,7 +361,7 @@ __device__ __forceinline__ int sweep_water_exact(const DevCtx& c, WarpSmem& ws, 
       poll_backoff();
     }
     if (acq) (void)ld_acquire_u32(&c.fin[j]);
-    r = water_interact_coop(w, a, p, mid);
+    r = do_interact_coop(w, a, p, mid);
     a.flush(w);
   }
   // stalled or left the map in move(): only track[] was written
@@ -572,9 +582,9 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
       }
       int r = SM_ALIVE;
       bool exact_now = false;
-      if constexpr (EXACT && KIND == KIND_WATER) {
+      if constexpr (EXACT) {
         exact_now = ws.cnt <= SM_SW_NEAR && !(MULTI && ws.remote);
-        if (exact_now) r = sweep_water_exact<MULTI, BUDGET>(c, ws, w, s_soils, tag, pid, ix, iy, myR, p, edge);
+        if (exact_now) r = sweep_exact<KIND, MULTI, BUDGET>(c, ws, w, s_soils, tag, pid, ix, iy, myR, p, edge);
       }
       if (!exact_now) {
         coop_wait<MULTI>(c, tag, tgt);

@@ -232,7 +232,7 @@ int hs_wind_sweep(Stats* st) {
     int r;
     if (G_coop) {
       WarpHost w; HostBack b; CoopScratch sc; CoopWin<HostBack> cw(b, &sc);
-      r = wind_step_coop(w, cw, D[i]);
+      r = wind_step_coop(w, cw, D[i], G_coop == 2 ? SM_CW_PLUS : 0x1FFu);
       cw.flush(w);
       for (int k = 0; k < SM_BUDGET_SLOTS; k++) BUD[(size_t)i * SM_BUDGET_SLOTS + k] += sc.acc[k];
     } else r = wind_step(a, D[i]);
