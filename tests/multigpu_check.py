@@ -20,6 +20,25 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from soilmachine_b200 import capi, presets, host, sharded  # noqa: E402
 
 
+def _sweepstat(ctx, g, kind, rank, reset_only=False):
+    """-DSM_PROFILE builds (SM_LIB_PATH): per-sweep statistics of this rank's sweep kernel"""
+    import ctypes as C
+    buf = np.zeros((16384, 8), np.uint64)
+    n = min(int(g.sweeps), 16384)
+    ctx.lib.sm_debug_sweeps8(ctx.h, buf.ctypes.data_as(C.c_void_p), max(n, 1))
+    if reset_only or n < 2:
+        return
+    b = buf[:n].astype(np.float64)
+    t0 = (~buf[:n, 6]).astype(np.float64)
+    ok = buf[:n, 6] != 0
+    cyc = 1.965e3
+    period = np.diff(t0[ok]) / 1e3 if ok.sum() > 2 else np.zeros(1)
+    span = (b[ok, 7] - t0[ok]) / 1e3
+    print("rank %d %s: sweeps=%d ms=%.1f | live/rank avg %.0f | avg step %.2f us, max step %.1f, max wait %.1f, max warp busy %.1f, span %.1f, period(active sweeps) %.1f"
+          % (rank, kind, g.sweeps, g.device_ms, b[:, 0].mean(), b[:, 4].sum() / max(b[:, 5].sum(), 1) / cyc, b[:, 1].mean() / cyc,
+             b[:, 2].mean() / cyc, b[:, 3].mean() / cyc, span.mean(), np.median(period)), flush=True)
+
+
 def main():
     dim = int(sys.argv[1]) if len(sys.argv) > 1 else 512
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 4000
@@ -46,7 +65,11 @@ def main():
         dw, dd = sh.ctx.device_spawn(xw), sh.ctx.device_spawn(xd)
         dist.barrier()
         a = sh.run("water", dw, n)
+        if os.environ.get("SM_SWEEPSTAT") == "1":
+            _sweepstat(sh.ctx, a, "water", rank, reset_only=True)
         b = sh.run("wind", dd, n)
+        if os.environ.get("SM_SWEEPSTAT") == "1":
+            _sweepstat(sh.ctx, b, "wind", rank)
         sh.ctx.frequency_update()
         tot += [a.steps, b.steps, a.exit_oob + a.exit_evap + a.exit_stall, b.exit_oob]
         t_ms += a.device_ms + b.device_ms
