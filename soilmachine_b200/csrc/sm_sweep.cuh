@@ -299,6 +299,8 @@ template <class W, class A> __device__ __forceinline__ int do_move_coop(W& w, A&
 template <class W, class A> __device__ __forceinline__ int do_move_coop(W& w, A& a, WindP& p, WindMidCoop& m) { return wind_move_coop(w, a, p, m, SM_CW_PLUS); }
 template <class W, class A> __device__ __forceinline__ int do_interact_coop(W& w, A& a, WaterP& p, const WaterMidCoop& m) { return water_interact_coop(w, a, p, m); }
 template <class W, class A> __device__ __forceinline__ int do_interact_coop(W& w, A& a, WindP& p, const WindMidCoop& m) { return wind_interact_coop(w, a, p, m); }
+template <class W, class A> __device__ __forceinline__ int do_move_coop_full(W& w, A& a, WaterP& p, WaterMidCoop& m) { return water_move_coop(w, a, p, m, 0x1FFu); }
+template <class W, class A> __device__ __forceinline__ int do_move_coop_full(W& w, A& a, WindP& p, WindMidCoop& m) { return wind_move_coop(w, a, p, m, 0x1FFu); }
 template <int KIND> struct MidCoopType { typedef WaterMidCoop T; };
 template <> struct MidCoopType<KIND_WIND> { typedef WindMidCoop T; };
 
@@ -541,7 +543,7 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
     unsigned int my_alive = 0;
 #ifdef SM_PROFILE
     unsigned long long prof_warp = 0;
-    if (gtid == 0 && s < 16384) c.dbg[8 * s + 0] = live;
+    if (gtid == 0 && s < 16380) c.dbg[8 * s + 0] = live;
 #endif
     {
     // Rank g belongs to warp g; the ranks beyond the first nslots are claimed one at a time, in order, by whichever
@@ -559,7 +561,7 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
       last_active = s;
 #ifdef SM_PROFILE
       const long long pc0 = clock64();
-      if (lane == 0 && s < 16384) {
+      if (lane == 0 && s < 16380) {
         unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         atomicMax(&c.dbg[8 * s + 6], ~gt);             // max of the complement = earliest start
       }
@@ -593,7 +595,18 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
 #endif
         DevBack<MULTI, BUDGET> back(c, s_soils, tag);
         CoopWin<DevBack<MULTI, BUDGET> > a(back, &ws.cs);
+#ifdef SM_PROFILE
+        long long pcm, pci;
+        {
+          typename MidCoopType<KIND>::T mid;
+          r = do_move_coop_full(w, a, p, mid);
+          pcm = clock64();
+          if (r == SM_ALIVE) r = do_interact_coop(w, a, p, mid);
+          pci = clock64();
+        }
+#else
         r = do_step_coop(w, a, p);
+#endif
         // hand-off first: the map writes are all the successors of this step wait for
         a.flush(w);
         if (lane == 0) {
@@ -610,6 +623,19 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
             st_volatile_u32(&c.done[pid], pub);
           }
         }
+#ifdef SM_PROFILE
+        if (lane == 0) {   // phase sums of the conservative path, row 16383 of the debug buffer
+          const long long pcp = clock64();
+          unsigned long long* const ph = c.dbg + 8 * 16383;
+          atomicAdd(&ph[0], (unsigned long long)(pc1 - pc0));
+          atomicAdd(&ph[1], (unsigned long long)(pc2 - pc1));
+          atomicAdd(&ph[2], (unsigned long long)(pcm - pc2));
+          atomicAdd(&ph[3], (unsigned long long)(pci - pcm));
+          atomicAdd(&ph[4], (unsigned long long)(pcp - pci));
+          atomicAdd(&ph[5], 1ull);
+          if (ws.succ) { atomicAdd(&ph[6], (unsigned long long)(pcp - pci)); atomicAdd(&ph[7], 1ull); }
+        }
+#endif
       }
       const int jx = (int)roundf(p.px), jy = (int)roundf(p.py);
       if (lane == 0) {
@@ -669,7 +695,7 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
       {
         const long long pc3 = clock64();
         prof_warp += (unsigned long long)(pc3 - pc0);
-        if (lane == 0 && s < 16384) {
+        if (lane == 0 && s < 16380) {
           atomicMax(&c.dbg[8 * s + 1], (unsigned long long)(pc3 - pc2));
           atomicMax(&c.dbg[8 * s + 2], (unsigned long long)(pc2 - pc1));
           atomicAdd(&c.dbg[8 * s + 4], (unsigned long long)(pc3 - pc2));
@@ -690,7 +716,7 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
     }
     }
 #ifdef SM_PROFILE
-    if (lane == 0 && s < 16384 && prof_warp) {
+    if (lane == 0 && s < 16380 && prof_warp) {
       atomicMax(&c.dbg[8 * s + 3], prof_warp);
       unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
       atomicMax(&c.dbg[8 * s + 7], gt);

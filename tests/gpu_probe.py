@@ -214,8 +214,13 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "sweepstat":
         buf = np.zeros((16384, 8), np.uint64)
         sim.ctx.lib.sm_debug_sweeps8(sim.ctx.h, buf.ctypes.data_as(C.c_void_p), 16384)      # clear
         g = sim.ctx.water_run(xy) if kind == "water" else sim.ctx.wind_run(xy)
-        n = min(int(g.sweeps), 16384)
-        sim.ctx.lib.sm_debug_sweeps8(sim.ctx.h, buf.ctypes.data_as(C.c_void_p), n)
+        n = min(int(g.sweeps), 16380)
+        sim.ctx.lib.sm_debug_sweeps8(sim.ctx.h, buf.ctypes.data_as(C.c_void_p), 16384)
+        ph = buf[16383].astype(np.float64)
+        if ph[5] > 0:
+            k = 1.0 / ph[5] / 1.965e3
+            print("%s phases (us per step, conservative path, %d steps): load+scan %.2f | wait %.2f | fetch+move %.2f | interact %.2f | flush+publish %.2f (with a release fence: %.2f over %d steps)"
+                  % (kind, ph[5], ph[0] * k, ph[1] * k, ph[2] * k, ph[3] * k, ph[4] * k, ph[6] / max(ph[7], 1) / 1.965e3, ph[7]))
         b = buf[:n].astype(np.float64)
         live, mxstep, mxwait, mxwarp, sumstep, nstep = b[:, 0], b[:, 1], b[:, 2], b[:, 3], b[:, 4], b[:, 5]
         t0 = (~buf[:n, 6]).astype(np.float64); t1 = b[:, 7]
