@@ -21,6 +21,8 @@
 #define SM_SW_MINBLOCKS 3    // resident blocks per SM the kernel is compiled for (register cap)
 #endif
 #define SM_SW_NEAR 31        // in-range lower-index particles tracked exactly (one polling lane each)
+#define SM_SW_NEARX 128      // ... by the exact schedule, which polls them in rounds of 32 (dense clusters - water
+                             // collecting in a pit - are where exact footprints pay most: scripts/chain_analysis.py)
 
 // warp policy of sm_coop.cuh on the device.  Every primitive is a full-warp synchronisation point on both
 // sides: __syncwarp() orders the memory accesses of the participating lanes, so what lanes wrote before a
@@ -116,13 +118,14 @@ template <bool MULTI, bool BUDGET = false> struct DevBack {
 
 struct __align__(32) WarpSmem {
   CoopScratch cs;
-  uint32_t blk[32];      // in-range lower-index particles of this sweep (rank in bits 28-31 on a sharded map)
+  uint32_t blk[SM_SW_NEARX];   // in-range lower-index particles of this sweep (rank in bits 28-31 on a sharded map)
   uint32_t pred[12];     // per-bin predecessors (largest lower index in each of the 3x3 bins)
   uint32_t cnt;
-  uint32_t m0;           // exact schedule: bit l = entry l can delay move() (its box can meet plus(ipos))
+  uint32_t m0[SM_SW_NEARX / 32];   // exact schedule: bit l = entry l can delay move() (its box can meet plus(ipos))
+  uint32_t n1[SM_SW_NEARX / 32];   // exact schedule: bit l = entry l still unresolved after the wait to move
   uint32_t remote;       // exact schedule: some in-range lower-index particle is executed by another rank
   uint32_t succ;         // a higher-index particle lives in the 3x3 bins: somebody may wait for this particle's hand-off
-  uint32_t blkxy[32];    // exact schedule: packed (ipos, reach) of entry l, as in the bin node
+  uint32_t blkxy[SM_SW_NEARX];   // exact schedule: packed (ipos, reach) of entry l, as in the bin node
 };
 
 #ifndef SM_PREFETCH
@@ -145,7 +148,8 @@ __device__ __forceinline__ uint32_t coop_scan(const DevCtx& c, WarpSmem& ws, int
   const unsigned int par = tag & 1u;
   const int G = Reach<KIND>::G;
   const int nbx = (c.dimx + G - 1) / G, nby = (c.dimy + G - 1) / G;
-  if (lane == 0) { ws.cnt = 0; ws.succ = 0; if (EXACT) { ws.m0 = 0; ws.remote = 0; } }
+  if (lane == 0) { ws.cnt = 0; ws.succ = 0; if (EXACT) ws.remote = 0; }
+  if (EXACT && lane < SM_SW_NEARX / 32) ws.m0[lane] = 0;
   __syncwarp();
   if (lane < 9) {
     const int cx = ix / G + lane / 3 - 1, cy = iy / G + lane % 3 - 1;
@@ -169,13 +173,13 @@ __device__ __forceinline__ uint32_t coop_scan(const DevCtx& c, WarpSmem& ws, int
             dy = dy < 0 ? -dy : dy;
             if (dx <= D && dy <= D) {
               const unsigned int at = atomicAdd(&ws.cnt, 1u);
-              if (at < SM_SW_NEAR) {
+              if (at < (EXACT ? SM_SW_NEARX : SM_SW_NEAR)) {
                 ws.blk[at] = j | qtag;
                 if (EXACT) {
                   ws.blkxy[at] = nd.y;
                   // static pruning: a neighbour whose box cannot meet plus(ipos) never delays the move
                   if (Foot<KIND>::box_hits_M((int)(nd.y >> 18) - ix, (int)((nd.y >> 4) & 0x3FFFu) - iy, (int)(nd.y & 0xFu)))
-                    atomicOr(&ws.m0, 1u << at);
+                    atomicOr(&ws.m0[at >> 5], 1u << (at & 31u));
                   if (MULTI && bq != c.rank) ws.remote = 1u;
                 }
               }
@@ -292,7 +296,7 @@ __device__ __forceinline__ unsigned int grid_barrier_x(const DevCtx& c, unsigned
 //                       (B not moved yet: while B's box can),
 //   before A.interact() only while F_B can meet F_A (B not moved yet: while B's box can meet F_A).
 // The oracle emulation of this rule halves the longest chain per sweep at config-3 density.  Particles with more
-// than SM_SW_NEAR neighbours in range, or (sharded maps) with a neighbour executed by another rank, take the
+// than SM_SW_NEARX neighbours in range, or (sharded maps) with a neighbour executed by another rank, take the
 // conservative path for that sweep - waiting for `done` is always sufficient.
 // Returns the step's result; fin and done are published inside.
 template <class W, class A> __device__ __forceinline__ int do_move_coop(W& w, A& a, WaterP& p, WaterMidCoop& m) { return water_move_coop(w, a, p, m, SM_CW_PLUS); }
@@ -311,32 +315,36 @@ __device__ __forceinline__ int sweep_exact(const DevCtx& c, WarpSmem& ws, WarpDe
   const int lane = w.lane;
   const unsigned int cnt = ws.cnt;
   const uint32_t ownpred = ws.pred[4];
-  // this lane's neighbour
-  const bool mine = lane < (int)cnt;
-  const uint32_t j = mine ? (ws.blk[lane] & 0x0FFFFFFFu) : 0u;   // executed by this rank (else the caller goes conservative)
-  const uint32_t jxy = mine ? ws.blkxy[lane] : 0u;
-  const int jx = (int)(jxy >> 18), jy = (int)((jxy >> 4) & 0x3FFFu), jR = (int)(jxy & 0xFu);
-  bool need1 = mine;                                   // still to be resolved before interact()
-  bool need0 = mine && ((ws.m0 >> lane) & 1u);         // ... before move()
-  int mx = 0, my = 0;
-  bool moved = false;                                  // neighbour's npos known
+  // Entry base + lane of the neighbour list is this lane's in round base / 32; both waits are conjunctions over the
+  // entries, so the rounds simply follow one another.
   // ---- wait to move ----
-  bool acq = false;            // this lane's neighbour was resolved by its fin word: acquire it once after the loop
-  for (;;) {
-    if (need0) {
-      if (ld_relaxed_u32(&c.fin[j]) >= tag) { need0 = false; need1 = false; acq = true; }
-      else {
-        const unsigned long long v = *((volatile unsigned long long*)&c.mv[j]);
-        if ((unsigned int)(v >> 32) == tag) {
-          mx = (int)((v >> 16) & 0xFFFFu); my = (int)(v & 0xFFFFu); moved = true;
-          if (!Foot<KIND>::W_hits_M(jx, jy, mx, my, ix, iy)) need0 = false;
+  for (unsigned int base = 0; base < cnt; base += 32u) {
+    const bool mine = base + (unsigned int)lane < cnt;
+    const uint32_t j = mine ? (ws.blk[base + lane] & 0x0FFFFFFFu) : 0u;   // executed by this rank (else the caller goes conservative)
+    const uint32_t jxy = mine ? ws.blkxy[base + lane] : 0u;
+    const int jx = (int)(jxy >> 18), jy = (int)((jxy >> 4) & 0x3FFFu);
+    bool need1 = mine;                                                    // still to be resolved before interact()
+    bool need0 = mine && ((ws.m0[base >> 5] >> lane) & 1u);               // ... before move()
+    bool acq = false;          // this lane's neighbour was resolved by its fin word: acquire it once after the loop
+    for (;;) {
+      if (need0) {
+        if (ld_relaxed_u32(&c.fin[j]) >= tag) { need0 = false; need1 = false; acq = true; }
+        else {
+          const unsigned long long v = *((volatile unsigned long long*)&c.mv[j]);
+          if ((unsigned int)(v >> 32) == tag) {
+            const int mx = (int)((v >> 16) & 0xFFFFu), my = (int)(v & 0xFFFFu);
+            if (!Foot<KIND>::W_hits_M(jx, jy, mx, my, ix, iy)) need0 = false;
+          }
         }
       }
+      if (!__any_sync(0xffffffffu, need0)) break;
+      poll_backoff();
     }
-    if (!__any_sync(0xffffffffu, need0)) break;
-    poll_backoff();
+    if (acq) (void)ld_acquire_u32(&c.fin[j]);
+    const unsigned int left = __ballot_sync(0xffffffffu, need1);
+    if (lane == 0) ws.n1[base >> 5] = left;
   }
-  if (acq) { (void)ld_acquire_u32(&c.fin[j]); acq = false; }
+  __syncwarp();
   DevBack<MULTI, BUDGET> back(c, s_soils, tag);
   CoopWin<DevBack<MULTI, BUDGET> > a(back, &ws.cs);
   typename MidCoopType<KIND>::T mid;
@@ -346,23 +354,34 @@ __device__ __forceinline__ int sweep_exact(const DevCtx& c, WarpSmem& ws, WarpDe
     if (lane == 0)
       *((volatile unsigned long long*)&c.mv[pid]) = ((unsigned long long)tag << 32) | ((unsigned long long)nx << 16) | (unsigned long long)ny;
     // ---- wait to interact ----
-    for (;;) {
-      if (need1) {
-        if (ld_relaxed_u32(&c.fin[j]) >= tag) { need1 = false; acq = true; }
-        else {
-          if (!moved) {
-            const unsigned long long v = *((volatile unsigned long long*)&c.mv[j]);
-            if ((unsigned int)(v >> 32) == tag) { mx = (int)((v >> 16) & 0xFFFFu); my = (int)(v & 0xFFFFu); moved = true; }
+    for (unsigned int base = 0; base < cnt; base += 32u) {
+      const unsigned int left = ws.n1[base >> 5];
+      if (left == 0u) continue;
+      bool need1 = (left >> lane) & 1u;
+      const uint32_t j = need1 ? (ws.blk[base + lane] & 0x0FFFFFFFu) : 0u;
+      const uint32_t jxy = need1 ? ws.blkxy[base + lane] : 0u;
+      const int jx = (int)(jxy >> 18), jy = (int)((jxy >> 4) & 0x3FFFu), jR = (int)(jxy & 0xFu);
+      int mx = 0, my = 0;
+      bool moved = false;                                  // neighbour's npos known
+      bool acq = false;
+      for (;;) {
+        if (need1) {
+          if (ld_relaxed_u32(&c.fin[j]) >= tag) { need1 = false; acq = true; }
+          else {
+            if (!moved) {
+              const unsigned long long v = *((volatile unsigned long long*)&c.mv[j]);
+              if ((unsigned int)(v >> 32) == tag) { mx = (int)((v >> 16) & 0xFFFFu); my = (int)(v & 0xFFFFu); moved = true; }
+            }
+            const bool hit = moved ? Foot<KIND>::F_hits_F(ix, iy, nx, ny, jx, jy, mx, my)
+                                   : Foot<KIND>::box_hits_F(ix, iy, nx, ny, jx, jy, jR);
+            if (!hit) need1 = false;
           }
-          const bool hit = moved ? Foot<KIND>::F_hits_F(ix, iy, nx, ny, jx, jy, mx, my)
-                                 : Foot<KIND>::box_hits_F(ix, iy, nx, ny, jx, jy, jR);
-          if (!hit) need1 = false;
         }
+        if (!__any_sync(0xffffffffu, need1)) break;
+        poll_backoff();
       }
-      if (!__any_sync(0xffffffffu, need1)) break;
-      poll_backoff();
+      if (acq) (void)ld_acquire_u32(&c.fin[j]);
     }
-    if (acq) (void)ld_acquire_u32(&c.fin[j]);
     r = do_interact_coop(w, a, p, mid);
     a.flush(w);
   }
@@ -585,7 +604,7 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
       int r = SM_ALIVE;
       bool exact_now = false;
       if constexpr (EXACT) {
-        exact_now = ws.cnt <= SM_SW_NEAR && !(MULTI && ws.remote);
+        exact_now = ws.cnt <= SM_SW_NEARX && !(MULTI && ws.remote);
         if (exact_now) r = sweep_exact<KIND, MULTI, BUDGET>(c, ws, w, s_soils, tag, pid, ix, iy, myR, p, edge);
       }
       if (!exact_now) {
