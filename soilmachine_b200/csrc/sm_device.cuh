@@ -135,6 +135,11 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
 __device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// one release for several flag words: fence.acq_rel, then relaxed stores (the pattern st.release expands to)
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void st_relaxed_u32(unsigned int* p, unsigned int v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 // relaxed polls: a spin loop reads with relaxed loads (an acquire load drags an L1 invalidation along on every
 // iteration - CCTL.IVALL was 12 % of all stall samples of the first warp-kernel profile, and the poll traffic slows
 // every other L2 access down) and acquires ONCE when the value it waited for has arrived

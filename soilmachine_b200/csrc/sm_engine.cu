@@ -57,7 +57,8 @@ __device__ __forceinline__ int particle_reach(const WindP& p) {
 #endif
 #define SM_SWEEPS_NONE 0x40000000   // internal: run the prologue only
 #ifndef SM_DEFAULT_EXACT
-#define SM_DEFAULT_EXACT 0             // warp kernel: exact footprints for water batches (flipped once measured)
+#define SM_DEFAULT_EXACT 1             // warp kernel: exact footprints for water batches (bit 0; measured -43 % on the
+                                       // water batch of config 3, -51 % on config 4, profiles/r02_exp12_exact_rounds.log), bit 1 = wind (-1 %)
 #endif
 #ifndef SM_DEFAULT_COOP
 #define SM_DEFAULT_COOP true           // k_sweep (warp per particle); SM_KERNEL=thread selects the round-1 kernels
