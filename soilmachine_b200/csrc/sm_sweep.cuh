@@ -119,7 +119,6 @@ template <bool MULTI, bool BUDGET = false> struct DevBack {
 struct __align__(32) WarpSmem {
   CoopScratch cs;
   uint32_t blk[SM_SW_NEARX];   // in-range lower-index particles of this sweep (rank in bits 28-31 on a sharded map)
-  uint32_t pred[12];     // per-bin predecessors (largest lower index in each of the 3x3 bins)
   uint32_t cnt;
   uint32_t m0[SM_SW_NEARX / 32];   // exact schedule: bit l = entry l can delay move() (its box can meet plus(ipos))
   uint32_t n1[SM_SW_NEARX / 32];   // exact schedule: bit l = entry l still unresolved after the wait to move
@@ -137,11 +136,9 @@ template <class W, class A> __device__ __forceinline__ int do_step_coop(W& w, A&
 template <class W, class A> __device__ __forceinline__ int do_step_coop(W& w, A& a, WindP& p) { return wind_step_coop(w, a, p); }
 
 // Conflict detection for one particle and one sweep, nine lanes = the 3x3 bins around ipos.  Two steps are
-// ordered iff their published boxes can meet (|dipos|_inf <= R_A + R_B).  Sparse case: every lower-index
-// particle in range gets a polling lane, plus the own-bin predecessor.  Crowded case (more than SM_SW_NEAR in
-// range): the nine per-bin predecessors.  Every particle always waits for its own-bin predecessor, hence
-// "X done => every lower index in X's bin done", which makes the per-bin predecessors a complete (conservative)
-// blocker set however large the cluster is.  Returns this lane's wait target (SM_NIL = none).
+// ordered iff their published boxes can meet (|dipos|_inf <= R_A + R_B).  Every lower-index particle in range is
+// listed (ws.blk) and gets a polling lane; with more of them than the list holds the particle takes crowded_wait().
+// Returns this lane's wait target (SM_NIL = none).
 template <int KIND, bool MULTI, bool EXACT = false>
 __device__ __forceinline__ uint32_t coop_scan(const DevCtx& c, WarpSmem& ws, int lane, unsigned int tag, int pid, int ix,
                                               int iy, int R) {
@@ -153,7 +150,6 @@ __device__ __forceinline__ uint32_t coop_scan(const DevCtx& c, WarpSmem& ws, int
   __syncwarp();
   if (lane < 9) {
     const int cx = ix / G + lane / 3 - 1, cy = iy / G + lane % 3 - 1;
-    uint32_t best = SM_NIL;
     if (cx >= 0 && cx < nbx && cy >= 0 && cy < nby) {
       const int bq = MULTI ? owner_of_x<MULTI>(c, cx * G) : 0;
       const unsigned long long* hp = MULTI ? c.peer[bq].head[par] : c.head[par];
@@ -166,7 +162,6 @@ __device__ __forceinline__ uint32_t coop_scan(const DevCtx& c, WarpSmem& ws, int
           const uint2 nd = nodes[j];
           if (j > (uint32_t)pid) ws.succ = 1u;        // (same value from every lane that sees one)
           if (j < (uint32_t)pid) {
-            if (best == SM_NIL || (j | qtag) > best) best = j | qtag;
             int dx = (int)(nd.y >> 18) - ix, dy = (int)((nd.y >> 4) & 0x3FFFu) - iy;
             const int D = R + (int)(nd.y & 0xFu);
             dx = dx < 0 ? -dx : dx;
@@ -189,16 +184,49 @@ __device__ __forceinline__ uint32_t coop_scan(const DevCtx& c, WarpSmem& ws, int
         }
       }
     }
-    ws.pred[lane] = best;
   }
   __syncwarp();
   const unsigned int cnt = ws.cnt;
-  if (cnt <= SM_SW_NEAR) {
-    if (lane < (int)cnt) return ws.blk[lane];
-    if (lane == 31) return ws.pred[4];
-    return SM_NIL;
+  return (cnt <= SM_SW_NEAR && lane < (int)cnt) ? ws.blk[lane] : SM_NIL;
+}
+
+// Crowded case of the conservative rule (more lower-index particles in range than the scan lists): nine lanes walk
+// the 3x3 bins again and wait for every lower-index particle in range, one after the other.  Rare (a list holds 31
+// entries, 128 under the exact schedule) and then the particle sits in a cluster that runs serially anyway.
+template <int KIND, bool MULTI>
+__device__ __forceinline__ void crowded_wait(const DevCtx& c, int lane, unsigned int tag, int pid, int ix, int iy, int R) {
+  const unsigned int par = tag & 1u;
+  const int G = Reach<KIND>::G;
+  const int nbx = (c.dimx + G - 1) / G, nby = (c.dimy + G - 1) / G;
+  if (lane < 9) {
+    const int cx = ix / G + lane / 3 - 1, cy = iy / G + lane % 3 - 1;
+    if (cx >= 0 && cx < nbx && cy >= 0 && cy < nby) {
+      const int bq = MULTI ? owner_of_x<MULTI>(c, cx * G) : 0;
+      const unsigned long long* hp = MULTI ? c.peer[bq].head[par] : c.head[par];
+      const unsigned long long h = *((volatile const unsigned long long*)&hp[cx * nby + cy]);
+      if ((unsigned int)(h >> 32) == tag) {
+        const uint2* nodes = MULTI ? c.peer[bq].node[par] : c.node[par];
+        const unsigned int* dones = MULTI ? c.peer[bq].done : c.done;
+        const bool remote = MULTI && bq != c.rank;
+        uint32_t j = (uint32_t)h;
+        while (j != SM_NIL) {
+          const uint2 nd = nodes[j];
+          if (j < (uint32_t)pid) {
+            int dx = (int)(nd.y >> 18) - ix, dy = (int)((nd.y >> 4) & 0x3FFFu) - iy;
+            const int D = R + (int)(nd.y & 0xFu);
+            dx = dx < 0 ? -dx : dx;
+            dy = dy < 0 ? -dy : dy;
+            if (dx <= D && dy <= D)
+              while ((remote ? ld_relaxed_sys_u32(&dones[j]) : ld_relaxed_u32(&dones[j])) < tag) poll_backoff();
+          }
+          j = nd.x;
+        }
+      }
+    }
   }
-  return lane < 9 ? ws.pred[lane] : SM_NIL;
+  __syncwarp();
+  // acquire for every release the polls observed
+  if (MULTI) __threadfence_system(); else fence_acq_rel_gpu();
 }
 
 // spin until every lane's target has published this sweep
@@ -289,8 +317,8 @@ __device__ __forceinline__ unsigned int grid_barrier_x(const DevCtx& c, unsigned
 // is only known after move().  The per-sweep statistics (profiles/r02_sweepstat.log) show what that costs: in every
 // wind sweep some particle waits ~17 us for a chain of 2-3 boxes that overlap while the footprints do not.  With EXACT a
 // particle publishes three words per sweep: mv (= npos, right after move(); it only lets others SKIP a wait, so it
-// needs no fence), fin (its map writes are complete; release) and done (published in own-bin index order, which
-// keeps "X done => every lower index in X's bin done" and with it the crowded fallback sound).  A lower-index
+// needs no fence) and fin / done (its map writes are complete; one release fence, both words - the exact schedule
+// polls fin, the conservative one done; on a strip edge done is released at system scope).  A lower-index
 // particle B in range holds A back
 //   before A.move()     only while B's writes {ipos_B} U 3x3(npos_B) can meet plus(ipos_A)
 //                       (B not moved yet: while B's box can),
@@ -314,7 +342,6 @@ __device__ __forceinline__ int sweep_exact(const DevCtx& c, WarpSmem& ws, WarpDe
                                            typename PType<KIND>::T& p, bool edge) {
   const int lane = w.lane;
   const unsigned int cnt = ws.cnt;
-  const uint32_t ownpred = ws.pred[4];
   // Entry base + lane of the neighbour list is this lane's in round base / 32; both waits are conjunctions over the
   // entries, so the rounds simply follow one another.
   // ---- wait to move ----
@@ -389,23 +416,11 @@ __device__ __forceinline__ int sweep_exact(const DevCtx& c, WarpSmem& ws, WarpDe
   if (lane == 0) {
     const unsigned int pub = (r == SM_ALIVE) ? tag : 0xFFFFFFFFu;
     if (ws.succ) {
-      // `done` in own-bin index order
-      const unsigned int* dp = nullptr;
-      if (ownpred != SM_NIL) dp = MULTI ? &c.peer[ownpred >> 28].done[ownpred & 0x0FFFFFFFu] : &c.done[ownpred];
-      if (!(MULTI && edge) && (dp == nullptr || ld_relaxed_u32(dp) >= tag)) {
-        // the predecessor has published already (the usual case): one release fence covers both words
-        if (dp != nullptr) (void)ld_acquire_u32(dp);
+      if (MULTI && edge) { st_release_u32(&c.fin[pid], pub); st_release_sys_u32(&c.done[pid], pub); }
+      else {                               // one release fence covers both words
         fence_acq_rel_gpu();
         st_relaxed_u32(&c.fin[pid], pub);
         st_relaxed_u32(&c.done[pid], pub);
-      } else {
-        st_release_u32(&c.fin[pid], pub);
-        if (dp != nullptr) {
-          while (ld_relaxed_u32(dp) < tag) poll_backoff();
-          (void)ld_acquire_u32(dp);
-        }
-        if (MULTI && edge) st_release_sys_u32(&c.done[pid], pub);
-        else st_release_u32(&c.done[pid], pub);
       }
     } else {             // no higher index in the 3x3 bins: nobody waits for fin or done (see the conservative path)
       st_volatile_u32(&c.fin[pid], pub);
@@ -613,13 +628,14 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
       int r = SM_ALIVE;
       bool exact_now = false;
       if constexpr (EXACT) {
-        // a particle with no lower-index particle in range has nothing to gain from the two-stage schedule (and its
-        // second staging fetch and ordered `done` cost ~10 % where a batch is throughput-bound, config 5)
-        exact_now = ws.cnt >= 1u && ws.cnt <= SM_SW_NEARX && !(MULTI && ws.remote);
+        // (also for a particle with nothing in range: its mv word is what lets the particles behind it skip waits -
+        // sending those down the conservative path cost 15-20 %, profiles/r02_exp13_timing.log)
+        exact_now = ws.cnt <= SM_SW_NEARX && !(MULTI && ws.remote);
         if (exact_now) r = sweep_exact<KIND, MULTI, BUDGET>(c, ws, w, s_soils, tag, pid, ix, iy, myR, p, edge);
       }
       if (!exact_now) {
-        coop_wait<MULTI>(c, tag, tgt);
+        if (ws.cnt > SM_SW_NEAR) crowded_wait<KIND, MULTI>(c, lane, tag, pid, ix, iy, myR);
+        else coop_wait<MULTI>(c, tag, tgt);
 #ifdef SM_PROFILE
         pc2 = clock64();
 #endif
