@@ -20,9 +20,9 @@
 #ifndef SM_SW_MINBLOCKS
 #define SM_SW_MINBLOCKS 3    // resident blocks per SM the kernel is compiled for (register cap)
 #endif
-#define SM_SW_NEAR 31        // in-range lower-index particles tracked exactly (one polling lane each)
-#define SM_SW_NEARX 128      // ... by the exact schedule, which polls them in rounds of 32 (dense clusters - water
-                             // collecting in a pit - are where exact footprints pay most: scripts/chain_analysis.py)
+#define SM_SW_NEARX 128      // in-range lower-index particles listed per particle and sweep, polled in rounds of 32 (dense
+                             // clusters - water collecting in a pit - are where exact footprints pay most:
+                             // scripts/chain_analysis.py)
 
 // warp policy of sm_coop.cuh on the device.  Every primitive is a full-warp synchronisation point on both
 // sides: __syncwarp() orders the memory accesses of the participating lanes, so what lanes wrote before a
@@ -137,10 +137,10 @@ template <class W, class A> __device__ __forceinline__ int do_step_coop(W& w, A&
 
 // Conflict detection for one particle and one sweep, nine lanes = the 3x3 bins around ipos.  Two steps are
 // ordered iff their published boxes can meet (|dipos|_inf <= R_A + R_B).  Every lower-index particle in range is
-// listed (ws.blk) and gets a polling lane; with more of them than the list holds the particle takes crowded_wait().
-// Returns this lane's wait target (SM_NIL = none).
+// listed (ws.blk, ws.cnt entries) and polled by a lane, 32 at a time; the ones a full list has no room for are
+// waited for on the spot.
 template <int KIND, bool MULTI, bool EXACT = false>
-__device__ __forceinline__ uint32_t coop_scan(const DevCtx& c, WarpSmem& ws, int lane, unsigned int tag, int pid, int ix,
+__device__ __forceinline__ void coop_scan(const DevCtx& c, WarpSmem& ws, int lane, unsigned int tag, int pid, int ix,
                                               int iy, int R) {
   const unsigned int par = tag & 1u;
   const int G = Reach<KIND>::G;
@@ -168,7 +168,12 @@ __device__ __forceinline__ uint32_t coop_scan(const DevCtx& c, WarpSmem& ws, int
             dy = dy < 0 ? -dy : dy;
             if (dx <= D && dy <= D) {
               const unsigned int at = atomicAdd(&ws.cnt, 1u);
-              if (at < (EXACT ? SM_SW_NEARX : SM_SW_NEAR)) {
+              if (at >= SM_SW_NEARX) {
+                // more in range than the list holds (a cluster that runs serially anyway): wait for this one here
+                const unsigned int* dp = MULTI ? &c.peer[bq].done[j] : &c.done[j];
+                const bool far = MULTI && bq != c.rank;
+                while ((far ? ld_relaxed_sys_u32(dp) : ld_relaxed_u32(dp)) < tag) poll_backoff();
+              } else {
                 ws.blk[at] = j | qtag;
                 if (EXACT) {
                   ws.blkxy[at] = nd.y;
@@ -187,46 +192,11 @@ __device__ __forceinline__ uint32_t coop_scan(const DevCtx& c, WarpSmem& ws, int
   }
   __syncwarp();
   const unsigned int cnt = ws.cnt;
-  return (cnt <= SM_SW_NEAR && lane < (int)cnt) ? ws.blk[lane] : SM_NIL;
-}
-
-// Crowded case of the conservative rule (more lower-index particles in range than the scan lists): nine lanes walk
-// the 3x3 bins again and wait for every lower-index particle in range, one after the other.  Rare (a list holds 31
-// entries, 128 under the exact schedule) and then the particle sits in a cluster that runs serially anyway.
-template <int KIND, bool MULTI>
-__device__ __forceinline__ void crowded_wait(const DevCtx& c, int lane, unsigned int tag, int pid, int ix, int iy, int R) {
-  const unsigned int par = tag & 1u;
-  const int G = Reach<KIND>::G;
-  const int nbx = (c.dimx + G - 1) / G, nby = (c.dimy + G - 1) / G;
-  if (lane < 9) {
-    const int cx = ix / G + lane / 3 - 1, cy = iy / G + lane % 3 - 1;
-    if (cx >= 0 && cx < nbx && cy >= 0 && cy < nby) {
-      const int bq = MULTI ? owner_of_x<MULTI>(c, cx * G) : 0;
-      const unsigned long long* hp = MULTI ? c.peer[bq].head[par] : c.head[par];
-      const unsigned long long h = *((volatile const unsigned long long*)&hp[cx * nby + cy]);
-      if ((unsigned int)(h >> 32) == tag) {
-        const uint2* nodes = MULTI ? c.peer[bq].node[par] : c.node[par];
-        const unsigned int* dones = MULTI ? c.peer[bq].done : c.done;
-        const bool remote = MULTI && bq != c.rank;
-        uint32_t j = (uint32_t)h;
-        while (j != SM_NIL) {
-          const uint2 nd = nodes[j];
-          if (j < (uint32_t)pid) {
-            int dx = (int)(nd.y >> 18) - ix, dy = (int)((nd.y >> 4) & 0x3FFFu) - iy;
-            const int D = R + (int)(nd.y & 0xFu);
-            dx = dx < 0 ? -dx : dx;
-            dy = dy < 0 ? -dy : dy;
-            if (dx <= D && dy <= D)
-              while ((remote ? ld_relaxed_sys_u32(&dones[j]) : ld_relaxed_u32(&dones[j])) < tag) poll_backoff();
-          }
-          j = nd.x;
-        }
-      }
-    }
+  if (cnt > SM_SW_NEARX) {          // acquire for the releases the overflow polls observed
+    if (MULTI) __threadfence_system(); else fence_acq_rel_gpu();
+    if (lane == 0) ws.cnt = SM_SW_NEARX;
+    __syncwarp();
   }
-  __syncwarp();
-  // acquire for every release the polls observed
-  if (MULTI) __threadfence_system(); else fence_acq_rel_gpu();
 }
 
 // spin until every lane's target has published this sweep
@@ -324,8 +294,8 @@ __device__ __forceinline__ unsigned int grid_barrier_x(const DevCtx& c, unsigned
 //                       (B not moved yet: while B's box can),
 //   before A.interact() only while F_B can meet F_A (B not moved yet: while B's box can meet F_A).
 // The oracle emulation of this rule halves the longest chain per sweep at config-3 density.  Particles with more
-// than SM_SW_NEARX neighbours in range, or (sharded maps) with a neighbour executed by another rank, take the
-// conservative path for that sweep - waiting for `done` is always sufficient.
+// a neighbour executed by another rank (sharded maps) take the conservative path for that sweep - waiting for `done`
+// is always sufficient.
 // Returns the step's result; fin and done are published inside.
 template <class W, class A> __device__ __forceinline__ int do_move_coop(W& w, A& a, WaterP& p, WaterMidCoop& m) { return water_move_coop(w, a, p, m, SM_CW_PLUS); }
 template <class W, class A> __device__ __forceinline__ int do_move_coop(W& w, A& a, WindP& p, WindMidCoop& m) { return wind_move_coop(w, a, p, m, SM_CW_PLUS); }
@@ -613,7 +583,7 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
       load_particle(c, pid, p);
       const int ix = (int)roundf(p.px), iy = (int)roundf(p.py);
       const int myR = particle_reach(p);
-      const uint32_t tgt = coop_scan<KIND, MULTI, EXACT>(c, ws, lane, tag, pid, ix, iy, myR);
+      coop_scan<KIND, MULTI, EXACT>(c, ws, lane, tag, pid, ix, iy, myR);
 #ifdef SM_PROFILE
       const long long pc1 = clock64();
       long long pc2 = pc1;
@@ -630,12 +600,12 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
       if constexpr (EXACT) {
         // (also for a particle with nothing in range: its mv word is what lets the particles behind it skip waits -
         // sending those down the conservative path cost 15-20 %, profiles/r02_exp13_timing.log)
-        exact_now = ws.cnt <= SM_SW_NEARX && !(MULTI && ws.remote);
+        exact_now = !(MULTI && ws.remote);
         if (exact_now) r = sweep_exact<KIND, MULTI, BUDGET>(c, ws, w, s_soils, tag, pid, ix, iy, myR, p, edge);
       }
       if (!exact_now) {
-        if (ws.cnt > SM_SW_NEAR) crowded_wait<KIND, MULTI>(c, lane, tag, pid, ix, iy, myR);
-        else coop_wait<MULTI>(c, tag, tgt);
+        for (unsigned int base = 0; base < ws.cnt; base += 32u)
+          coop_wait<MULTI>(c, tag, base + (unsigned int)lane < ws.cnt ? ws.blk[base + lane] : SM_NIL);
 #ifdef SM_PROFILE
         pc2 = clock64();
 #endif
