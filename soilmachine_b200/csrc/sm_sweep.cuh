@@ -20,9 +20,9 @@
 #ifndef SM_SW_MINBLOCKS
 #define SM_SW_MINBLOCKS 3    // resident blocks per SM the kernel is compiled for (register cap)
 #endif
-#define SM_SW_NEARX 128      // in-range lower-index particles listed per particle and sweep, polled in rounds of 32 (dense
-                             // clusters - water collecting in a pit - are where exact footprints pay most:
-                             // scripts/chain_analysis.py)
+#define SM_SW_NEAR 31        // in-range lower-index particles tracked exactly (one polling lane each)
+#define SM_SW_NEARX 128      // ... by the exact schedule, which polls them in rounds of 32 (dense clusters - water
+                             // collecting in a pit - are where exact footprints pay most: scripts/chain_analysis.py)
 
 // warp policy of sm_coop.cuh on the device.  Every primitive is a full-warp synchronisation point on both
 // sides: __syncwarp() orders the memory accesses of the participating lanes, so what lanes wrote before a
@@ -119,6 +119,7 @@ template <bool MULTI, bool BUDGET = false> struct DevBack {
 struct __align__(32) WarpSmem {
   CoopScratch cs;
   uint32_t blk[SM_SW_NEARX];   // in-range lower-index particles of this sweep (rank in bits 28-31 on a sharded map)
+  uint32_t pred[12];     // per-bin predecessors (largest lower index in each of the 3x3 bins)
   uint32_t cnt;
   uint32_t m0[SM_SW_NEARX / 32];   // exact schedule: bit l = entry l can delay move() (its box can meet plus(ipos))
   uint32_t n1[SM_SW_NEARX / 32];   // exact schedule: bit l = entry l still unresolved after the wait to move
@@ -136,11 +137,13 @@ template <class W, class A> __device__ __forceinline__ int do_step_coop(W& w, A&
 template <class W, class A> __device__ __forceinline__ int do_step_coop(W& w, A& a, WindP& p) { return wind_step_coop(w, a, p); }
 
 // Conflict detection for one particle and one sweep, nine lanes = the 3x3 bins around ipos.  Two steps are
-// ordered iff their published boxes can meet (|dipos|_inf <= R_A + R_B).  Every lower-index particle in range is
-// listed (ws.blk, ws.cnt entries) and polled by a lane, 32 at a time; the ones a full list has no room for are
-// waited for on the spot.
+// ordered iff their published boxes can meet (|dipos|_inf <= R_A + R_B).  Sparse case: every lower-index
+// particle in range gets a polling lane, plus the own-bin predecessor.  Crowded case (more than SM_SW_NEAR in
+// range): the nine per-bin predecessors.  Every particle always waits for its own-bin predecessor, hence
+// "X done => every lower index in X's bin done", which makes the per-bin predecessors a complete (conservative)
+// blocker set however large the cluster is.  Returns this lane's wait target (SM_NIL = none).
 template <int KIND, bool MULTI, bool EXACT = false>
-__device__ __forceinline__ void coop_scan(const DevCtx& c, WarpSmem& ws, int lane, unsigned int tag, int pid, int ix,
+__device__ __forceinline__ uint32_t coop_scan(const DevCtx& c, WarpSmem& ws, int lane, unsigned int tag, int pid, int ix,
                                               int iy, int R) {
   const unsigned int par = tag & 1u;
   const int G = Reach<KIND>::G;
@@ -150,6 +153,7 @@ __device__ __forceinline__ void coop_scan(const DevCtx& c, WarpSmem& ws, int lan
   __syncwarp();
   if (lane < 9) {
     const int cx = ix / G + lane / 3 - 1, cy = iy / G + lane % 3 - 1;
+    uint32_t best = SM_NIL;
     if (cx >= 0 && cx < nbx && cy >= 0 && cy < nby) {
       const int bq = MULTI ? owner_of_x<MULTI>(c, cx * G) : 0;
       const unsigned long long* hp = MULTI ? c.peer[bq].head[par] : c.head[par];
@@ -162,18 +166,14 @@ __device__ __forceinline__ void coop_scan(const DevCtx& c, WarpSmem& ws, int lan
           const uint2 nd = nodes[j];
           if (j > (uint32_t)pid) ws.succ = 1u;        // (same value from every lane that sees one)
           if (j < (uint32_t)pid) {
+            if (best == SM_NIL || (j | qtag) > best) best = j | qtag;
             int dx = (int)(nd.y >> 18) - ix, dy = (int)((nd.y >> 4) & 0x3FFFu) - iy;
             const int D = R + (int)(nd.y & 0xFu);
             dx = dx < 0 ? -dx : dx;
             dy = dy < 0 ? -dy : dy;
             if (dx <= D && dy <= D) {
               const unsigned int at = atomicAdd(&ws.cnt, 1u);
-              if (at >= SM_SW_NEARX) {
-                // more in range than the list holds (a cluster that runs serially anyway): wait for this one here
-                const unsigned int* dp = MULTI ? &c.peer[bq].done[j] : &c.done[j];
-                const bool far = MULTI && bq != c.rank;
-                while ((far ? ld_relaxed_sys_u32(dp) : ld_relaxed_u32(dp)) < tag) poll_backoff();
-              } else {
+              if (at < (EXACT ? SM_SW_NEARX : SM_SW_NEAR)) {
                 ws.blk[at] = j | qtag;
                 if (EXACT) {
                   ws.blkxy[at] = nd.y;
@@ -189,14 +189,16 @@ __device__ __forceinline__ void coop_scan(const DevCtx& c, WarpSmem& ws, int lan
         }
       }
     }
+    ws.pred[lane] = best;
   }
   __syncwarp();
   const unsigned int cnt = ws.cnt;
-  if (cnt > SM_SW_NEARX) {          // acquire for the releases the overflow polls observed
-    if (MULTI) __threadfence_system(); else fence_acq_rel_gpu();
-    if (lane == 0) ws.cnt = SM_SW_NEARX;
-    __syncwarp();
+  if (cnt <= SM_SW_NEAR) {
+    if (lane < (int)cnt) return ws.blk[lane];
+    if (lane == 31) return ws.pred[4];
+    return SM_NIL;
   }
+  return lane < 9 ? ws.pred[lane] : SM_NIL;
 }
 
 // spin until every lane's target has published this sweep
@@ -287,15 +289,15 @@ __device__ __forceinline__ unsigned int grid_barrier_x(const DevCtx& c, unsigned
 // is only known after move().  The per-sweep statistics (profiles/r02_sweepstat.log) show what that costs: in every
 // wind sweep some particle waits ~17 us for a chain of 2-3 boxes that overlap while the footprints do not.  With EXACT a
 // particle publishes three words per sweep: mv (= npos, right after move(); it only lets others SKIP a wait, so it
-// needs no fence) and fin / done (its map writes are complete; one release fence, both words - the exact schedule
-// polls fin, the conservative one done; on a strip edge done is released at system scope).  A lower-index
+// needs no fence), fin (its map writes are complete; release) and done (published in own-bin index order, which
+// keeps "X done => every lower index in X's bin done" and with it the crowded fallback sound).  A lower-index
 // particle B in range holds A back
 //   before A.move()     only while B's writes {ipos_B} U 3x3(npos_B) can meet plus(ipos_A)
 //                       (B not moved yet: while B's box can),
 //   before A.interact() only while F_B can meet F_A (B not moved yet: while B's box can meet F_A).
 // The oracle emulation of this rule halves the longest chain per sweep at config-3 density.  Particles with more
-// a neighbour executed by another rank (sharded maps) take the conservative path for that sweep - waiting for `done`
-// is always sufficient.
+// than SM_SW_NEARX neighbours in range, or (sharded maps) with a neighbour executed by another rank, take the
+// conservative path for that sweep - waiting for `done` is always sufficient.
 // Returns the step's result; fin and done are published inside.
 template <class W, class A> __device__ __forceinline__ int do_move_coop(W& w, A& a, WaterP& p, WaterMidCoop& m) { return water_move_coop(w, a, p, m, SM_CW_PLUS); }
 template <class W, class A> __device__ __forceinline__ int do_move_coop(W& w, A& a, WindP& p, WindMidCoop& m) { return wind_move_coop(w, a, p, m, SM_CW_PLUS); }
@@ -312,6 +314,7 @@ __device__ __forceinline__ int sweep_exact(const DevCtx& c, WarpSmem& ws, WarpDe
                                            typename PType<KIND>::T& p, bool edge) {
   const int lane = w.lane;
   const unsigned int cnt = ws.cnt;
+  const uint32_t ownpred = ws.pred[4];
   // Entry base + lane of the neighbour list is this lane's in round base / 32; both waits are conjunctions over the
   // entries, so the rounds simply follow one another.
   // ---- wait to move ----
@@ -386,11 +389,23 @@ __device__ __forceinline__ int sweep_exact(const DevCtx& c, WarpSmem& ws, WarpDe
   if (lane == 0) {
     const unsigned int pub = (r == SM_ALIVE) ? tag : 0xFFFFFFFFu;
     if (ws.succ) {
-      if (MULTI && edge) { st_release_u32(&c.fin[pid], pub); st_release_sys_u32(&c.done[pid], pub); }
-      else {                               // one release fence covers both words
+      // `done` in own-bin index order
+      const unsigned int* dp = nullptr;
+      if (ownpred != SM_NIL) dp = MULTI ? &c.peer[ownpred >> 28].done[ownpred & 0x0FFFFFFFu] : &c.done[ownpred];
+      if (!(MULTI && edge) && (dp == nullptr || ld_relaxed_u32(dp) >= tag)) {
+        // the predecessor has published already (the usual case): one release fence covers both words
+        if (dp != nullptr) (void)ld_acquire_u32(dp);
         fence_acq_rel_gpu();
         st_relaxed_u32(&c.fin[pid], pub);
         st_relaxed_u32(&c.done[pid], pub);
+      } else {
+        st_release_u32(&c.fin[pid], pub);
+        if (dp != nullptr) {
+          while (ld_relaxed_u32(dp) < tag) poll_backoff();
+          (void)ld_acquire_u32(dp);
+        }
+        if (MULTI && edge) st_release_sys_u32(&c.done[pid], pub);
+        else st_release_u32(&c.done[pid], pub);
       }
     } else {             // no higher index in the 3x3 bins: nobody waits for fin or done (see the conservative path)
       st_volatile_u32(&c.fin[pid], pub);
@@ -583,7 +598,7 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
       load_particle(c, pid, p);
       const int ix = (int)roundf(p.px), iy = (int)roundf(p.py);
       const int myR = particle_reach(p);
-      coop_scan<KIND, MULTI, EXACT>(c, ws, lane, tag, pid, ix, iy, myR);
+      const uint32_t tgt = coop_scan<KIND, MULTI, EXACT>(c, ws, lane, tag, pid, ix, iy, myR);
 #ifdef SM_PROFILE
       const long long pc1 = clock64();
       long long pc2 = pc1;
@@ -600,12 +615,11 @@ __global__ void __launch_bounds__(SM_SW_WARPS * 32, SM_SW_MINBLOCKS) k_sweep(Dev
       if constexpr (EXACT) {
         // (also for a particle with nothing in range: its mv word is what lets the particles behind it skip waits -
         // sending those down the conservative path cost 15-20 %, profiles/r02_exp13_timing.log)
-        exact_now = !(MULTI && ws.remote);
+        exact_now = ws.cnt <= SM_SW_NEARX && !(MULTI && ws.remote);
         if (exact_now) r = sweep_exact<KIND, MULTI, BUDGET>(c, ws, w, s_soils, tag, pid, ix, iy, myR, p, edge);
       }
       if (!exact_now) {
-        for (unsigned int base = 0; base < ws.cnt; base += 32u)
-          coop_wait<MULTI>(c, tag, base + (unsigned int)lane < ws.cnt ? ws.blk[base + lane] : SM_NIL);
+        coop_wait<MULTI>(c, tag, tgt);
 #ifdef SM_PROFILE
         pc2 = clock64();
 #endif
