@@ -51,7 +51,10 @@ typedef struct sm_config {
   int32_t dimx, dimy;       /* SIZEX, SIZEY (SoilMachine.cpp:9-10) */
   int32_t scale;            /* SCALE (SoilMachine.cpp:11) */
   int32_t device;           /* CUDA device ordinal */
-  int64_t pool_capacity;    /* buried-section pool slots (POOLSIZE, SoilMachine.cpp:16); 0 = auto */
+  int64_t pool_capacity;    /* buried-section pool slots (POOLSIZE, SoilMachine.cpp:16); 0 = auto: one GPU - grows
+                               with sm_initialize / sm_upload_columns; sharded - 2 x strip cells + 4 Mi, FIXED at
+                               creation (the peers map it), so give strip cells x (layers - 1) + headroom for
+                               presets with four or more layers (SM_ERR_POOL says so otherwise) */
   int32_t max_particles;    /* largest batch a *_run call will be given; 0 = 262144 */
   int32_t flags;            /* SM_FLAG_* */
 } sm_config;
