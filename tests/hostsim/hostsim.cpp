@@ -2,6 +2,7 @@
 // for the HOST behind the same lockstep driver shape as the oracle.  TEST TOOL ONLY: it lets the
 // CPU test-suite check the type-exact transcription against oracle/_ref bit for bit without a
 // GPU.  It is not shipped, not linked into the product library and is not a CPU fallback.
+#include <array>
 #include <vector>
 #include <cstring>
 #include <cstdint>
@@ -77,13 +78,28 @@ struct WarpHost {
 };
 std::vector<float> G_field_store;
 WindField G_field = {nullptr, 0, 0, 0, 0, 0, 0};
+// Footprint audit (mode 2): every record access of a cooperative step goes through HostBack::cell_ptr - the staging
+// fetches, the in-place accesses beyond the staged blocks, the write-back - so recording the calls by phase shows what
+// a step can read or write, and the sets the exact-footprint schedule orders steps by (Foot<KIND>, sm_engine.cu) can
+// be checked to contain it.
+struct FootAudit {
+  bool on = false;
+  int phase = 0;                                  // 0 move(), 1 interact(), 2 write-back
+  std::vector<std::array<int, 3> > acc;           // x, y, phase
+  long long steps = 0, viol[3] = {0, 0, 0};       // accesses outside M / F / the write set
+  long long max_step = 0;                         // largest |npos - ipos|_inf seen
+};
+FootAudit G_foot;
 struct HostBack {   // backing store of CoopWin on the host
   HostAccess h;
   int dimx() const { return M.dimx; }
   int dimy() const { return M.dimy; }
   int scale() const { return M.scale; }
   const SoilDev* soilp(uint32_t t) const { return &M.soils[t]; }
-  Sec32* cell_ptr(int x, int y) { return &M.top[(size_t)x * M.dimy + y]; }
+  Sec32* cell_ptr(int x, int y) {
+    if (G_foot.on) G_foot.acc.push_back({x, y, G_foot.phase});
+    return &M.top[(size_t)x * M.dimy + y];
+  }
   void focus(int, int) {}
   Sec32 pool_load(uint32_t i) { return h.pool_load(i); }
   void pool_store(uint32_t i, const Sec32& r) { h.pool_store(i, r); }
@@ -106,6 +122,34 @@ int G_coop = 0;   // 1: the sweeps below run the warp-cooperative step
 std::vector<double> BUD;   // coop mode: 6 mass-budget accumulators per particle (sm_coop.cuh)
 
 struct Stats { int64_t steps, sweeps, exit_oob, exit_evap, exit_stall; double seconds; };
+// kind 0 water: move() reads plus(ipos); the step touches plus(ipos) U 3x3(npos) and writes {ipos} U 3x3(npos).
+// kind 1 wind : move() reads plus(ipos); the step touches and writes 5x5(ipos) U 5x5(npos).   (Foot<KIND>)
+void foot_check(int kind, int ix, int iy, bool moved, int nx, int ny) {
+  auto ab = [](int v) { return v < 0 ? -v : v; };
+  G_foot.steps++;
+  if (moved) {
+    const long long d = std::max(ab(nx - ix), ab(ny - iy));
+    if (d > G_foot.max_step) G_foot.max_step = d;
+  }
+  for (const auto& a : G_foot.acc) {
+    const int dxi = ab(a[0] - ix), dyi = ab(a[1] - iy);
+    const int dxn = moved ? ab(a[0] - nx) : 1 << 20, dyn = moved ? ab(a[1] - ny) : 1 << 20;
+    const bool plus = dxi + dyi <= 1;
+    bool inF, inW;
+    if (kind == 0) {
+      const bool n3 = dxn <= 1 && dyn <= 1;
+      inF = plus || n3;
+      inW = (dxi == 0 && dyi == 0) || n3;
+    } else {
+      inF = (dxi <= 2 && dyi <= 2) || (dxn <= 2 && dyn <= 2);
+      inW = inF;
+    }
+    if (a[2] == 0 && !plus) G_foot.viol[0]++;
+    if (a[2] == 1 && !inF) G_foot.viol[1]++;
+    if (a[2] == 2 && !inW) G_foot.viol[2]++;
+  }
+  G_foot.acc.clear();
+}
 std::vector<WaterP> W; std::vector<int> Wlive;
 std::vector<WindP> D; std::vector<int> Dlive;
 }  // namespace
@@ -176,6 +220,12 @@ double hs_remove(int x, int y, double h) { HostAccess a; return col_remove(a, *a
 void hs_cascade(float x, float y, int loop) { HostAccess a; Cascade<3, HostAccess>::run(a, (int)roundf(x), (int)roundf(y), loop); }
 
 void hs_set_mode(int coop, int lane_order) { G_coop = coop; G_lane_order = lane_order; }
+// footprint audit of the steps run in mode 2 since the last call: steps, accesses outside plus(ipos) during move(),
+// outside the footprint during interact(), write-backs outside the write set, largest |npos - ipos|
+void hs_footprint_audit(long long* out5) {
+  out5[0] = G_foot.steps; out5[1] = G_foot.viol[0]; out5[2] = G_foot.viol[1]; out5[3] = G_foot.viol[2]; out5[4] = G_foot.max_step;
+  G_foot = FootAudit();
+}
 void hs_set_volume_factor(double v) { M.volume_factor = v; }
 // attach (v4 != null) or detach a lattice velocity field for the wind particles' prevailing wind
 void hs_set_wind_field(const float* v4, int nx, int ny, int nz) {
@@ -198,8 +248,23 @@ int hs_water_sweep(Stats* st) {
     int r;
     if (G_coop) {
       WarpHost w; HostBack b; CoopScratch sc; CoopWin<HostBack> cw(b, &sc);
-      r = water_step_coop(w, cw, W[i], G_coop == 2 ? SM_CW_PLUS : 0x1FFu);   // 2: staged as the exact-footprint schedule does
-      cw.flush(w);
+      if (G_coop == 2) {        // staged and split as the exact-footprint schedule does (sweep_exact), with the audit
+        const int ix = (int)roundf(W[i].px), iy = (int)roundf(W[i].py);
+        WaterMidCoop mid;
+        G_foot.on = true; G_foot.phase = 0;
+        r = water_move_coop(w, cw, W[i], mid, SM_CW_PLUS);
+        const bool moved = r == SM_ALIVE;
+        const int nx = (int)roundf(W[i].px), ny = (int)roundf(W[i].py);
+        G_foot.phase = 1;
+        if (moved) r = water_interact_coop(w, cw, W[i], mid);
+        G_foot.phase = 2;
+        cw.flush(w);
+        G_foot.on = false;
+        foot_check(0, ix, iy, moved, nx, ny);
+      } else {
+        r = water_step_coop(w, cw, W[i]);
+        cw.flush(w);
+      }
       for (int k = 0; k < SM_BUDGET_SLOTS; k++) BUD[(size_t)i * SM_BUDGET_SLOTS + k] += sc.acc[k];
     } else r = water_step(a, W[i]);
     if (r == SM_EXIT_OOB) { st->exit_oob++; continue; }
@@ -232,8 +297,23 @@ int hs_wind_sweep(Stats* st) {
     int r;
     if (G_coop) {
       WarpHost w; HostBack b; CoopScratch sc; CoopWin<HostBack> cw(b, &sc);
-      r = wind_step_coop(w, cw, D[i], G_coop == 2 ? SM_CW_PLUS : 0x1FFu);
-      cw.flush(w);
+      if (G_coop == 2) {
+        const int ix = (int)roundf(D[i].px), iy = (int)roundf(D[i].py);
+        WindMidCoop mid;
+        G_foot.on = true; G_foot.phase = 0;
+        r = wind_move_coop(w, cw, D[i], mid, SM_CW_PLUS);
+        const bool moved = r == SM_ALIVE;
+        const int nx = (int)roundf(D[i].px), ny = (int)roundf(D[i].py);
+        G_foot.phase = 1;
+        if (moved) r = wind_interact_coop(w, cw, D[i], mid);
+        G_foot.phase = 2;
+        cw.flush(w);
+        G_foot.on = false;
+        foot_check(1, ix, iy, moved, nx, ny);
+      } else {
+        r = wind_step_coop(w, cw, D[i]);
+        cw.flush(w);
+      }
       for (int k = 0; k < SM_BUDGET_SLOTS; k++) BUD[(size_t)i * SM_BUDGET_SLOTS + k] += sc.acc[k];
     } else r = wind_step(a, D[i]);
     if (r != SM_ALIVE) { st->exit_oob++; continue; }

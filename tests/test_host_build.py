@@ -79,6 +79,32 @@ def test_warp_cooperative_step_with_late_corner_staging(case):
 
 
 @pytest.mark.parametrize("case", _golden.FRAME_CASES)
+def test_exact_footprints_contain_every_access_of_a_step(case):
+    """The exact-footprint schedule (sweep_exact, Foot<KIND> in sm_engine.cu) lets two steps overlap unless their
+    footprints can meet: move() reads plus(ipos); a water step touches plus(ipos) U 3x3(npos) and writes
+    {ipos} U 3x3(npos); a wind step touches and writes 5x5(ipos) U 5x5(npos).  Every record access of the cooperative
+    step goes through one function of its backing store, so the host build records them by phase on the golden frames
+    (split and staged exactly as the schedule does) and checks the sets really contain them - and that npos stays within
+    the STEP the conflict range assumes (2 water, 3 wind)."""
+    import ctypes as C
+    g = _golden.load(case)
+    b = Backend(g)
+    out = (C.c_longlong * 5)()
+    b.hs.lib.hs_set_mode(2, 0)
+    try:
+        b.hs.lib.hs_footprint_audit(out)          # reset
+        b.hs.set_columns(_golden.cols(g, "init"))
+        _golden.replay_frame(g, b, stats5)
+        b.hs.lib.hs_footprint_audit(out)
+    finally:
+        b.hs.lib.hs_set_mode(0, 0)
+    steps, in_move, in_interact, in_writeback, max_step = list(out)
+    assert steps > 1000
+    assert (in_move, in_interact, in_writeback) == (0, 0, 0)
+    assert max_step <= 3
+
+
+@pytest.mark.parametrize("case", _golden.FRAME_CASES)
 @pytest.mark.parametrize("lane_order", [0, 1], ids=["lanes_up", "lanes_down"])
 def test_warp_cooperative_step_replays_golden_frame(case, lane_order):
     """sm_coop.cuh - the step as the sweep kernel's warps execute it (lane-parallel gathers and cascade
