@@ -459,55 +459,7 @@ __global__ void __launch_bounds__(SM_BLOCK, SM_MINBLOCKS) k_run(DevCtx c, int n,
 // exact waiters look at `fin`.
 #define SM_KX 128            // in-range lower-index neighbours tracked exactly (ids in shared memory)
 #define SM_KXW (SM_KX / 64)
-__device__ __forceinline__ bool plus_hits_3x3(int dx, int dy) {   // plus(c) meets 3x3(c + d)
-  dx = dx < 0 ? -dx : dx; dy = dy < 0 ? -dy : dy;
-  return (dx <= 1 && dy <= 2) || (dx <= 2 && dy <= 1);
-}
-__device__ __forceinline__ bool plus_hits_box3(int dx, int dy) {  // plus(c) meets the box (c + d) +- 3
-  dx = dx < 0 ? -dx : dx; dy = dy < 0 ? -dy : dy;
-  return (dx <= 4 && dy <= 3) || (dx <= 3 && dy <= 4);
-}
-__device__ __forceinline__ int iabs_(int v) { return v < 0 ? -v : v; }
-__device__ __forceinline__ bool plus_hits_5x5(int dx, int dy) {   // plus(c) meets 5x5(c + d)
-  dx = iabs_(dx); dy = iabs_(dy);
-  return (dx <= 3 && dy <= 2) || (dx <= 2 && dy <= 3);
-}
-// Footprints of one step, by kind.  ip = ipos, np = npos (known after move), R = published reach.
-//   water: reads plus(ip) in move; touches {ip} U 3x3(np) in interact        (no nested re-cascade)
-//   wind : reads plus(ip) in move; touches 5x5(ip) U 5x5(np) in interact     (cascade(.,1) + one re-cascade)
-template <int KIND> struct Foot;
-template <> struct Foot<KIND_WATER> {
-  static __device__ __forceinline__ bool in_range(int dx, int dy, int, int) { return iabs_(dx) <= 6 && iabs_(dy) <= 6; }
-  // d* = B - A
-  static __device__ __forceinline__ bool box_hits_M(int dx, int dy, int) { return plus_hits_box3(dx, dy); }
-  static __device__ __forceinline__ bool W_hits_M(int ibx, int iby, int nbx, int nby, int ax, int ay) {
-    return (iabs_(ibx - ax) + iabs_(iby - ay) <= 1) || plus_hits_3x3(nbx - ax, nby - ay);
-  }
-  static __device__ __forceinline__ bool F_hits_F(int ax, int ay, int nax, int nay, int bx, int by, int nbx, int nby) {
-    return (iabs_(bx - ax) + iabs_(by - ay) <= 2) || plus_hits_3x3(nbx - ax, nby - ay) ||
-           plus_hits_3x3(nax - bx, nay - by) || (iabs_(nbx - nax) <= 2 && iabs_(nby - nay) <= 2);
-  }
-  static __device__ __forceinline__ bool box_hits_F(int ax, int ay, int nax, int nay, int bx, int by, int) {
-    return plus_hits_box3(bx - ax, by - ay) || (iabs_(bx - nax) <= 4 && iabs_(by - nay) <= 4);
-  }
-};
-template <> struct Foot<KIND_WIND> {
-  static __device__ __forceinline__ bool in_range(int dx, int dy, int RA, int RB) { return iabs_(dx) <= RA + RB && iabs_(dy) <= RA + RB; }
-  static __device__ __forceinline__ bool box_hits_M(int dx, int dy, int RB) {
-    dx = iabs_(dx); dy = iabs_(dy);
-    return (dx <= RB + 1 && dy <= RB) || (dx <= RB && dy <= RB + 1);
-  }
-  static __device__ __forceinline__ bool W_hits_M(int ibx, int iby, int nbx, int nby, int ax, int ay) {
-    return plus_hits_5x5(ibx - ax, iby - ay) || plus_hits_5x5(nbx - ax, nby - ay);
-  }
-  static __device__ __forceinline__ bool c4(int dx, int dy) { return iabs_(dx) <= 4 && iabs_(dy) <= 4; }
-  static __device__ __forceinline__ bool F_hits_F(int ax, int ay, int nax, int nay, int bx, int by, int nbx, int nby) {
-    return c4(bx - ax, by - ay) || c4(nbx - ax, nby - ay) || c4(bx - nax, by - nay) || c4(nbx - nax, nby - nay);
-  }
-  static __device__ __forceinline__ bool box_hits_F(int ax, int ay, int nax, int nay, int bx, int by, int RB) {
-    return (iabs_(bx - ax) <= RB + 2 && iabs_(by - ay) <= RB + 2) || (iabs_(bx - nax) <= RB + 2 && iabs_(by - nay) <= RB + 2);
-  }
-};
+#include "sm_foot.cuh"
 template <int KIND> struct MidType { typedef WaterMid T; };
 template <> struct MidType<KIND_WIND> { typedef WindMid T; };
 template <class A> __device__ __forceinline__ int do_move(A& a, WaterP& p, WaterMid& m) { return water_move(a, p, m); }

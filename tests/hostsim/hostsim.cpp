@@ -3,6 +3,9 @@
 // CPU test-suite check the type-exact transcription against oracle/_ref bit for bit without a
 // GPU.  It is not shipped, not linked into the product library and is not a CPU fallback.
 #include <array>
+#include <memory>
+#include <cmath>
+#include <cstdlib>
 #include <vector>
 #include <cstring>
 #include <cstdint>
@@ -12,6 +15,7 @@
 #include "../../soilmachine_b200/csrc/sm_hydro.cuh"
 #include "../../soilmachine_b200/csrc/sm_coop.cuh"
 #include "../../soilmachine_b200/csrc/sm_hydro_coop.cuh"
+#include "../../soilmachine_b200/csrc/sm_foot.cuh"
 
 namespace {
 struct HostMap {
@@ -154,6 +158,141 @@ std::vector<WaterP> W; std::vector<int> Wlive;
 std::vector<WindP> D; std::vector<int> Dlive;
 }  // namespace
 
+// ---- mode 3: the exact-footprint schedule run ADVERSARIALLY ---------------------------------------------------
+// The device lets a step run ahead of lower-index steps whenever the rule of sweep_exact (sm_sweep.cuh) allows it; which
+// legal order a GPU run takes depends on timing.  Here one sweep is executed in the legal order that departs most
+// from index order: passes over the live particles from the HIGHEST index down, each particle advancing one phase
+// (move, then interact) whenever the rule lets it, until all are done - with the step split and staged exactly as on
+// the device (a particle's window lives across the two phases while other particles run in between).  The rule is
+// stated on cell sets by brute force, not with the closed-form predicates of Foot<KIND>:
+//   B < A, B not finished, holds A back
+//     before A.move()     while B's (possible) writes can meet plus(ipos_A):
+//                           B not moved: its box ipos_B +- R_B;  B moved: {ipos_B} U 3x3(npos_B) (wind: 5x5 U 5x5)
+//     before A.interact() while B's (possible) footprint can meet A's footprint plus(ipos_A) U 3x3(npos_A)
+//                           (wind: 5x5(ipos_A) U 5x5(npos_A)):  B not moved: its box;  B moved: its footprint.
+// If the golden frames come out bit for bit under this order too, footprints that cannot meet commute - the rule is sound.
+struct CellSet {
+  struct Part { int kind, x, y, r; };        // kind 0: square of half-width r; kind 1: plus
+  Part p[2]; int n = 0;
+  void rect(int x, int y, int r) { p[n++] = Part{0, x, y, r}; }
+  void plus(int x, int y) { p[n++] = Part{1, x, y, 1}; }
+  bool has(int x, int y) const {
+    for (int i = 0; i < n; i++) {
+      const int dx = std::abs(x - p[i].x), dy = std::abs(y - p[i].y);
+      if (p[i].kind == 0 ? (dx <= p[i].r && dy <= p[i].r) : (dx + dy <= 1)) return true;
+    }
+    return false;
+  }
+  bool meets(const CellSet& o) const {
+    for (int i = 0; i < n; i++)
+      for (int x = p[i].x - p[i].r; x <= p[i].x + p[i].r; x++)
+        for (int y = p[i].y - p[i].r; y <= p[i].y + p[i].r; y++)
+          if ((p[i].kind == 0 || std::abs(x - p[i].x) + std::abs(y - p[i].y) <= 1) && o.has(x, y)) return true;
+    return false;
+  }
+};
+struct Fly { int id, phase, ix, iy, nx, ny, R; };     // phase 0 not moved, 1 moved, 2 finished
+inline int host_reach(const WaterP&) { return 3; }
+inline int host_reach(const WindP& p) {                // particle_reach, sm_engine.cu
+  const float len = sqrtf(p.sx * p.sx + p.sy * p.sy + p.sz * p.sz);
+  int r = (int)floorf(1.0f + 0.8f * len + 0.4f + 0.01f);
+  r = r < 1 ? 1 : (r > 3 ? 3 : r);
+  return r + 2;
+}
+template <int KIND> CellSet set_box(const Fly& f) { CellSet s; s.rect(f.ix, f.iy, f.R); return s; }
+template <int KIND> CellSet set_M(const Fly& f) { CellSet s; s.plus(f.ix, f.iy); return s; }
+template <int KIND> CellSet set_W(const Fly& f) {      // writes of a moved step
+  CellSet s;
+  if (KIND == 0) { s.rect(f.ix, f.iy, 0); s.rect(f.nx, f.ny, 1); } else { s.rect(f.ix, f.iy, 2); s.rect(f.nx, f.ny, 2); }
+  return s;
+}
+template <int KIND> CellSet set_F(const Fly& f) {      // everything a moved step touches
+  CellSet s;
+  if (KIND == 0) { s.plus(f.ix, f.iy); s.rect(f.nx, f.ny, 1); } else { s.rect(f.ix, f.iy, 2); s.rect(f.nx, f.ny, 2); }
+  return s;
+}
+long long G_adv_ahead = 0;      // phases executed while a lower-index particle of the sweep was still unfinished
+int G_adv_weak = 0;             // negative control: 1 = footprints shrunk by one ring (the test must then FAIL)
+inline int adv_move(WarpHost& w, CoopWin<HostBack>& a, WaterP& p, WaterMidCoop& m) { return water_move_coop(w, a, p, m, SM_CW_PLUS); }
+inline int adv_move(WarpHost& w, CoopWin<HostBack>& a, WindP& p, WindMidCoop& m) { return wind_move_coop(w, a, p, m, SM_CW_PLUS); }
+inline int adv_interact(WarpHost& w, CoopWin<HostBack>& a, WaterP& p, const WaterMidCoop& m) { return water_interact_coop(w, a, p, m); }
+inline int adv_interact(WarpHost& w, CoopWin<HostBack>& a, WindP& p, const WindMidCoop& m) { return wind_interact_coop(w, a, p, m); }
+// runs one sweep; res[k] = result of live[k]'s step
+template <int KIND, class P, class MID>
+void sweep_adversarial(std::vector<P>& parts, const std::vector<int>& live, std::vector<int>& res) {
+  const size_t n = live.size();
+  std::vector<Fly> fly(n);
+  std::vector<HostBack> backs(n);
+  std::vector<CoopScratch> scr(n);
+  std::vector<MID> mids(n);
+  std::vector<std::unique_ptr<CoopWin<HostBack> > > wins(n);
+  WarpHost w;
+  for (size_t k = 0; k < n; k++) {
+    const P& p = parts[live[k]];
+    fly[k] = Fly{live[k], 0, (int)roundf(p.px), (int)roundf(p.py), 0, 0, host_reach(p)};
+    wins[k].reset(new CoopWin<HostBack>(backs[k], &scr[k]));
+  }
+  res.assign(n, SM_ALIVE);
+  size_t left = n;
+  for (int pass = 0; left > 0; pass++) {
+    if (pass > 100000) { fprintf(stderr, "sweep_adversarial: no progress\n"); abort(); }
+    for (size_t kk = n; kk-- > 0;) {          // highest index first (live[] is ascending)
+      Fly& A = fly[kk];
+      if (A.phase == 2) continue;
+      bool ok = true, lower_open = false;
+      const CellSet mine = A.phase == 0 ? set_M<KIND>(A) : set_F<KIND>(A);
+      for (size_t j = 0; j < kk && ok; j++) {
+        const Fly& B = fly[j];
+        if (B.phase == 2) continue;
+        lower_open = true;
+        if (std::abs(B.ix - A.ix) > 16 || std::abs(B.iy - A.iy) > 16) continue;
+        CellSet theirs = B.phase == 0 ? set_box<KIND>(B) : (A.phase == 0 ? set_W<KIND>(B) : set_F<KIND>(B));
+        if (G_adv_weak)
+          for (int q = 0; q < theirs.n; q++) if (theirs.p[q].kind == 0 && theirs.p[q].r > 0) theirs.p[q].r--;
+        if (theirs.meets(mine)) ok = false;
+      }
+      if (!ok) continue;
+      if (lower_open) G_adv_ahead++;
+      P& p = parts[A.id];
+      if (A.phase == 0) {
+        const int r = adv_move(w, *wins[kk], p, mids[kk]);
+        if (r == SM_ALIVE) { A.nx = (int)roundf(p.px); A.ny = (int)roundf(p.py); A.phase = 1; }
+        else { wins[kk]->flush(w); res[kk] = r; A.phase = 2; left--; }
+      } else {
+        res[kk] = adv_interact(w, *wins[kk], p, mids[kk]);
+        wins[kk]->flush(w);
+        A.phase = 2; left--;
+      }
+    }
+  }
+}
+
+// The closed-form predicates the device schedules use (sm_foot.cuh) against the explicit cell sets, exhaustively over
+// every relative position that can occur (|B - A| up to 12, |npos - ipos| up to 2 water / 3 wind, reach 3..5).
+// out[2 * k] = cases where the sets meet but predicate k says no (UNSOUND), out[2 * k + 1] = predicate yes but the sets
+// do not meet (merely conservative); k = box_hits_M, W_hits_M, F_hits_F, box_hits_F for water, then the same for wind.
+template <int KIND> void foot_exhaustive(long long* out) {
+  const int S = KIND == 0 ? 2 : 3, half = KIND == 0 ? 1 : 2;
+  auto tally = [&](int k, bool pred, bool truth) { if (truth && !pred) out[2 * k]++; if (pred && !truth) out[2 * k + 1]++; };
+  for (int RB = 3; RB <= (KIND == 0 ? 3 : 5); RB++)
+  for (int bx = -12; bx <= 12; bx++) for (int by = -12; by <= 12; by++) {
+    const Fly A0{0, 0, 0, 0, 0, 0, 0}, B0{1, 0, bx, by, 0, 0, RB};
+    tally(0, Foot<KIND>::box_hits_M(bx, by, RB), set_box<KIND>(B0).meets(set_M<KIND>(A0)));
+    for (int mx = -S; mx <= S; mx++) for (int my = -S; my <= S; my++) {
+      Fly B1 = B0; B1.nx = bx + mx; B1.ny = by + my;
+      tally(1, Foot<KIND>::W_hits_M(bx, by, B1.nx, B1.ny, 0, 0), set_W<KIND>(B1).meets(set_M<KIND>(A0)));
+      Fly A1 = A0; A1.nx = mx; A1.ny = my;      // (reuse the offsets for A's own move)
+      tally(3, Foot<KIND>::box_hits_F(0, 0, A1.nx, A1.ny, bx, by, RB), set_box<KIND>(B0).meets(set_F<KIND>(A1)));
+      if (RB == 3)
+        for (int ax = -S; ax <= S; ax++) for (int ay = -S; ay <= S; ay++) {
+          Fly A2 = A0; A2.nx = ax; A2.ny = ay;
+          tally(2, Foot<KIND>::F_hits_F(0, 0, ax, ay, bx, by, B1.nx, B1.ny), set_F<KIND>(B1).meets(set_F<KIND>(A2)));
+        }
+    }
+  }
+  (void)half;
+}
+
 extern "C" {
 void hs_init(int dimx, int dimy, int scale, int nsoils, const SoilDev* soils) {
   M = HostMap();
@@ -222,6 +361,13 @@ void hs_cascade(float x, float y, int loop) { HostAccess a; Cascade<3, HostAcces
 void hs_set_mode(int coop, int lane_order) { G_coop = coop; G_lane_order = lane_order; }
 // footprint audit of the steps run in mode 2 since the last call: steps, accesses outside plus(ipos) during move(),
 // outside the footprint during interact(), write-backs outside the write set, largest |npos - ipos|
+void hs_check_foot_predicates(long long* out16) {
+  for (int i = 0; i < 16; i++) out16[i] = 0;
+  foot_exhaustive<0>(out16);
+  foot_exhaustive<1>(out16 + 8);
+}
+void hs_adversarial_weaken(int on) { G_adv_weak = on; }
+long long hs_adversarial_ahead(void) { const long long v = G_adv_ahead; G_adv_ahead = 0; return v; }
 void hs_footprint_audit(long long* out5) {
   out5[0] = G_foot.steps; out5[1] = G_foot.viol[0]; out5[2] = G_foot.viol[1]; out5[3] = G_foot.viol[2]; out5[4] = G_foot.max_step;
   G_foot = FootAudit();
@@ -244,8 +390,13 @@ void hs_water_begin(int n, const float* xy) {
 }
 int hs_water_sweep(Stats* st) {
   HostAccess a; std::vector<int> next;
+  std::vector<int> adv;
+  if (G_coop == 3) sweep_adversarial<0, WaterP, WaterMidCoop>(W, Wlive, adv);
+  size_t kpos = 0;
   for (int i : Wlive) {
     int r;
+    if (G_coop == 3) r = adv[kpos++];
+    else
     if (G_coop) {
       WarpHost w; HostBack b; CoopScratch sc; CoopWin<HostBack> cw(b, &sc);
       if (G_coop == 2) {        // staged and split as the exact-footprint schedule does (sweep_exact), with the audit
@@ -293,8 +444,13 @@ void hs_wind_begin(int n, const float* xy) {
 }
 int hs_wind_sweep(Stats* st) {
   HostAccess a; std::vector<int> next;
+  std::vector<int> adv;
+  if (G_coop == 3) sweep_adversarial<1, WindP, WindMidCoop>(D, Dlive, adv);
+  size_t kpos = 0;
   for (int i : Dlive) {
     int r;
+    if (G_coop == 3) r = adv[kpos++];
+    else
     if (G_coop) {
       WarpHost w; HostBack b; CoopScratch sc; CoopWin<HostBack> cw(b, &sc);
       if (G_coop == 2) {

@@ -79,6 +79,61 @@ def test_warp_cooperative_step_with_late_corner_staging(case):
 
 
 @pytest.mark.parametrize("case", _golden.FRAME_CASES)
+def test_exact_schedule_is_sound_under_the_most_out_of_order_legal_execution(case):
+    """Which legal order a GPU run of the exact-footprint schedule takes depends on timing.  tests/hostsim mode 3 runs
+    every sweep of the golden frames in the legal order that departs MOST from index order - highest index first, each
+    particle advancing a phase (move / interact) as soon as no unfinished lower-index particle's (possible) writes or
+    footprint can meet what the phase touches, its staged window living across the two phases while others run in
+    between - and must still reproduce the reference byte for byte.  The rule is evaluated on explicit cell sets."""
+    g = _golden.load(case)
+    b = Backend(g)
+    b.hs.lib.hs_adversarial_ahead.restype = __import__("ctypes").c_longlong
+    b.hs.lib.hs_set_mode(3, 0)
+    try:
+        b.hs.lib.hs_adversarial_ahead()
+        b.hs.set_columns(_golden.cols(g, "init"))
+        _golden.replay_frame(g, b, stats5)
+        ahead = b.hs.lib.hs_adversarial_ahead()
+    finally:
+        b.hs.lib.hs_set_mode(0, 0)
+    assert ahead > 1000        # the order really was far from index order
+
+
+def test_footprint_predicates_equal_the_cell_sets():
+    """sm_foot.cuh (the closed forms sweep_exact / k_run_exact evaluate on the device) against explicit cell sets, over
+    every relative position that can occur: never "no" when the sets meet (sound), and - except where a predicate is
+    documented as a bound - never "yes" when they do not (exact)."""
+    import ctypes as C
+    from _hostsim import HostSim
+    hs = HostSim()
+    out = (C.c_longlong * 16)()
+    hs.lib.hs_check_foot_predicates(out)
+    v = list(out)
+    names = ["box_hits_M", "W_hits_M", "F_hits_F", "box_hits_F"]
+    for kind in (0, 1):
+        for k, nm in enumerate(names):
+            unsound, loose = v[8 * kind + 2 * k], v[8 * kind + 2 * k + 1]
+            assert unsound == 0, ("water" if kind == 0 else "wind", nm, unsound)
+            assert loose == 0, ("water" if kind == 0 else "wind", nm, "conservative in", loose, "cases")
+
+
+def test_out_of_order_execution_with_too_small_footprints_is_caught():
+    """negative control of the test above: with every square of the other particle's sets shrunk by one ring the same
+    adversarial order must NOT reproduce the reference - i.e. the test can see an unsound rule."""
+    g = _golden.load("frame_rocksand_56")
+    b = Backend(g)
+    b.hs.lib.hs_set_mode(3, 0)
+    b.hs.lib.hs_adversarial_weaken(1)
+    try:
+        b.hs.set_columns(_golden.cols(g, "init"))
+        with pytest.raises(AssertionError):
+            _golden.replay_frame(g, b, stats5)
+    finally:
+        b.hs.lib.hs_adversarial_weaken(0)
+        b.hs.lib.hs_set_mode(0, 0)
+
+
+@pytest.mark.parametrize("case", _golden.FRAME_CASES)
 def test_exact_footprints_contain_every_access_of_a_step(case):
     """The exact-footprint schedule (sweep_exact, Foot<KIND> in sm_engine.cu) lets two steps overlap unless their
     footprints can meet: move() reads plus(ipos); a water step touches plus(ipos) U 3x3(npos) and writes
