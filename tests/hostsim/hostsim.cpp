@@ -90,7 +90,7 @@ struct FootAudit {
   bool on = false;
   int phase = 0;                                  // 0 move(), 1 interact(), 2 write-back
   std::vector<std::array<int, 3> > acc;           // x, y, phase
-  long long steps = 0, viol[3] = {0, 0, 0};       // accesses outside M / F / the write set
+  long long steps = 0, viol[4] = {0, 0, 0, 0};    // accesses outside M / F / the write set / the published box
   long long max_step = 0;                         // largest |npos - ipos|_inf seen
 };
 FootAudit G_foot;
@@ -128,7 +128,7 @@ std::vector<double> BUD;   // coop mode: 6 mass-budget accumulators per particle
 struct Stats { int64_t steps, sweeps, exit_oob, exit_evap, exit_stall; double seconds; };
 // kind 0 water: move() reads plus(ipos); the step touches plus(ipos) U 3x3(npos) and writes {ipos} U 3x3(npos).
 // kind 1 wind : move() reads plus(ipos); the step touches and writes 5x5(ipos) U 5x5(npos).   (Foot<KIND>)
-void foot_check(int kind, int ix, int iy, bool moved, int nx, int ny) {
+void foot_check(int kind, int ix, int iy, bool moved, int nx, int ny, int R) {
   auto ab = [](int v) { return v < 0 ? -v : v; };
   G_foot.steps++;
   if (moved) {
@@ -148,6 +148,7 @@ void foot_check(int kind, int ix, int iy, bool moved, int nx, int ny) {
       inF = (dxi <= 2 && dyi <= 2) || (dxn <= 2 && dyn <= 2);
       inW = inF;
     }
+    if (dxi > R || dyi > R) G_foot.viol[3]++;
     if (a[2] == 0 && !plus) G_foot.viol[0]++;
     if (a[2] == 1 && !inF) G_foot.viol[1]++;
     if (a[2] == 2 && !inW) G_foot.viol[2]++;
@@ -368,8 +369,9 @@ void hs_check_foot_predicates(long long* out16) {
 }
 void hs_adversarial_weaken(int on) { G_adv_weak = on; }
 long long hs_adversarial_ahead(void) { const long long v = G_adv_ahead; G_adv_ahead = 0; return v; }
-void hs_footprint_audit(long long* out5) {
-  out5[0] = G_foot.steps; out5[1] = G_foot.viol[0]; out5[2] = G_foot.viol[1]; out5[3] = G_foot.viol[2]; out5[4] = G_foot.max_step;
+void hs_footprint_audit(long long* out6) {
+  out6[0] = G_foot.steps; out6[1] = G_foot.viol[0]; out6[2] = G_foot.viol[1]; out6[3] = G_foot.viol[2]; out6[4] = G_foot.max_step;
+  out6[5] = G_foot.viol[3];
   G_foot = FootAudit();
 }
 void hs_set_volume_factor(double v) { M.volume_factor = v; }
@@ -400,7 +402,7 @@ int hs_water_sweep(Stats* st) {
     if (G_coop) {
       WarpHost w; HostBack b; CoopScratch sc; CoopWin<HostBack> cw(b, &sc);
       if (G_coop == 2) {        // staged and split as the exact-footprint schedule does (sweep_exact), with the audit
-        const int ix = (int)roundf(W[i].px), iy = (int)roundf(W[i].py);
+        const int ix = (int)roundf(W[i].px), iy = (int)roundf(W[i].py), R = host_reach(W[i]);
         WaterMidCoop mid;
         G_foot.on = true; G_foot.phase = 0;
         r = water_move_coop(w, cw, W[i], mid, SM_CW_PLUS);
@@ -411,7 +413,7 @@ int hs_water_sweep(Stats* st) {
         G_foot.phase = 2;
         cw.flush(w);
         G_foot.on = false;
-        foot_check(0, ix, iy, moved, nx, ny);
+        foot_check(0, ix, iy, moved, nx, ny, R);
       } else {
         r = water_step_coop(w, cw, W[i]);
         cw.flush(w);
@@ -454,7 +456,7 @@ int hs_wind_sweep(Stats* st) {
     if (G_coop) {
       WarpHost w; HostBack b; CoopScratch sc; CoopWin<HostBack> cw(b, &sc);
       if (G_coop == 2) {
-        const int ix = (int)roundf(D[i].px), iy = (int)roundf(D[i].py);
+        const int ix = (int)roundf(D[i].px), iy = (int)roundf(D[i].py), R = host_reach(D[i]);
         WindMidCoop mid;
         G_foot.on = true; G_foot.phase = 0;
         r = wind_move_coop(w, cw, D[i], mid, SM_CW_PLUS);
@@ -465,7 +467,7 @@ int hs_wind_sweep(Stats* st) {
         G_foot.phase = 2;
         cw.flush(w);
         G_foot.on = false;
-        foot_check(1, ix, iy, moved, nx, ny);
+        foot_check(1, ix, iy, moved, nx, ny, R);
       } else {
         r = wind_step_coop(w, cw, D[i]);
         cw.flush(w);

@@ -144,7 +144,7 @@ def test_exact_footprints_contain_every_access_of_a_step(case):
     import ctypes as C
     g = _golden.load(case)
     b = Backend(g)
-    out = (C.c_longlong * 5)()
+    out = (C.c_longlong * 6)()
     b.hs.lib.hs_set_mode(2, 0)
     try:
         b.hs.lib.hs_footprint_audit(out)          # reset
@@ -153,9 +153,10 @@ def test_exact_footprints_contain_every_access_of_a_step(case):
         b.hs.lib.hs_footprint_audit(out)
     finally:
         b.hs.lib.hs_set_mode(0, 0)
-    steps, in_move, in_interact, in_writeback, max_step = list(out)
+    steps, in_move, in_interact, in_writeback, max_step, out_of_box = list(out)
     assert steps > 1000
     assert (in_move, in_interact, in_writeback) == (0, 0, 0)
+    assert out_of_box == 0      # the box ipos +- R a particle publishes in its bin (particle_reach) holds the whole step
     assert max_step <= 3
 
 
